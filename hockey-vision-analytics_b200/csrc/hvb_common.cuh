@@ -1,0 +1,78 @@
+// Internal helpers shared by the libhvb translation units (not part of the C ABI).
+#pragma once
+
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <stdarg.h>
+#include <string>
+#include <vector>
+
+#include "hvb.h"
+
+struct hvb_ctx {
+    int device = 0;
+    int sm_count = 148;
+    int max_smem_optin = 0;
+    cudaStream_t own_stream = nullptr;
+    cudaStream_t stream = nullptr;
+    cudaEvent_t ev_start = nullptr, ev_stop = nullptr;
+    uint64_t launches = 0;
+    // colour tables (uploaded once): sdiv int32[256], hdiv int32[256], gtab u16[256], ctab u16[3072]
+    void* tables_dev = nullptr;
+    // growable scratch used by the *_host entry points and by multi-kernel ops
+    void* scratch_dev = nullptr;
+    size_t scratch_bytes = 0;
+    void* scratch2_dev = nullptr;
+    size_t scratch2_bytes = 0;
+    void* scratch3_dev = nullptr;
+    size_t scratch3_bytes = 0;
+    void* pinned = nullptr;
+    size_t pinned_bytes = 0;
+};
+
+void hvb_set_error(const char* fmt, ...);
+int hvb_cuda_fail(cudaError_t e, const char* what, const char* file, int line);
+int hvb_scratch(hvb_ctx* ctx, size_t bytes, void** out);     // device scratch #1 (grow-only)
+int hvb_scratch2(hvb_ctx* ctx, size_t bytes, void** out);    // device scratch #2 (grow-only)
+int hvb_scratch3(hvb_ctx* ctx, size_t bytes, void** out);    // device scratch #3 (grow-only)
+int hvb_pinned(hvb_ctx* ctx, size_t bytes, void** out);      // pinned host staging (grow-only)
+
+#define HVB_CUDA(call)                                                            \
+    do {                                                                          \
+        cudaError_t e__ = (call);                                                 \
+        if (e__ != cudaSuccess) return hvb_cuda_fail(e__, #call, __FILE__, __LINE__); \
+    } while (0)
+
+#define HVB_CHECK_CTX(ctx)                                          \
+    do {                                                            \
+        if (!(ctx)) { hvb_set_error("null context"); return HVB_ERR_ARG; } \
+        HVB_CUDA(cudaSetDevice((ctx)->device));                     \
+    } while (0)
+
+#define HVB_ARG(cond, msg)                                  \
+    do {                                                    \
+        if (!(cond)) { hvb_set_error("%s: %s", __func__, msg); return HVB_ERR_ARG; } \
+    } while (0)
+
+#define HVB_TRY(expr)                       \
+    do {                                    \
+        int s__ = (expr);                   \
+        if (s__ != HVB_OK) return s__;      \
+    } while (0)
+
+// Call after every kernel launch: counts it and surfaces launch-configuration errors.
+#define HVB_LAUNCHED(ctx)                   \
+    do {                                    \
+        (ctx)->launches++;                  \
+        HVB_CUDA(cudaGetLastError());       \
+    } while (0)
+
+static inline int hvb_div_up(int64_t a, int64_t b) { return (int)((a + b - 1) / b); }
+
+// Byte offsets of the colour tables inside ctx->tables_dev
+constexpr int HVB_TAB_SDIV = 0;                    // int32[256]
+constexpr int HVB_TAB_HDIV = 1024;                 // int32[256]
+constexpr int HVB_TAB_GTAB = 2048;                 // uint16[256]
+constexpr int HVB_TAB_CTAB = 2560;                 // uint16[3072]
+constexpr int HVB_TAB_BYTES = 2560 + 6144;         // 8704

@@ -1,0 +1,224 @@
+// Context, error reporting and memory plumbing of libhvb (C ABI in include/hvb.h).
+#include "hvb_common.cuh"
+
+#include <math.h>
+#include <string.h>
+
+#include "hvb_tables.inc"
+
+static thread_local char g_err[1024] = "";
+
+void hvb_set_error(const char* fmt, ...) {
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof(g_err), fmt, ap);
+    va_end(ap);
+}
+
+int hvb_cuda_fail(cudaError_t e, const char* what, const char* file, int line) {
+    hvb_set_error("CUDA error %d (%s) at %s:%d in `%s`", (int)e, cudaGetErrorString(e), file, line, what);
+    return (e == cudaErrorNoDevice || e == cudaErrorInsufficientDriver) ? HVB_ERR_NO_DEVICE : HVB_ERR_CUDA;
+}
+
+static int grow(void** buf, size_t* have, size_t want, bool pinned) {
+    if (*have >= want && *buf) return HVB_OK;
+    size_t n = want + want / 4 + 4096;
+    if (*buf) {
+        HVB_CUDA(cudaDeviceSynchronize());
+        if (pinned) HVB_CUDA(cudaFreeHost(*buf)); else HVB_CUDA(cudaFree(*buf));
+        *buf = nullptr;
+        *have = 0;
+    }
+    if (pinned) HVB_CUDA(cudaMallocHost(buf, n)); else HVB_CUDA(cudaMalloc(buf, n));
+    *have = n;
+    return HVB_OK;
+}
+
+int hvb_scratch(hvb_ctx* ctx, size_t bytes, void** out) {
+    HVB_TRY(grow(&ctx->scratch_dev, &ctx->scratch_bytes, bytes, false));
+    *out = ctx->scratch_dev;
+    return HVB_OK;
+}
+int hvb_scratch2(hvb_ctx* ctx, size_t bytes, void** out) {
+    HVB_TRY(grow(&ctx->scratch2_dev, &ctx->scratch2_bytes, bytes, false));
+    *out = ctx->scratch2_dev;
+    return HVB_OK;
+}
+int hvb_scratch3(hvb_ctx* ctx, size_t bytes, void** out) {
+    HVB_TRY(grow(&ctx->scratch3_dev, &ctx->scratch3_bytes, bytes, false));
+    *out = ctx->scratch3_dev;
+    return HVB_OK;
+}
+int hvb_pinned(hvb_ctx* ctx, size_t bytes, void** out) {
+    HVB_TRY(grow(&ctx->pinned, &ctx->pinned_bytes, bytes, true));
+    *out = ctx->pinned;
+    return HVB_OK;
+}
+
+extern "C" {
+
+int hvb_version(void) { return HVB_VERSION; }
+
+const char* hvb_last_error(void) { return g_err; }
+
+int hvb_device_count(int* out_count) {
+    if (!out_count) { hvb_set_error("null out_count"); return HVB_ERR_ARG; }
+    int n = 0;
+    cudaError_t e = cudaGetDeviceCount(&n);
+    if (e != cudaSuccess) { (void)cudaGetLastError(); n = 0; }
+    *out_count = n;
+    return HVB_OK;
+}
+
+int hvb_ctx_create(int device, hvb_ctx** out_ctx) {
+    if (!out_ctx) { hvb_set_error("null out_ctx"); return HVB_ERR_ARG; }
+    *out_ctx = nullptr;
+    int n = 0;
+    cudaError_t e = cudaGetDeviceCount(&n);
+    if (e != cudaSuccess || n == 0) {
+        (void)cudaGetLastError();
+        hvb_set_error("no CUDA device available (%s); libhvb has no CPU fallback",
+                      e != cudaSuccess ? cudaGetErrorString(e) : "device count 0");
+        return HVB_ERR_NO_DEVICE;
+    }
+    if (device < 0 || device >= n) { hvb_set_error("device %d out of range [0,%d)", device, n); return HVB_ERR_ARG; }
+    HVB_CUDA(cudaSetDevice(device));
+    cudaDeviceProp prop;
+    HVB_CUDA(cudaGetDeviceProperties(&prop, device));
+    if (prop.major != 10) {
+        hvb_set_error("device %d is sm_%d%d; libhvb is built for sm_100a only", device, prop.major, prop.minor);
+        return HVB_ERR_NO_DEVICE;
+    }
+    hvb_ctx* c = new hvb_ctx();
+    c->device = device;
+    c->sm_count = prop.multiProcessorCount;
+    c->max_smem_optin = (int)prop.sharedMemPerBlockOptin;
+    HVB_CUDA(cudaStreamCreateWithFlags(&c->own_stream, cudaStreamNonBlocking));
+    c->stream = c->own_stream;
+    HVB_CUDA(cudaEventCreate(&c->ev_start));
+    HVB_CUDA(cudaEventCreate(&c->ev_stop));
+
+    // colour tables: HSV division tables (exact in double) + the generated LAB tables
+    std::vector<unsigned char> tab(HVB_TAB_BYTES);
+    int32_t* sdiv = (int32_t*)(tab.data() + HVB_TAB_SDIV);
+    int32_t* hdiv = (int32_t*)(tab.data() + HVB_TAB_HDIV);
+    sdiv[0] = hdiv[0] = 0;
+    for (int i = 1; i < 256; i++) {
+        sdiv[i] = (int32_t)nearbyint((double)(255 << 12) / (double)i);
+        hdiv[i] = (int32_t)nearbyint((double)(180 << 12) / (6.0 * (double)i));
+    }
+    memcpy(tab.data() + HVB_TAB_GTAB, kHvbLabGammaTab, sizeof(kHvbLabGammaTab));
+    memcpy(tab.data() + HVB_TAB_CTAB, kHvbLabCbrtTab, sizeof(kHvbLabCbrtTab));
+    HVB_CUDA(cudaMalloc(&c->tables_dev, HVB_TAB_BYTES));
+    HVB_CUDA(cudaMemcpy(c->tables_dev, tab.data(), HVB_TAB_BYTES, cudaMemcpyHostToDevice));
+    *out_ctx = c;
+    return HVB_OK;
+}
+
+int hvb_ctx_destroy(hvb_ctx* ctx) {
+    if (!ctx) return HVB_OK;
+    cudaSetDevice(ctx->device);
+    cudaDeviceSynchronize();
+    if (ctx->tables_dev) cudaFree(ctx->tables_dev);
+    if (ctx->scratch_dev) cudaFree(ctx->scratch_dev);
+    if (ctx->scratch2_dev) cudaFree(ctx->scratch2_dev);
+    if (ctx->scratch3_dev) cudaFree(ctx->scratch3_dev);
+    if (ctx->pinned) cudaFreeHost(ctx->pinned);
+    if (ctx->ev_start) cudaEventDestroy(ctx->ev_start);
+    if (ctx->ev_stop) cudaEventDestroy(ctx->ev_stop);
+    if (ctx->own_stream) cudaStreamDestroy(ctx->own_stream);
+    delete ctx;
+    return HVB_OK;
+}
+
+int hvb_ctx_set_stream(hvb_ctx* ctx, void* cuda_stream) {
+    if (!ctx) { hvb_set_error("null context"); return HVB_ERR_ARG; }
+    ctx->stream = cuda_stream ? (cudaStream_t)cuda_stream : ctx->own_stream;
+    return HVB_OK;
+}
+
+int hvb_ctx_get_stream(hvb_ctx* ctx, void** out_stream) {
+    if (!ctx || !out_stream) { hvb_set_error("null argument"); return HVB_ERR_ARG; }
+    *out_stream = (void*)ctx->stream;
+    return HVB_OK;
+}
+
+int hvb_ctx_synchronize(hvb_ctx* ctx) {
+    HVB_CHECK_CTX(ctx);
+    HVB_CUDA(cudaStreamSynchronize(ctx->stream));
+    return HVB_OK;
+}
+
+int hvb_ctx_sm_count(hvb_ctx* ctx, int* out_sms) {
+    if (!ctx || !out_sms) { hvb_set_error("null argument"); return HVB_ERR_ARG; }
+    *out_sms = ctx->sm_count;
+    return HVB_OK;
+}
+
+int hvb_malloc(hvb_ctx* ctx, size_t bytes, void** out_dev) {
+    HVB_CHECK_CTX(ctx);
+    HVB_ARG(out_dev != nullptr, "null out_dev");
+    HVB_CUDA(cudaMalloc(out_dev, bytes ? bytes : 1));
+    return HVB_OK;
+}
+
+int hvb_free(hvb_ctx* ctx, void* ptr_dev) {
+    HVB_CHECK_CTX(ctx);
+    if (ptr_dev) HVB_CUDA(cudaFree(ptr_dev));
+    return HVB_OK;
+}
+
+int hvb_host_alloc(hvb_ctx* ctx, size_t bytes, void** out_host) {
+    HVB_CHECK_CTX(ctx);
+    HVB_ARG(out_host != nullptr, "null out_host");
+    HVB_CUDA(cudaMallocHost(out_host, bytes ? bytes : 1));
+    return HVB_OK;
+}
+
+int hvb_host_free(hvb_ctx* ctx, void* ptr_host) {
+    HVB_CHECK_CTX(ctx);
+    if (ptr_host) HVB_CUDA(cudaFreeHost(ptr_host));
+    return HVB_OK;
+}
+
+int hvb_memcpy_h2d(hvb_ctx* ctx, void* dst_dev, const void* src_host, size_t bytes) {
+    HVB_CHECK_CTX(ctx);
+    if (bytes) HVB_CUDA(cudaMemcpyAsync(dst_dev, src_host, bytes, cudaMemcpyHostToDevice, ctx->stream));
+    return HVB_OK;
+}
+
+int hvb_memcpy_d2h(hvb_ctx* ctx, void* dst_host, const void* src_dev, size_t bytes) {
+    HVB_CHECK_CTX(ctx);
+    if (bytes) HVB_CUDA(cudaMemcpyAsync(dst_host, src_dev, bytes, cudaMemcpyDeviceToHost, ctx->stream));
+    return HVB_OK;
+}
+
+int hvb_memset(hvb_ctx* ctx, void* dst_dev, int value, size_t bytes) {
+    HVB_CHECK_CTX(ctx);
+    if (bytes) HVB_CUDA(cudaMemsetAsync(dst_dev, value, bytes, ctx->stream));
+    return HVB_OK;
+}
+
+int hvb_ctx_launch_count(hvb_ctx* ctx, int reset, uint64_t* out_launches) {
+    if (!ctx) { hvb_set_error("null context"); return HVB_ERR_ARG; }
+    if (out_launches) *out_launches = ctx->launches;
+    if (reset) ctx->launches = 0;
+    return HVB_OK;
+}
+
+int hvb_timer_start(hvb_ctx* ctx) {
+    HVB_CHECK_CTX(ctx);
+    HVB_CUDA(cudaEventRecord(ctx->ev_start, ctx->stream));
+    return HVB_OK;
+}
+
+int hvb_timer_stop_ms(hvb_ctx* ctx, float* out_ms) {
+    HVB_CHECK_CTX(ctx);
+    HVB_ARG(out_ms != nullptr, "null out_ms");
+    HVB_CUDA(cudaEventRecord(ctx->ev_stop, ctx->stream));
+    HVB_CUDA(cudaEventSynchronize(ctx->ev_stop));
+    HVB_CUDA(cudaEventElapsedTime(out_ms, ctx->ev_start, ctx->ev_stop));
+    return HVB_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,240 @@
+// K3b — MobileNetV3 crop preprocessing: self.preprocess of hockey/common/team_hybrid.py:31-36
+// (ToPILImage -> Resize((128,64)) -> ToTensor -> Normalize) applied to the jersey ROI of every
+// crop (team_hybrid.py:49-64, 73-77), batched into one float32[n,3,128,64] tensor.
+//
+// The resize is Pillow's ImagingResample with the bilinear (triangle) filter, reproduced bit-exactly
+// (SURVEY.md App. A4): per-axis coefficients computed in float64 exactly like precompute_coeffs,
+// normalised, converted to 22-bit fixed point, horizontal pass to a uint8 intermediate, then the
+// vertical pass (order swapped when in_h > 100*in_w, as the installed Pillow does).  ToTensor is a
+// true float32 /255 and Normalize a true (x-mean)/std (IEEE division); the BGR crop goes through
+// the RGB statistics unswapped, like the reference.
+//
+// One CTA per crop (persistent loop).  Coefficients and the uint8 intermediate live in shared
+// memory; tall ROIs are processed in output-row blocks so that the intermediate window always fits.
+#include "hvb_common.cuh"
+#include "hvb_roi.cuh"
+
+namespace {
+
+constexpr int kThreads = 256;
+constexpr int kOutW = 64, kOutH = 128;
+constexpr int kKMax = 48;               // max taps per output sample (ROI up to ~1400 x 2900 px)
+constexpr int kInterRows = 256;         // rows of the uint8 intermediate held in shared memory
+constexpr int kPrecision = 22;
+
+struct Smem {
+    int bh[kOutW][2];                   // horizontal bounds: xmin, n
+    int bv[kOutH][2];
+    int kh[kOutW * kKMax];
+    int kv[kOutH * kKMax];
+    uint8_t inter[kInterRows * kOutW * 3];
+    int blk[4];
+};
+
+// Pillow precompute_coeffs + normalize_coeffs_8bpc for output sample `o` (bilinear, support 1).
+__device__ void pil_coeffs(int in_size, int out_size, int o, int ksize, int* bounds, int* kk) {
+    const double scale = __ddiv_rn((double)in_size, (double)out_size);
+    const double filterscale = scale < 1.0 ? 1.0 : scale;
+    const double support = filterscale;         // 1.0 * filterscale
+    const double ss = __ddiv_rn(1.0, filterscale);
+    const double center = __dmul_rn(__dadd_rn((double)o, 0.5), scale);
+    int xmin = (int)__dadd_rn(__dsub_rn(center, support), 0.5);
+    if (xmin < 0) xmin = 0;
+    int xmax = (int)__dadd_rn(__dadd_rn(center, support), 0.5);
+    if (xmax > in_size) xmax = in_size;
+    const int n = xmax - xmin;
+    double ww = 0.0;
+    for (int x = 0; x < n; x++) {
+        double t = __dmul_rn(__dadd_rn(__dsub_rn((double)(x + xmin), center), 0.5), ss);
+        if (t < 0.0) t = -t;
+        double w = t < 1.0 ? __dsub_rn(1.0, t) : 0.0;
+        ww = __dadd_rn(ww, w);
+    }
+    for (int x = 0; x < n; x++) {
+        double t = __dmul_rn(__dadd_rn(__dsub_rn((double)(x + xmin), center), 0.5), ss);
+        if (t < 0.0) t = -t;
+        double w = t < 1.0 ? __dsub_rn(1.0, t) : 0.0;
+        if (ww != 0.0) w = __ddiv_rn(w, ww);
+        kk[o * ksize + x] = (int)__dadd_rn(0.5, __dmul_rn(w, (double)(1 << kPrecision)));
+    }
+    for (int x = n; x < ksize; x++) kk[o * ksize + x] = 0;
+    bounds[0] = xmin;
+    bounds[1] = n;
+}
+
+__device__ __forceinline__ int pil_ksize(int in_size, int out_size) {
+    const double scale = __ddiv_rn((double)in_size, (double)out_size);
+    const double support = scale < 1.0 ? 1.0 : scale;
+    return (int)ceil(support) * 2 + 1;
+}
+
+__device__ __forceinline__ int clip8(int v) {
+    v >>= kPrecision;
+    return min(max(v, 0), 255);
+}
+
+__device__ __forceinline__ void write_out(float* __restrict__ out, uint8_t* __restrict__ out_u8, int y, int x, int v0, int v1, int v2) {
+    const float mean[3] = {0.485f, 0.456f, 0.406f};
+    const float stdv[3] = {0.229f, 0.224f, 0.225f};
+    const int v[3] = {v0, v1, v2};
+#pragma unroll
+    for (int c = 0; c < 3; c++) {
+        float t = __fdiv_rn((float)v[c], 255.0f);
+        out[(c * kOutH + y) * kOutW + x] = __fdiv_rn(__fsub_rn(t, mean[c]), stdv[c]);
+    }
+    if (out_u8) {
+        uint8_t* o = out_u8 + (y * kOutW + x) * 3;
+        o[0] = (uint8_t)v0; o[1] = (uint8_t)v1; o[2] = (uint8_t)v2;
+    }
+}
+
+__global__ void __launch_bounds__(kThreads)
+mnv3_prep_kernel(const uint8_t* __restrict__ pixels, const hvb_crop_desc* __restrict__ crops, int n, int roi_mode,
+                 float* __restrict__ out, uint8_t* __restrict__ out_u8, uint8_t* __restrict__ out_valid) {
+    extern __shared__ __align__(16) uint8_t smem_raw[];
+    Smem& S = *reinterpret_cast<Smem*>(smem_raw);
+
+    for (int ci = blockIdx.x; ci < n; ci += gridDim.x) {
+        const hvb_crop_desc cd = crops[ci];
+        const hvb_rect rc = hvb_roi_rect(cd.h, cd.w, roi_mode);
+        const int rw = max(rc.right - rc.left, 0), rh = max(rc.bottom - rc.top, 0);
+        float* o = out + (int64_t)ci * 3 * kOutH * kOutW;
+        uint8_t* o8 = out_u8 ? out_u8 + (int64_t)ci * kOutH * kOutW * 3 : nullptr;
+        const int ksh = (rw > 0) ? pil_ksize(rw, kOutW) : 1, ksv = (rh > 0) ? pil_ksize(rh, kOutH) : 1;
+        const bool vfirst = rh > 100 * rw;
+        const bool ok = rw > 0 && rh > 0 && ksh <= kKMax && ksv <= kKMax && (!vfirst || rw * kOutH * 3 <= (int)sizeof(S.inter));
+        if (!ok) {
+            // empty ROI: the reference's `except:` path (zero feature row); too-large ROI: flagged 0xFF
+            for (int i = threadIdx.x; i < 3 * kOutH * kOutW; i += kThreads) o[i] = 0.f;
+            if (o8) for (int i = threadIdx.x; i < 3 * kOutH * kOutW; i += kThreads) o8[i] = 0;
+            if (out_valid && threadIdx.x == 0) out_valid[ci] = (rw > 0 && rh > 0) ? 0xFF : 0;
+            continue;
+        }
+        if (out_valid && threadIdx.x == 0) out_valid[ci] = 1;
+        const uint8_t* base = pixels + cd.offset + (int64_t)rc.top * cd.pitch + (int64_t)rc.left * 3;
+
+        __syncthreads();   // previous crop's readers are done with the tables
+        if (threadIdx.x < kOutW) pil_coeffs(rw, kOutW, threadIdx.x, ksh, S.bh[threadIdx.x], S.kh);
+        else if (threadIdx.x >= 128 && threadIdx.x < 128 + kOutH) pil_coeffs(rh, kOutH, threadIdx.x - 128, ksv, S.bv[threadIdx.x - 128], S.kv);
+        __syncthreads();
+
+        if (!vfirst) {
+            int y0 = 0;
+            while (y0 < kOutH) {
+                // largest block of output rows whose source-row window fits the intermediate buffer
+                if (threadIdx.x == 0) {
+                    const int r_lo = S.bv[y0][0];
+                    int y1 = y0 + 1;
+                    while (y1 < kOutH && S.bv[y1][0] + S.bv[y1][1] - r_lo <= kInterRows) y1++;
+                    S.blk[0] = y1; S.blk[1] = r_lo; S.blk[2] = S.bv[y1 - 1][0] + S.bv[y1 - 1][1];
+                }
+                __syncthreads();
+                const int y1 = S.blk[0], r_lo = S.blk[1], r_hi = S.blk[2];
+                // horizontal pass: rows [r_lo, r_hi) -> inter[row - r_lo][xx][c]
+                for (int it = threadIdx.x; it < (r_hi - r_lo) * kOutW; it += kThreads) {
+                    const int row = it / kOutW, xx = it % kOutW;
+                    const int xmin = S.bh[xx][0], cnt = S.bh[xx][1];
+                    const uint8_t* src = base + (int64_t)(r_lo + row) * cd.pitch + xmin * 3;
+                    const int* k = S.kh + xx * ksh;
+                    int s0 = 1 << (kPrecision - 1), s1 = s0, s2 = s0;
+                    for (int x = 0; x < cnt; x++) {
+                        const int kk = k[x];
+                        s0 += __ldg(src + 3 * x) * kk; s1 += __ldg(src + 3 * x + 1) * kk; s2 += __ldg(src + 3 * x + 2) * kk;
+                    }
+                    uint8_t* d = S.inter + (row * kOutW + xx) * 3;
+                    d[0] = (uint8_t)clip8(s0); d[1] = (uint8_t)clip8(s1); d[2] = (uint8_t)clip8(s2);
+                }
+                __syncthreads();
+                // vertical pass: output rows [y0, y1)
+                for (int it = threadIdx.x; it < (y1 - y0) * kOutW; it += kThreads) {
+                    const int y = y0 + it / kOutW, x = it % kOutW;
+                    const int ymin = S.bv[y][0], cnt = S.bv[y][1];
+                    const int* k = S.kv + y * ksv;
+                    const uint8_t* src = S.inter + ((ymin - r_lo) * kOutW + x) * 3;
+                    int s0 = 1 << (kPrecision - 1), s1 = s0, s2 = s0;
+                    for (int t = 0; t < cnt; t++) {
+                        const int kk = k[t];
+                        s0 += src[t * kOutW * 3] * kk; s1 += src[t * kOutW * 3 + 1] * kk; s2 += src[t * kOutW * 3 + 2] * kk;
+                    }
+                    write_out(o, o8, y, x, clip8(s0), clip8(s1), clip8(s2));
+                }
+                __syncthreads();
+                y0 = y1;
+            }
+        } else {
+            // degenerate tall-narrow ROI: vertical pass first -> inter[y][col][c] (128 x rw), then horizontal
+            for (int it = threadIdx.x; it < kOutH * rw; it += kThreads) {
+                const int y = it / rw, col = it % rw;
+                const int ymin = S.bv[y][0], cnt = S.bv[y][1];
+                const int* k = S.kv + y * ksv;
+                const uint8_t* src = base + (int64_t)ymin * cd.pitch + col * 3;
+                int s0 = 1 << (kPrecision - 1), s1 = s0, s2 = s0;
+                for (int t = 0; t < cnt; t++) {
+                    const int kk = k[t];
+                    const uint8_t* p = src + (int64_t)t * cd.pitch;
+                    s0 += __ldg(p) * kk; s1 += __ldg(p + 1) * kk; s2 += __ldg(p + 2) * kk;
+                }
+                uint8_t* d = S.inter + (y * rw + col) * 3;
+                d[0] = (uint8_t)clip8(s0); d[1] = (uint8_t)clip8(s1); d[2] = (uint8_t)clip8(s2);
+            }
+            __syncthreads();
+            for (int it = threadIdx.x; it < kOutH * kOutW; it += kThreads) {
+                const int y = it / kOutW, xx = it % kOutW;
+                const int xmin = S.bh[xx][0], cnt = S.bh[xx][1];
+                const int* k = S.kh + xx * ksh;
+                const uint8_t* src = S.inter + (y * rw + xmin) * 3;
+                int s0 = 1 << (kPrecision - 1), s1 = s0, s2 = s0;
+                for (int x = 0; x < cnt; x++) {
+                    const int kk = k[x];
+                    s0 += src[3 * x] * kk; s1 += src[3 * x + 1] * kk; s2 += src[3 * x + 2] * kk;
+                }
+                write_out(o, o8, y, xx, clip8(s0), clip8(s1), clip8(s2));
+            }
+            __syncthreads();
+        }
+    }
+}
+
+}  // namespace
+
+extern "C" {
+
+int hvb_mnv3_preprocess(hvb_ctx* ctx, const uint8_t* pixels_dev, const hvb_crop_desc* crops_dev, int n, int roi_mode,
+                        float* out_dev, uint8_t* out_u8_dev, uint8_t* out_valid_dev) {
+    HVB_CHECK_CTX(ctx);
+    HVB_ARG(n >= 0, "n < 0");
+    HVB_ARG(roi_mode >= 0 && roi_mode <= 2, "bad roi_mode");
+    if (n == 0) return HVB_OK;
+    HVB_ARG(pixels_dev && crops_dev && out_dev, "null pointer");
+    static_assert(sizeof(Smem) < 200 * 1024, "smem budget");
+    HVB_CUDA(cudaFuncSetAttribute(mnv3_prep_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(Smem)));
+    const int grid = n < ctx->sm_count * 2 ? n : ctx->sm_count * 2;
+    mnv3_prep_kernel<<<grid, kThreads, sizeof(Smem), ctx->stream>>>(pixels_dev, crops_dev, n, roi_mode, out_dev, out_u8_dev,
+                                                                     out_valid_dev);
+    HVB_LAUNCHED(ctx);
+    return HVB_OK;
+}
+
+int hvb_mnv3_preprocess_host(hvb_ctx* ctx, const uint8_t* pixels_host, size_t pixel_bytes, const hvb_crop_desc* crops_host,
+                             int n, int roi_mode, float* out_host, uint8_t* out_valid_host) {
+    HVB_CHECK_CTX(ctx);
+    HVB_ARG(n >= 0, "n < 0");
+    if (n == 0) return HVB_OK;
+    HVB_ARG(pixels_host && crops_host && out_host, "null pointer");
+    const size_t per = (size_t)3 * kOutH * kOutW * sizeof(float);
+    size_t o_crops = (pixel_bytes + 255) & ~(size_t)255;
+    size_t o_out = o_crops + (((size_t)n * sizeof(hvb_crop_desc) + 255) & ~(size_t)255);
+    size_t o_valid = o_out + (size_t)n * per;
+    uint8_t* d = nullptr;
+    HVB_TRY(hvb_scratch(ctx, o_valid + n, (void**)&d));
+    HVB_CUDA(cudaMemcpyAsync(d, pixels_host, pixel_bytes, cudaMemcpyHostToDevice, ctx->stream));
+    HVB_CUDA(cudaMemcpyAsync(d + o_crops, crops_host, (size_t)n * sizeof(hvb_crop_desc), cudaMemcpyHostToDevice, ctx->stream));
+    HVB_TRY(hvb_mnv3_preprocess(ctx, d, (const hvb_crop_desc*)(d + o_crops), n, roi_mode, (float*)(d + o_out), nullptr,
+                                d + o_valid));
+    HVB_CUDA(cudaMemcpyAsync(out_host, d + o_out, (size_t)n * per, cudaMemcpyDeviceToHost, ctx->stream));
+    if (out_valid_host) HVB_CUDA(cudaMemcpyAsync(out_valid_host, d + o_valid, n, cudaMemcpyDeviceToHost, ctx->stream));
+    HVB_CUDA(cudaStreamSynchronize(ctx->stream));
+    return HVB_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,291 @@
+/*
+ * hvb.h — C ABI of libhvb.so, the B200 (sm_100a) implementation of the per-frame hot path of
+ * JetJadeja/hockey-vision-analytics.
+ *
+ * The reference has no FFI of its own (it is pure Python gluing ultralytics / supervision /
+ * OpenCV / torchvision / scikit-learn); every entry point below names the reference call site
+ * (file:line under the reference tree) whose arithmetic it replaces.  The Python host layer
+ * (hockey-vision-analytics_b200/hvb/) binds these with ctypes and presents the reference's own
+ * call surface (InferenceSlicer callback, sv.Detections, TeamClassifier/HybridTeamClassifier);
+ * INTEGRATION.md shows the binding a maintainer of the reference would add.
+ *
+ * Conventions
+ *   - every function returns 0 on success, a negative hvb_status otherwise; the message is in
+ *     hvb_last_error() (thread-local);
+ *   - pointers named *_dev are device pointers on the context's GPU (allocated by the caller —
+ *     e.g. a torch tensor's data_ptr() — or by hvb_malloc); pointers named *_host are host
+ *     pointers; nothing is retained after a call returns unless stated;
+ *   - all work is enqueued on the context's stream (hvb_ctx_set_stream) and is asynchronous
+ *     unless the function name ends in _host or the comment says it synchronises;
+ *   - a context is not re-entrant: one caller at a time per hvb_ctx (the Python layer locks).
+ *   - there is NO CPU fallback anywhere in this library.
+ */
+#ifndef HVB_H_
+#define HVB_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define HVB_VERSION 100
+
+#if defined(__GNUC__)
+#define HVB_API __attribute__((visibility("default")))
+#else
+#define HVB_API
+#endif
+
+typedef enum {
+    HVB_OK = 0,
+    HVB_ERR_CUDA = -1,         /* a CUDA runtime call failed (message has the CUDA error string)   */
+    HVB_ERR_ARG = -2,          /* invalid argument                                                  */
+    HVB_ERR_NO_DEVICE = -3,    /* no usable CUDA device / not an sm_100 part                        */
+    HVB_ERR_CAPACITY = -4,     /* a fixed on-chip capacity was exceeded (e.g. NMS candidates)       */
+    HVB_ERR_UNSUPPORTED = -5
+} hvb_status;
+
+typedef struct hvb_ctx hvb_ctx;
+
+/* ---------------------------------------------------------------- context / memory plumbing */
+HVB_API int hvb_version(void);
+HVB_API const char* hvb_last_error(void);
+HVB_API int hvb_device_count(int* out_count);                       /* never fails hard: count 0 without a GPU */
+HVB_API int hvb_ctx_create(int device, hvb_ctx** out_ctx);
+HVB_API int hvb_ctx_destroy(hvb_ctx* ctx);
+HVB_API int hvb_ctx_set_stream(hvb_ctx* ctx, void* cuda_stream);    /* NULL -> the context's own stream    */
+HVB_API int hvb_ctx_get_stream(hvb_ctx* ctx, void** out_stream);
+HVB_API int hvb_ctx_synchronize(hvb_ctx* ctx);
+HVB_API int hvb_ctx_sm_count(hvb_ctx* ctx, int* out_sms);
+HVB_API int hvb_malloc(hvb_ctx* ctx, size_t bytes, void** out_dev);
+HVB_API int hvb_free(hvb_ctx* ctx, void* ptr_dev);
+HVB_API int hvb_host_alloc(hvb_ctx* ctx, size_t bytes, void** out_host);   /* pinned */
+HVB_API int hvb_host_free(hvb_ctx* ctx, void* ptr_host);
+HVB_API int hvb_memcpy_h2d(hvb_ctx* ctx, void* dst_dev, const void* src_host, size_t bytes);  /* async */
+HVB_API int hvb_memcpy_d2h(hvb_ctx* ctx, void* dst_host, const void* src_dev, size_t bytes);  /* async */
+HVB_API int hvb_memset(hvb_ctx* ctx, void* dst_dev, int value, size_t bytes);
+/* Launch counter: number of libhvb kernels launched on this context since the last reset. */
+HVB_API int hvb_ctx_launch_count(hvb_ctx* ctx, int reset, uint64_t* out_launches);
+/* Device event timing helpers (events recorded on the context's stream). */
+HVB_API int hvb_timer_start(hvb_ctx* ctx);
+HVB_API int hvb_timer_stop_ms(hvb_ctx* ctx, float* out_ms);          /* synchronises on the stop event      */
+
+/* ---------------------------------------------------------------- K1: letterbox / slicing
+ * Replaces ultralytics LetterBox + BasePredictor.preprocess reached from
+ * hockey/main.py:179-184 (whole frame, imgsz 1280) and, per tile, the documented
+ * sv.InferenceSlicer(callback, slice_wh=(640,640), overlap 0.2) path (README.md:25, CLAUDE.md:55):
+ * crop_image -> LetterBox(auto) -> cv2.resize(INTER_LINEAR) -> copyMakeBorder(114) ->
+ * BGR->RGB, HWC->CHW, float32, /255.
+ *
+ * A plan fixes the geometry for a chunk of `n_frames` equally-sized frames; running it is ONE
+ * kernel launch that writes every tile of every frame into one output buffer laid out as a
+ * sequence of shape-class batches:  for class c: float32[n_frames * tiles_per_frame_c, 3, out_h_c, out_w_c]
+ * starting at element offset class.out_offset.
+ */
+typedef struct hvb_lb_plan hvb_lb_plan;
+
+typedef enum {
+    HVB_LB_WHOLE = 0,          /* one job per frame: letterbox the whole frame to imgsz             */
+    HVB_LB_SLICE_EXACT = 1,    /* InferenceSlicer tiles, each LetterBox(auto=True) -> per-shape-class batches */
+    HVB_LB_SLICE_UNIFORM = 2   /* InferenceSlicer tiles, each LetterBox(auto=False) -> uniform imgsz x imgsz  */
+} hvb_lb_mode;
+
+typedef struct {
+    int32_t out_h, out_w;        /* letterboxed (padded) shape of this class                        */
+    int32_t tiles_per_frame;     /* how many tiles of one frame fall in this class                  */
+    int32_t batch;               /* n_frames * tiles_per_frame, batch index = frame * tiles_per_frame + k */
+    int64_t out_offset;          /* float offset of the class batch inside the output buffer        */
+} hvb_lb_class;
+
+typedef struct {
+    int32_t frame;               /* source frame index inside the chunk                              */
+    int32_t tile;                /* tile index inside the frame (slicer row-major order), 0 for WHOLE */
+    int32_t cls;                 /* shape class                                                       */
+    int32_t batch_index;         /* index inside the class batch                                      */
+    int32_t src_x, src_y, src_w, src_h;   /* source rectangle in the frame (slicer offset + clipped size) */
+    int32_t new_w, new_h;        /* resized, unpadded size                                            */
+    int32_t top, left;           /* padding before the image                                          */
+    int32_t out_h, out_w;
+    float gain, pad_x, pad_y;    /* ultralytics scale_boxes() constants for (out_h,out_w)->(src_h,src_w) */
+} hvb_lb_tile;
+
+HVB_API int hvb_lb_plan_create(hvb_ctx* ctx, int n_frames, int frame_h, int frame_w, int mode, int imgsz,
+                       int auto_pad, int stride, int slice_w, int slice_h, int overlap_w, int overlap_h,
+                       hvb_lb_plan** out_plan);
+HVB_API int hvb_lb_plan_destroy(hvb_lb_plan* plan);
+HVB_API int hvb_lb_plan_num_classes(const hvb_lb_plan* plan, int* out_n);
+HVB_API int hvb_lb_plan_get_class(const hvb_lb_plan* plan, int cls, hvb_lb_class* out_class);
+HVB_API int hvb_lb_plan_num_tiles(const hvb_lb_plan* plan, int* out_n);              /* n_frames * tiles per frame */
+HVB_API int hvb_lb_plan_get_tiles(const hvb_lb_plan* plan, hvb_lb_tile* out_tiles_host, int capacity);
+HVB_API int hvb_lb_plan_out_floats(const hvb_lb_plan* plan, int64_t* out_floats);    /* size of the output buffer */
+HVB_API int hvb_lb_plan_bytes(const hvb_lb_plan* plan, int64_t* out_read_bytes, int64_t* out_write_bytes); /* algorithmic */
+/* frames_dev: uint8[n_frames, frame_h, frame_w, 3] BGR, dense.  out_dev: float32[out_floats]. */
+HVB_API int hvb_lb_plan_run(hvb_lb_plan* plan, const uint8_t* frames_dev, float* out_dev);
+/* Test hook: the uint8 stage only (resize + 114 padding, still BGR/HWC), same batch layout in bytes. */
+HVB_API int hvb_lb_plan_run_u8(hvb_lb_plan* plan, const uint8_t* frames_dev, uint8_t* out_dev);
+
+/* ---------------------------------------------------------------- K2a: YOLOv8 head decode + NMS
+ * Replaces ultralytics Detect._inference (DFL softmax-expectation, dist2bbox, x stride, sigmoid),
+ * ops.non_max_suppression (conf gate, per-image class-aware NMS through torchvision.ops.nms with
+ * the +cls*7680 offset, max_det) and ops.scale_boxes/clip_boxes, reached from
+ * hockey/main.py:179-186, plus sv.move_detections for sliced tiles.
+ *
+ * level_dev[i]: float32 raw Detect output of level i (stride 8,16,32): channel c of anchor a of
+ * image b at  b*batch_stride[i] + c*chan_stride[i] + a*anchor_stride[i]  (NCHW: chan_stride=H*W,
+ * anchor_stride=1).  Channels: 64 box bins (side-major, 16 bins each: l,t,r,b) then nc class logits.
+ * meta_dev: one hvb_img_meta per image.  Outputs hold max_det rows per slot (row block = meta.out_slot),
+ * score order; out_count[slot] = kept count, or -1 if the image had more than 1024 candidates.
+ */
+typedef struct {
+    float gain, pad_x, pad_y;    /* scale_boxes: (x - pad) / gain                                    */
+    float clip_w, clip_h;        /* clip x to [0,clip_w], y to [0,clip_h] (original tile/frame shape) */
+    float off_x, off_y;          /* slice offset (sv.move_detections), applied by hvb_gather_tiles, not here   */
+    int32_t out_slot;            /* row of the output arrays this image writes (e.g. frame * tiles + tile)     */
+} hvb_img_meta;                  /* 32 bytes */
+
+HVB_API int hvb_decode_nms(hvb_ctx* ctx, const float* const level_dev[3], const int32_t level_h[3],
+                   const int32_t level_w[3], const int64_t batch_stride[3], const int64_t chan_stride[3],
+                   const int64_t anchor_stride[3], int batch, int nc, float conf_thres, float iou_thres,
+                   int max_det, int agnostic, const hvb_img_meta* meta_dev,
+                   float* out_xyxy_dev /*[batch,max_det,4]*/, float* out_conf_dev /*[batch,max_det]*/,
+                   int32_t* out_cls_dev /*[batch,max_det]*/, int32_t* out_count_dev /*[batch]*/);
+/* Images whose out_count came back -1 had more than 1024 candidates above conf_thres; re-run just
+ * those (images_dev: int32[n_images] batch indices) with the 8192-candidate tier.  Still -1 after
+ * that means the on-chip capacity (hvb_nms_capacity) is exceeded. */
+HVB_API int hvb_decode_nms_large(hvb_ctx* ctx, const float* const level_dev[3], const int32_t level_h[3],
+                         const int32_t level_w[3], const int64_t batch_stride[3], const int64_t chan_stride[3],
+                         const int64_t anchor_stride[3], const int32_t* images_dev, int n_images, int nc,
+                         float conf_thres, float iou_thres, int max_det, int agnostic,
+                         const hvb_img_meta* meta_dev, float* out_xyxy_dev, float* out_conf_dev,
+                         int32_t* out_cls_dev, int32_t* out_count_dev);
+/* Test hooks: decode only (float32[batch, 4+nc, A] like Detect._inference) and NMS only on
+ * caller-provided candidates (boxes xyxy float32[n,4], scores, classes; one image). */
+HVB_API int hvb_decode_only(hvb_ctx* ctx, const float* const level_dev[3], const int32_t level_h[3],
+                    const int32_t level_w[3], const int64_t batch_stride[3], const int64_t chan_stride[3],
+                    const int64_t anchor_stride[3], int batch, int nc, float* out_pred_dev);
+HVB_API int hvb_nms_f32(hvb_ctx* ctx, const float* boxes_dev, const float* scores_dev, const int32_t* cls_dev,
+                int n, float iou_thres, int max_det, int agnostic,
+                int32_t* out_keep_idx_dev /*[max_det]*/, int32_t* out_count_dev /*[1]*/);
+HVB_API int hvb_nms_capacity(int* out_max_candidates);
+
+/* ---------------------------------------------------------------- K2b: cross-slice merge NMS
+ * Replaces sv.Detections.with_nms -> box_non_max_suppression / box_iou_batch (float64, keep mask
+ * in input order, class-aware unless class_agnostic) applied to the merged slicer result.
+ * Segments: detections of segment s are rows seg_offsets[s] .. seg_offsets[s+1]-1 (one frame each).
+ */
+HVB_API int hvb_merge_nms(hvb_ctx* ctx, const double* xyxy_dev, const float* conf_dev, const int32_t* cls_dev,
+                  const int32_t* seg_offsets_dev, int n_segments, int n_total, double iou_thres,
+                  int class_agnostic, uint8_t* out_keep_dev);
+
+/* sv.move_detections + Detections.merge for a chunk of frames: compacts the per-slot K2a results
+ * (slot = frame * slots_per_frame + tile; rows 0..count[slot]-1 of each slot) into per-frame merged
+ * lists in slicer tile order, float64 boxes moved by the slot's offset (slot_off_xy_dev float32[n_slots,2]).
+ * out_seg_offsets_dev: int32[n_frames+1]; out_slot_dev (optional) records the source slot of each row.
+ * Output arrays must hold n_slots*max_det rows. */
+HVB_API int hvb_gather_tiles(hvb_ctx* ctx, const float* xyxy_dev, const float* conf_dev, const int32_t* cls_dev,
+                     const int32_t* count_dev, const float* slot_off_xy_dev, int n_slots, int slots_per_frame,
+                     int max_det, double* out_xyxy_dev, float* out_conf_dev, int32_t* out_cls_dev,
+                     int32_t* out_slot_dev, int32_t* out_seg_offsets_dev);
+
+/* ---------------------------------------------------------------- K3: per-detection crop features
+ * A crop is described by where its pixels live inside one device byte buffer (`pixels_dev`):
+ * either a view into a resident frame (offset of its first pixel, pitch = frame_w*3) or a packed
+ * copy of a host crop (pitch = w*3).
+ */
+typedef struct {
+    int64_t offset;              /* byte offset of pixel (0,0) of the crop inside pixels_dev         */
+    int32_t pitch;               /* bytes between rows                                                */
+    int32_t h, w;                /* crop size in pixels (may be 0)                                    */
+    int32_t reserved;
+} hvb_crop_desc;
+
+/* sv.crop_image (hockey/main.py:324-326): np.round(xyxy).astype(int) (half-to-even) then the numpy
+ * slice frame[y0:y1, x0:x1] (negative indices wrap, ends clamp).  frame_idx_dev may be NULL (frame 0). */
+HVB_API int hvb_crops_from_boxes(hvb_ctx* ctx, const float* xyxy_dev, const int32_t* frame_idx_dev, int n,
+                         int frame_h, int frame_w, hvb_crop_desc* out_crops_dev);
+
+typedef enum {
+    HVB_ROI_HYBRID = 0,          /* HybridTeamClassifier.extract_jersey_region, team_hybrid.py:49-64  */
+    HVB_ROI_SIMPLE = 1,          /* TeamClassifier.extract_jersey_region, team.py:76-99               */
+    HVB_ROI_WHOLE = 2
+} hvb_roi_mode;
+
+typedef struct {
+    uint32_t hist[34];           /* H 18 bins of 10, S 8 bins of 32, V 8 bins of 32 (cv2.calcHist)    */
+    uint32_t counts[3];          /* S<30, S>100, (V>200)&(S<30)                                       */
+    uint32_t n;                  /* ROI pixel count                                                   */
+    uint32_t roi[4];             /* top, bottom, left, right actually used                            */
+    uint32_t pad_[2];
+    uint64_t sums[6];            /* sum of H,S,V,L,a,b                                                */
+    uint64_t sumsq[6];           /* sum of squares of H,S,V,L,a,b                                     */
+} hvb_color_raw;                 /* 272 bytes */
+
+/* HybridTeamClassifier.extract_color_features, team_hybrid.py:89-142: cv2.cvtColor BGR2HSV/BGR2LAB
+ * (bit-exact), calcHist x3, per-channel mean / population std (/255), S<30, S>100, white ratios.
+ * out_feat_dev: float64[n,49] (layout as the reference's np.concatenate) or NULL;
+ * out_raw_dev: hvb_color_raw[n] or NULL.  An empty ROI yields NaN features (the reference raises). */
+HVB_API int hvb_color_features(hvb_ctx* ctx, const uint8_t* pixels_dev, const hvb_crop_desc* crops_dev, int n,
+                       int roi_mode, double* out_feat_dev, int64_t feat_row_stride /*doubles, >=49*/,
+                       hvb_color_raw* out_raw_dev);
+/* Test hook: plain per-pixel conversion of n_px BGR pixels (the 2^24 colour-cube test). */
+HVB_API int hvb_cvt_hsv_lab(hvb_ctx* ctx, const uint8_t* bgr_dev, int64_t n_px, uint8_t* out_hsv_dev,
+                    uint8_t* out_lab_dev);
+
+/* self.preprocess of team_hybrid.py:31-36 applied to the jersey ROI of each crop: Pillow-exact
+ * antialiased bilinear resize to 128x64 (uint8), /255, (x-mean)/std with the RGB statistics applied
+ * to the BGR channels unswapped, CHW float32.  out_dev: float32[n,3,128,64].
+ * out_u8_dev (optional, test hook): the resized uint8[n,128,64,3].  Empty ROI -> zeros + flag
+ * (the reference's except: -> zeros(576) path); out_valid_dev uint8[n] may be NULL. */
+HVB_API int hvb_mnv3_preprocess(hvb_ctx* ctx, const uint8_t* pixels_dev, const hvb_crop_desc* crops_dev, int n,
+                        int roi_mode, float* out_dev, uint8_t* out_u8_dev, uint8_t* out_valid_dev);
+
+/* ---------------------------------------------------------------- K4a: standardise + Gram / RBF affinity
+ * StandardScaler.fit_transform (team_hybrid.py:166) and the affinity SpectralClustering(affinity='rbf',
+ * gamma=1.0) builds inside fit (team_hybrid.py:185-193 -> sklearn pairwise rbf_kernel):
+ *   d2 = max(|x|^2 + |y|^2 - 2 x.y, 0), diag 0;  A = exp(-gamma d2).
+ * x_dev: float64[N,D] row-major.  mode 0: X.X^T on the tensor cores (tcgen05, split-TF32 operands,
+ * fp32 accumulate in TMEM) + float64 refinement of the pairs whose affinity does not underflow;
+ * mode 1: float64 CUDA-core path only.  Either output may be NULL.
+ */
+HVB_API int hvb_standardize(hvb_ctx* ctx, const double* x_dev, int n, int d, double* out_mean_dev,
+                    double* out_scale_dev, double* out_xs_dev);
+HVB_API int hvb_scale_transform(hvb_ctx* ctx, const double* x_dev, int n, int d, const double* mean_dev,
+                        const double* scale_dev, double* out_xs_dev);
+HVB_API int hvb_gram_affinity(hvb_ctx* ctx, const double* x_dev, int n, int d, double gamma, int mode,
+                      double* out_d2_dev, double* out_a_dev);
+/* The tensor-core Gram alone: G = X.X^T as float32[N,N] (bench / roofline hook). */
+HVB_API int hvb_gram_tc(hvb_ctx* ctx, const double* x_dev, int n, int d, float* out_g_dev);
+
+/* ---------------------------------------------------------------- K4b: ByteTrack IoU cost
+ * matching.iou_distance (+ fuse_score) of supervision's ByteTrack reached from hockey/main.py:228,265:
+ * cost[t,d] = 1 - IoU(a[t], b[d])  (nan -> IoU 0), optionally 1 - IoU*score[d].  float64 like numpy.
+ * Batched over independent problems (clips): problem p uses rows a_off[p]..a_off[p+1]-1 of a,
+ * b_off[p]..b_off[p+1]-1 of b and writes a dense [na_p, nb_p] block at out_off[p].
+ */
+HVB_API int hvb_iou_cost(hvb_ctx* ctx, const double* a_dev, const double* b_dev, const double* scores_dev,
+                 const int32_t* a_off_dev, const int32_t* b_off_dev, const int64_t* out_off_dev,
+                 int n_problems, int max_na, int max_nb, double* out_dev);
+
+/* ---------------------------------------------------------------- host-buffer entry points
+ * What a non-Python binding (cgo / JNI / N-API) would call: host in, host out, synchronous.
+ * They stage through context-owned pinned + device scratch and run the same kernels. */
+HVB_API int hvb_color_features_host(hvb_ctx* ctx, const uint8_t* pixels_host, size_t pixel_bytes,
+                            const hvb_crop_desc* crops_host, int n, int roi_mode,
+                            double* out_feat_host /*[n,49]*/, hvb_color_raw* out_raw_host /*or NULL*/);
+HVB_API int hvb_mnv3_preprocess_host(hvb_ctx* ctx, const uint8_t* pixels_host, size_t pixel_bytes,
+                             const hvb_crop_desc* crops_host, int n, int roi_mode,
+                             float* out_host /*[n,3,128,64]*/, uint8_t* out_valid_host /*or NULL*/);
+HVB_API int hvb_merge_nms_host(hvb_ctx* ctx, const double* xyxy_host, const float* conf_host,
+                       const int32_t* cls_host, int n, double iou_thres, int class_agnostic,
+                       uint8_t* out_keep_host);
+HVB_API int hvb_iou_cost_host(hvb_ctx* ctx, const double* a_host, int na, const double* b_host, int nb,
+                      const double* scores_host /*or NULL*/, double* out_host /*[na,nb]*/);
+HVB_API int hvb_gram_affinity_host(hvb_ctx* ctx, const double* x_host, int n, int d, double gamma, int mode,
+                           double* out_d2_host /*or NULL*/, double* out_a_host /*or NULL*/);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* HVB_H_ */
