@@ -1,0 +1,362 @@
+#!/usr/bin/env python
+"""bench.py — hot-path frames/s on synthetic 1080p frames (+ the 4K sliced puck path), with the
+roofline of the dominant libhvb kernel and the CPU reference path timed beside it.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl hvb|reference] [--chunk F]
+    torchrun --nnodes=1 --nproc-per-node N ... bench.py --gpus N ...
+
+A "step" is one pass of the hot path over one chunk of F synthetic 1080p frames per GPU
+(BASELINE.json configs[1] + configs[2]):
+    K1a letterbox -> YOLOv8m forward (torch fp32, random init) -> K2a decode+NMS ->
+    K3a colour features + K3b crop preprocessing on 12 player boxes / frame -> MobileNetV3 (torch fp32) ->
+    K4a scale_transform -> similarity rule.
+Random-init YOLO emits no detection above conf=0.4, so the team stage runs on the
+12 planted player boxes of each synthetic frame ("team_boxes": "planted"); the detection stage
+still does all of its work.  `value` has the frames resident in HBM; `e2e` goes through the public
+host API (pinned host frames in, H2D + D2H inside the timed region).
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+PKG = os.path.join(ROOT, "hockey-vision-analytics_b200")
+for p in (ROOT, PKG):
+    if p not in sys.path:
+        sys.path.insert(0, p)
+
+H, W, PLAYERS = 1080, 1920, 12
+METRIC = "hot_path_frames_per_sec_1080p"
+UNIT = "frames/s"
+
+
+def measured_peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        d = json.load(open(p))
+        return float(d["hbm_gbs"]), "measured"
+    return 6650.0, "fallback"
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled every 200 ms during the timed region."""
+    Q = "clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown," \
+        "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+
+    def __init__(self, index: int):
+        self.index, self.proc, self.lines = index, None, []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q,
+                                          "--format=csv,noheader,nounits", "-lms", "200"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.25)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for l in self.lines:
+            f = [x.strip() for x in l.split(",")]
+            if len(f) < 6:
+                continue
+            try:
+                sm.append(float(f[0])); mx.append(float(f[1]))
+            except ValueError:
+                continue
+            for n, v in zip(names, f[2:6]):
+                if v.lower().startswith("active"):
+                    reasons.add(n)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def synth_chunk(seed: int, n: int):
+    from hvb.synth import rink_frame
+    rng = np.random.default_rng(seed)
+    frames, boxes, fidx = [], [], []
+    for i in range(n):
+        f, b, _, _ = rink_frame(rng, H, W, PLAYERS)
+        frames.append(f); boxes.append(b); fidx.append(np.full(len(b), i, np.int32))
+    return np.stack(frames), np.concatenate(boxes).astype(np.float32), np.concatenate(fidx)
+
+
+# ------------------------------------------------------------------------------------------ reference arm
+class CpuReferencePath:
+    """The reference's own CPU implementation of the path, restated in oracle/ against the same real
+    libraries (cv2, Pillow/torchvision, sklearn, torchvision.ops.nms): kind = "port"."""
+
+    def __init__(self):
+        import torch
+        from hvb.models import build_trunk, build_yolov8
+        from oracle import team_reference as tr
+        self.torch = torch
+        self.yolo = build_yolov8("m", 2, 0)
+        self.trunk = build_trunk(0, calibrate=True)
+        self.ref = tr.HybridReference(self.trunk)
+        self.fitted = False
+
+    def fit(self, frames, boxes, fidx):
+        from oracle.supervision_restated import crop_image
+        crops = [crop_image(frames[f], b) for f, b in zip(fidx, boxes)]
+        self.ref.fit(crops, run_clustering=False)
+        self.fitted = True
+
+    def step(self, frames, boxes, fidx):
+        from oracle import ultralytics_restated as ur
+        from oracle.supervision_restated import crop_image
+        torch = self.torch
+        out = []
+        for i, frame in enumerate(frames):
+            lb = ur.letterbox(frame, 1280, auto=True)
+            x = torch.from_numpy(ur.preprocess([lb]))
+            with torch.no_grad():
+                heads = self.yolo(x)
+            det = ur.predict_from_head(heads, 2, tuple(x.shape[2:]), [frame.shape[:2]], 0.4)[0]
+            crops = [crop_image(frame, b) for b in boxes[fidx == i]]
+            out.append((det, self.ref.predict(crops)))
+        return out
+
+
+def run_reference(args, rank, world):
+    import torch
+    if rank != 0:
+        return
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    path = CpuReferencePath()
+    frames, boxes, fidx = synth_chunk(0, args.ref_frames)
+    path.fit(frames, boxes, fidx)
+    for _ in range(args.warmup):
+        path.step(frames[:1], boxes[fidx == 0], fidx[fidx == 0])
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        path.step(frames, boxes, fidx)
+    dt = time.perf_counter() - t0
+    fps = args.steps * len(frames) / dt
+    line = {
+        "impl": "reference", "metric": METRIC, "value": fps, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "u8/f32", "data": "synthetic",
+        "config": {"workload": "C2+C3 1080p player detection + team classification, CPU reference path",
+                   "frames_per_step": int(len(frames)), "players_per_frame": PLAYERS, "team_boxes": "planted"},
+        "cpu_baseline": {"value": fps, "unit": UNIT, "cores": cores, "kind": "port",
+                         "sample": "%d synthetic 1080p frames per step: cv2 letterbox + YOLOv8m CPU forward + restated "
+                                   "decode/torchvision NMS + reference colour/MobileNetV3 features + predict" % len(frames)},
+        "e2e": {"value": fps, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line))
+
+
+# ------------------------------------------------------------------------------------------ hvb arm
+def run_hvb(args, rank, world):
+    import torch
+    import torch.distributed as dist
+    local = int(os.environ.get("LOCAL_RANK", 0))
+    torch.cuda.set_device(local)
+    dev = "cuda:%d" % local
+    from hvb import _ffi
+    from hvb.pipeline import HotPath, SlicedPuckPath
+    from hvb.runtime import get_context
+
+    ctx = get_context(local)
+    F = args.chunk
+    path = HotPath(dev, "m", 2, 1280, 0.4, seed=0)
+    frames, boxes, fidx = synth_chunk(1000 + rank, F)             # each rank owns its own clip chunk (weak scaling)
+    pinned = torch.from_numpy(frames).pin_memory()
+    frames_dev = pinned.to(dev)
+    boxes_dev = torch.from_numpy(boxes).to(dev)
+    fidx_dev = torch.from_numpy(fidx).to(dev)
+
+    # ---- one-off team fit (per job): local crop features -> all-gather (NCCL) -> global standardise + affinity
+    t_fit0 = time.perf_counter()
+    feats, raw, _ = path.classifier.features_from_frame(frames_dev, boxes_dev, fidx_dev)
+    if world > 1:
+        from hvb.dist import all_gather_features
+        feats = all_gather_features(feats)
+    path.classifier.fit_features(feats, None, None)
+    torch.cuda.synchronize()
+    fit_ms = 1e3 * (time.perf_counter() - t_fit0)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def timed(fn, steps, warmup, sampler=None):
+        for _ in range(warmup):
+            fn()
+        barrier()
+        if sampler:
+            sampler.start()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(steps):
+            fn()
+        e1.record()
+        barrier()
+        ms = e0.elapsed_time(e1)
+        clocks = sampler.stop() if sampler else None
+        if world > 1:
+            t = torch.tensor([ms], device=dev)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            ms = float(t.item())
+        return ms, clocks
+
+    # ---- (i) device-resident hot path
+    k1_events = []
+
+    def step_device():
+        path.process_chunk_device(frames_dev, boxes_dev, fidx_dev)
+
+    ctx.launch_count(reset=True)
+    sampler = ClockSampler(local) if rank == 0 else None
+    ms_dev, clocks = timed(step_device, args.steps, args.warmup, sampler)
+    launches = ctx.launch_count() // (args.steps + args.warmup) * args.steps
+    fps_dev = world * F * args.steps / (ms_dev / 1e3)
+
+    # ---- (ii) end to end through the public host API (pinned frames, H2D + D2H inside)
+    def step_e2e():
+        path.process_chunk(pinned, boxes, fidx)
+
+    ms_e2e, _ = timed(step_e2e, args.steps, max(1, args.warmup // 2))
+    fps_e2e = world * F * args.steps / (ms_e2e / 1e3)
+    h2d = frames.nbytes + boxes.nbytes + fidx.nbytes
+    md = path.detector.max_det
+    d2h = F * md * (16 + 4 + 4) + F * 4 + len(boxes) * 80
+
+    # ---- roofline of the dominant libhvb kernel (K1 letterbox), timed live with CUDA events on its stream
+    plan = path.detector.plan(F, H, W, _ffi.LB_WHOLE)
+    out = plan.run(frames_dev)
+    torch.cuda.synchronize()
+    reps = max(args.steps, 10)
+    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(reps)]
+    for a, b in ev:
+        a.record(); plan.run(frames_dev, out); b.record()
+    torch.cuda.synchronize()
+    k1_ms = float(np.mean([a.elapsed_time(b) for a, b in ev]))
+    k1_bytes = plan.read_bytes + plan.write_bytes
+    peak, peak_src = measured_peaks()
+    achieved = k1_bytes / (k1_ms / 1e3) / 1e9
+
+    # ---- secondary workload: 4K sliced puck path (C4), reported in `extra`
+    extra = {"fit_ms": fit_ms}
+    if args.with_4k:
+        from hvb.synth import rink_frame
+        rng = np.random.default_rng(7 + rank)
+        F4 = args.chunk_4k
+        f4 = np.stack([rink_frame(rng, 2160, 3840, PLAYERS, 2.0)[0] for _ in range(F4)])
+        f4_dev = torch.from_numpy(f4).to(dev)
+        puck = SlicedPuckPath(dev, "n", 1, 0.4)
+        ms4, _ = timed(lambda: puck.process_chunk_device(f4_dev), max(2, args.steps // 2), 2)
+        plan4 = puck.detector.plan(F4, 2160, 3840, _ffi.LB_SLICE_EXACT, 640, (640, 640), (128, 128))
+        o4 = plan4.run(f4_dev)
+        torch.cuda.synchronize()
+        ev4 = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(10)]
+        for a, b in ev4:
+            a.record(); plan4.run(f4_dev, o4); b.record()
+        torch.cuda.synchronize()
+        k1b_ms = float(np.mean([a.elapsed_time(b) for a, b in ev4]))
+        extra.update({"c4_4k_sliced_frames_per_sec": world * F4 * max(2, args.steps // 2) / (ms4 / 1e3),
+                      "c4_frames_per_step": F4, "c4_tiles_per_frame": int(plan4.tiles_per_frame),
+                      "k1b_slice_letterbox_gbs": (plan4.read_bytes + plan4.write_bytes) / (k1b_ms / 1e3) / 1e9,
+                      "k1b_frac_of_hbm_peak": (plan4.read_bytes + plan4.write_bytes) / (k1b_ms / 1e3) / 1e9 / peak})
+
+    # ---- CPU baseline beside it (rank 0, N=1 only), bounded sample
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        cores = os.cpu_count() or 1
+        torch.set_num_threads(cores)
+        ref = CpuReferencePath()
+        nf = args.ref_frames
+        ref.fit(frames[:nf], boxes[fidx < nf], fidx[fidx < nf])
+        ref.step(frames[:1], boxes[fidx == 0], fidx[fidx == 0])
+        t0 = time.perf_counter()
+        ref.step(frames[:nf], boxes[fidx < nf], fidx[fidx < nf])
+        dt = time.perf_counter() - t0
+        cpu = {"value": nf / dt, "unit": UNIT, "cores": cores, "kind": "port",
+               "sample": "%d of the %d synthetic 1080p frames of one step, same stages on the host: cv2 letterbox, YOLOv8m "
+                         "CPU forward (torch, %d threads), restated decode + real torchvision NMS, reference colour + "
+                         "MobileNetV3 features, predict" % (nf, F, cores)}
+
+    if rank == 0:
+        line = {
+            "metric": METRIC, "value": fps_dev, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": ms_dev / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "u8/f32", "data": "synthetic",
+            "config": {"workload": "C2+C3: 1080p player detection (K1a letterbox, YOLOv8m fp32 random-init, K2a decode+NMS) + "
+                                   "team classification (K3a/K3b on 12 planted player boxes per frame, MobileNetV3-small fp32, "
+                                   "K4a scale_transform, rule)",
+                       "frames_per_step_per_gpu": F, "players_per_frame": PLAYERS, "team_boxes": "planted",
+                       "backbones": "torch fp32 (cudnn TF32 default for YOLO, TF32 off for MobileNetV3)",
+                       "l2": "inputs larger than L2 (%.0f MB frames + %.0f MB letterboxed per step)" % (frames.nbytes / 1e6, k1_bytes / 1e6),
+                       "parallelism": "frame chunks sharded per GPU, no data-path collective; one NCCL feature all-gather at fit"},
+            "e2e": {"value": fps_e2e, "unit": UNIT, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h)},
+            "gpu_launches": int(launches),
+            "clocks": clocks,
+            "roofline": {"kernel": "letterbox_kernel<false> (K1a, 1080p->736x1280, %d frames/launch)" % F, "bound": "hbm",
+                         "achieved": achieved, "peak": peak, "peak_source": peak_src, "unit": "GB/s", "frac": achieved / peak,
+                         "traffic": None, "algorithmic_bytes_per_launch": int(k1_bytes), "avg_launch_ms": k1_ms},
+            "cpu_baseline": cpu,
+            "extra": extra,
+        }
+        print(json.dumps(line))
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="hvb", choices=["hvb", "reference"])
+    ap.add_argument("--chunk", type=int, default=16, help="1080p frames per step per GPU")
+    ap.add_argument("--chunk-4k", type=int, default=4)
+    ap.add_argument("--ref-frames", type=int, default=2, help="frames per CPU-reference step (bounded sample)")
+    ap.add_argument("--no-4k", dest="with_4k", action="store_false")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl == "hvb" else args.warmup
+
+    rank = int(os.environ.get("RANK", 0))
+    world = int(os.environ.get("WORLD_SIZE", 1))
+    if args.impl == "reference":
+        run_reference(args, rank, world)
+        return
+    import torch
+    import torch.distributed as dist
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl")
+    try:
+        run_hvb(args, rank, world)
+    finally:
+        if world > 1:
+            dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,172 @@
+"""Detection front end: the drop-in for ``VideoProcessor.detect_players`` (reference
+hockey/main.py:177-195) and for the per-tile callback of ``sv.InferenceSlicer``.
+
+    frame(s) --H2D--> K1 letterbox kernel --> torch YOLOv8 forward --> K2a decode+NMS kernel --D2H--> Detections
+
+Only the backbone forward runs in PyTorch; letterboxing, head decode, NMS and box rescaling are
+libhvb kernels.  Batches of frames go through one K1 launch and one K2a launch.
+"""
+from __future__ import annotations
+
+from typing import Dict, List, Optional, Sequence, Tuple
+
+import numpy as np
+import torch
+
+from . import _ffi
+from .detections import Detections
+from .runtime import Context, LetterboxPlan, get_context
+
+PLAYER_CLASS_ID = 0
+GOALKEEPER_CLASS_ID = 1
+
+
+def _as_frames(frames) -> np.ndarray | torch.Tensor:
+    if isinstance(frames, np.ndarray) and frames.ndim == 3:
+        frames = frames[None]
+    if isinstance(frames, torch.Tensor) and frames.ndim == 3:
+        frames = frames[None]
+    return frames
+
+
+class Detector:
+    """YOLOv8 detector whose pre/post-processing runs in libhvb.
+
+    `model` is a module returning the three raw Detect tensors (hvb.models.YOLOv8).  Parameters
+    mirror the ultralytics predict call at hockey/main.py:179-184: imgsz, conf (+ iou 0.7,
+    max_det 300, class-aware NMS defaults)."""
+
+    def __init__(self, model: torch.nn.Module, device="cuda:0", imgsz: int = 1280, conf: float = 0.4, iou: float = 0.7,
+                 max_det: int = 300, agnostic_nms: bool = False, class_names: Optional[Dict[int, str]] = None,
+                 autocast_dtype: Optional[torch.dtype] = None, channels_last: bool = False):
+        self.ctx: Context = get_context(device)
+        self.device = self.ctx.device
+        self.model = model.to(self.device).eval()
+        if channels_last:
+            self.model = self.model.to(memory_format=torch.channels_last)
+        self.channels_last = channels_last
+        self.nc = int(model.nc)
+        self.imgsz, self.conf, self.iou, self.max_det, self.agnostic = imgsz, conf, iou, max_det, agnostic_nms
+        self.autocast_dtype = autocast_dtype
+        self.class_names = class_names or {i: str(i) for i in range(self.nc)}
+        self._plans: Dict[Tuple, LetterboxPlan] = {}
+        self._meta: Dict[Tuple, torch.Tensor] = {}
+
+    # -------------------------------------------------------------- plumbing
+    def plan(self, n: int, h: int, w: int, mode: int = _ffi.LB_WHOLE, imgsz: Optional[int] = None,
+             slice_wh=(640, 640), overlap_wh=(128, 128)) -> LetterboxPlan:
+        key = (n, h, w, mode, imgsz or self.imgsz, tuple(slice_wh), tuple(overlap_wh))
+        if key not in self._plans:
+            self._plans[key] = self.ctx.letterbox_plan(n, h, w, mode, imgsz or self.imgsz, True, 32, slice_wh, overlap_wh)
+        return self._plans[key]
+
+    def upload(self, frames) -> torch.Tensor:
+        """Host uint8[n,H,W,3] -> device (through a pinned staging tensor); device tensors pass through."""
+        frames = _as_frames(frames)
+        if isinstance(frames, torch.Tensor):
+            return frames.to(self.device).contiguous()
+        frames = np.ascontiguousarray(frames)
+        pinned = torch.from_numpy(frames).pin_memory() if torch.cuda.is_available() else torch.from_numpy(frames)
+        return pinned.to(self.device, non_blocking=True)
+
+    def forward_heads(self, x: torch.Tensor) -> List[torch.Tensor]:
+        """Backbone forward (PyTorch).  Returns the 3 raw head tensors as contiguous float32 NCHW."""
+        with torch.no_grad():
+            if self.channels_last:
+                x = x.contiguous(memory_format=torch.channels_last)
+            if self.autocast_dtype is not None:
+                with torch.autocast("cuda", dtype=self.autocast_dtype):
+                    heads = self.model(x)
+            else:
+                heads = self.model(x)
+        return [h.float().contiguous() for h in heads]
+
+    def _meta_dev(self, plan: LetterboxPlan, cls: int) -> Tuple[np.ndarray, torch.Tensor]:
+        key = (id(plan), cls)
+        if key not in self._meta:
+            m = plan.img_meta(cls)
+            self._meta[key] = (m, self.ctx.struct_to_device(m))
+        return self._meta[key]
+
+    # -------------------------------------------------------------- whole-frame path
+    def detect_device(self, frames_dev: torch.Tensor):
+        """frames_dev uint8[n,H,W,3] on the GPU -> device tensors (xyxy[n,max_det,4], conf, cls, count)."""
+        n, h, w, _ = frames_dev.shape
+        plan = self.plan(n, h, w, _ffi.LB_WHOLE)
+        x = plan.class_views(plan.run(frames_dev))[0]
+        heads = self.forward_heads(x)
+        meta_h, meta_d = self._meta_dev(plan, 0)
+        return self._decode(heads, meta_h, meta_d, n)
+
+    def _decode(self, heads, meta_h, meta_d, n_slots, out=None):
+        # meta stays resident on the device; the host copy is only used by the overflow retry
+        B = heads[0].shape[0]
+        ctx = self.ctx
+        with ctx.lock:
+            ctx._enter()
+            if out is None:
+                out = (ctx.empty((n_slots, self.max_det, 4), torch.float32), ctx.empty((n_slots, self.max_det), torch.float32),
+                       ctx.empty((n_slots, self.max_det), torch.int32), torch.zeros((n_slots,), dtype=torch.int32, device=ctx.device))
+            xyxy, cf, cl, cnt = out
+            args = ctx._level_args(heads)
+            _ffi.check(ctx.lib.hvb_decode_nms(ctx.handle, *args, B, self.nc, self.conf, self.iou, self.max_det,
+                                              int(self.agnostic), _ffi.ptr(meta_d), _ffi.ptr(xyxy), _ffi.ptr(cf), _ffi.ptr(cl),
+                                              _ffi.ptr(cnt)))
+        return xyxy, cf, cl, cnt, (heads, meta_h, meta_d)
+
+    def _retry_overflow(self, xyxy, cf, cl, cnt, state, cnt_host: np.ndarray):
+        """Images that reported -1 (> 1024 candidates) are re-run with the 8192-candidate tier."""
+        heads, meta_h, meta_d = state
+        ctx = self.ctx
+        bad = np.nonzero(cnt_host[meta_h["out_slot"]] < 0)[0].astype(np.int32)
+        if len(bad) == 0:
+            return cnt_host
+        with ctx.lock:
+            ctx._enter()
+            bad_dev = ctx.to_device(bad)
+            _ffi.check(ctx.lib.hvb_decode_nms_large(ctx.handle, *ctx._level_args(heads), _ffi.ptr(bad_dev), int(len(bad)),
+                                                    self.nc, self.conf, self.iou, self.max_det, int(self.agnostic),
+                                                    _ffi.ptr(meta_d), _ffi.ptr(xyxy), _ffi.ptr(cf), _ffi.ptr(cl), _ffi.ptr(cnt)))
+        cnt_host = cnt.cpu().numpy()
+        if (cnt_host[meta_h["out_slot"]] < 0).any():
+            raise _ffi.HvbError(_ffi.HVB_ERR_CAPACITY, "more than 8192 candidates above conf=%g in one image" % self.conf)
+        return cnt_host
+
+    def detect_batch(self, frames) -> List[Detections]:
+        """List of Detections (one per frame), equal to from_ultralytics(model(frame)[0]) per frame."""
+        frames_dev = self.upload(frames)
+        xyxy, cf, cl, cnt, state = self.detect_device(frames_dev)
+        cnt_h = cnt.cpu().numpy()
+        if (cnt_h < 0).any():
+            cnt_h = self._retry_overflow(xyxy, cf, cl, cnt, state, cnt_h)
+        xyxy_h, cf_h, cl_h = xyxy.cpu().numpy(), cf.cpu().numpy(), cl.cpu().numpy()
+        return [self._to_detections(xyxy_h[i, :k], cf_h[i, :k], cl_h[i, :k]) for i, k in enumerate(cnt_h)]
+
+    def _to_detections(self, xyxy, conf, cls) -> Detections:
+        cls = cls.astype(int)
+        names = np.array([self.class_names.get(int(c), str(int(c))) for c in cls], dtype=object) if len(cls) else np.array([], dtype=object)
+        return Detections(xyxy=xyxy.astype(np.float32).reshape(-1, 4).copy(), confidence=conf.astype(np.float32).copy(),
+                          class_id=cls, tracker_id=None, data={"class_name": names})
+
+    def __call__(self, frame: np.ndarray) -> Detections:
+        return self.detect_batch(frame)[0]
+
+    def detect_players(self, frame: np.ndarray) -> Detections:
+        """VideoProcessor.detect_players: detection + the class / confidence mask of main.py:189-193."""
+        d = self(frame)
+        keep = ((d.class_id == PLAYER_CLASS_ID) | (d.class_id == GOALKEEPER_CLASS_ID)) & (d.confidence > self.conf)
+        return d[keep]
+
+    # -------------------------------------------------------------- per-tile callback (compat path)
+    def as_callback(self, imgsz: int = 640):
+        """callback(image_slice) -> Detections for sv.InferenceSlicer(callback=...)."""
+        det = self
+
+        def callback(tile: np.ndarray) -> Detections:
+            old = det.imgsz
+            det.imgsz = imgsz
+            try:
+                return det(np.ascontiguousarray(tile))
+            finally:
+                det.imgsz = old
+        return callback

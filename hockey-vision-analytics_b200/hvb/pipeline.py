@@ -1,0 +1,110 @@
+"""Chunked hot path: what ``VideoProcessor.process_frame`` does between "decoded BGR frame" and
+"detections + team ids" (reference hockey/main.py:259-281), run on a chunk of frames per launch so
+that every libhvb kernel sees enough work to be bandwidth- rather than latency-bound.
+
+    frames --H2D--> K1a letterbox --> YOLOv8 forward (torch) --> K2a decode+NMS
+                 \\-> boxes --> K3a colour features + K3b crop preprocessing --> MobileNetV3 (torch)
+                               --> K4a scale_transform --> similarity rule (+ temporal vote on host)
+
+ByteTrack and the temporal vote are order-dependent per clip and stay on the clip's owner (host).
+"""
+from __future__ import annotations
+
+from typing import Dict, List, Optional, Sequence
+
+import numpy as np
+import torch
+
+from . import _ffi
+from .detect import Detector, PLAYER_CLASS_ID
+from .hybrid import HybridTeamClassifier
+from .runtime import get_context
+from .slicer import B200InferenceSlicer
+
+
+class HotPath:
+    def __init__(self, device="cuda:0", yolo_scale: str = "m", nc: int = 2, imgsz: int = 1280, conf: float = 0.4,
+                 seed: int = 0, trunk: Optional[torch.nn.Module] = None, affinity_mode: int = 0):
+        from .models import build_trunk, build_yolov8
+        self.ctx = get_context(device)
+        self.detector = Detector(build_yolov8(yolo_scale, nc, seed), device, imgsz=imgsz, conf=conf,
+                                 class_names={0: "player", 1: "goalie"})
+        self.classifier = HybridTeamClassifier(device=device, trunk=trunk if trunk is not None else build_trunk(seed, calibrate=True),
+                                               affinity_mode=affinity_mode)
+
+    # ------------------------------------------------------------------ one-off fit (per clip)
+    def fit_from_frames(self, frames_dev: torch.Tensor, boxes: torch.Tensor, frame_idx: torch.Tensor):
+        feats, raw, _ = self.classifier.features_from_frame(frames_dev, boxes, frame_idx)
+        raw_h = raw.cpu().numpy().view(_ffi.COLOR_RAW)[: boxes.shape[0]]
+        self.classifier.fit_features(feats, None, raw_h)
+        return feats
+
+    # ------------------------------------------------------------------ per-chunk hot path
+    def detect_device(self, frames_dev: torch.Tensor):
+        return self.detector.detect_device(frames_dev)
+
+    def team_device(self, frames_dev: torch.Tensor, boxes: torch.Tensor, frame_idx: torch.Tensor) -> torch.Tensor:
+        """Scaled tail features float64[M,10] (what the similarity rule reads), on the device."""
+        clf = self.classifier
+        m = boxes.shape[0]
+        h, w = frames_dev.shape[1], frames_dev.shape[2]
+        cd = self.ctx.crops_from_boxes(boxes, frame_idx, h, w)
+        feats, _, _ = clf._features_device(frames_dev, cd, m)
+        xs = self.ctx.scale_transform(feats, clf.scaler._mean_dev, clf.scaler._scale_dev)
+        return xs[:, -10:].contiguous()
+
+    def process_chunk_device(self, frames_dev: torch.Tensor, team_boxes: Optional[torch.Tensor] = None,
+                             team_frame_idx: Optional[torch.Tensor] = None):
+        """Everything on the device; returns the tensors a caller would copy back."""
+        xyxy, conf, cls, cnt, _ = self.detect_device(frames_dev)
+        if team_boxes is None:
+            # boxes of detected players (class 0), compacted with torch indexing (tiny)
+            n, md = conf.shape
+            valid = (torch.arange(md, device=conf.device)[None, :] < cnt[:, None]) & (cls == PLAYER_CLASS_ID)
+            fi, ki = torch.nonzero(valid, as_tuple=True)
+            team_boxes = xyxy[fi, ki].contiguous()
+            team_frame_idx = fi.to(torch.int32)
+        tail = self.team_device(frames_dev, team_boxes, team_frame_idx) if team_boxes.shape[0] else \
+            torch.zeros((0, 10), dtype=torch.float64, device=frames_dev.device)
+        return dict(xyxy=xyxy, conf=conf, cls=cls, count=cnt, team_tail=tail, team_frame_idx=team_frame_idx)
+
+    @staticmethod
+    def rule(tail: np.ndarray) -> np.ndarray:
+        """HybridTeamClassifier._predict_by_similarity on the scaled tail (team_hybrid.py:264-280)."""
+        if len(tail) == 0:
+            return np.zeros((0,), np.int64)
+        return np.where((tail[:, -1] > 0.3) | (np.argmax(tail[:, 0:3], axis=1) == 0), 0, 1).astype(np.int64)
+
+    def process_chunk(self, frames: np.ndarray, team_boxes: Optional[np.ndarray] = None,
+                      team_frame_idx: Optional[np.ndarray] = None) -> Dict[str, np.ndarray]:
+        """Public host API: host frames in (pinned H2D inside), host results out."""
+        det = self.detector
+        frames_dev = det.upload(frames)
+        tb = ti = None
+        if team_boxes is not None:
+            tb = torch.from_numpy(np.ascontiguousarray(team_boxes, np.float32)).to(self.ctx.device, non_blocking=True)
+            ti = torch.from_numpy(np.ascontiguousarray(team_frame_idx, np.int32)).to(self.ctx.device, non_blocking=True)
+        out = self.process_chunk_device(frames_dev, tb, ti)
+        cnt = out["count"].cpu().numpy()
+        if (cnt < 0).any():
+            raise _ffi.HvbError(_ffi.HVB_ERR_CAPACITY, "candidate overflow in the chunked path; lower the chunk's conf pressure")
+        res = dict(count=cnt, xyxy=out["xyxy"].cpu().numpy(), conf=out["conf"].cpu().numpy(), cls=out["cls"].cpu().numpy())
+        res["team"] = self.rule(out["team_tail"].cpu().numpy())
+        return res
+
+
+class SlicedPuckPath:
+    """4K puck detection through the slicer: K1b -> YOLOv8n forward per shape class -> K2a -> gather -> K2b."""
+
+    def __init__(self, device="cuda:0", yolo_scale: str = "n", nc: int = 1, conf: float = 0.4, seed: int = 0,
+                 uniform_tiles: bool = False, iou_threshold: float = 0.1):
+        from .models import build_yolov8
+        self.detector = Detector(build_yolov8(yolo_scale, nc, seed), device, imgsz=640, conf=conf, class_names={0: "puck"})
+        self.slicer = B200InferenceSlicer(detector=self.detector, slice_wh=(640, 640), overlap_ratio_wh=(0.2, 0.2),
+                                          iou_threshold=iou_threshold, tile_imgsz=640, uniform_tiles=uniform_tiles)
+
+    def process_chunk_device(self, frames_dev: torch.Tensor):
+        return self.slicer.run_device(frames_dev)
+
+    def process_chunk(self, frames: np.ndarray):
+        return self.slicer.run_batch(frames)

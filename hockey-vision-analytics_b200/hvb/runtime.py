@@ -1,0 +1,414 @@
+"""Thin object layer over the C ABI: one `Context` per (process, GPU).
+
+PyTorch is used here only as the device-memory / stream plumbing (tensors own the buffers whose
+``data_ptr()`` is handed to libhvb, and work is enqueued on torch's current stream so it orders
+with the backbone forwards).  All arithmetic on the hot path happens inside libhvb kernels.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import threading
+from typing import List, Optional, Sequence, Tuple
+
+import numpy as np
+import torch
+
+from . import _ffi
+from ._ffi import check, ptr
+
+_contexts = {}
+_contexts_lock = threading.Lock()
+
+
+def get_context(device: int | str | torch.device | None = None) -> "Context":
+    """Process-wide context cache keyed by CUDA device index."""
+    if device is None:
+        idx = torch.cuda.current_device() if torch.cuda.is_available() else 0
+    elif isinstance(device, int):
+        idx = device
+    else:
+        dev = torch.device(device)
+        if dev.type != "cuda":
+            raise _ffi.HvbError(_ffi.HVB_ERR_NO_DEVICE, "hvb runs on CUDA devices only (got %r); there is no CPU fallback" % (device,))
+        idx = dev.index if dev.index is not None else (torch.cuda.current_device() if torch.cuda.is_available() else 0)
+    with _contexts_lock:
+        if idx not in _contexts:
+            _contexts[idx] = Context(idx)
+        return _contexts[idx]
+
+
+class Context:
+    def __init__(self, device: int = 0):
+        self.lib = _ffi.lib()
+        self.device_index = device
+        h = C.c_void_p()
+        check(self.lib.hvb_ctx_create(device, C.byref(h)))
+        self.handle = h
+        self.device = torch.device("cuda", device)
+        self.lock = threading.RLock()
+        n = C.c_int()
+        check(self.lib.hvb_ctx_sm_count(self.handle, C.byref(n)))
+        self.sm_count = n.value
+
+    # ------------------------------------------------------------------ plumbing
+    def _enter(self):
+        """Bind libhvb's stream to torch's current stream on this device."""
+        s = torch.cuda.current_stream(self.device).cuda_stream
+        check(self.lib.hvb_ctx_set_stream(self.handle, C.c_void_p(s)))
+
+    def synchronize(self):
+        with self.lock:
+            self._enter()
+            check(self.lib.hvb_ctx_synchronize(self.handle))
+
+    def launch_count(self, reset: bool = False) -> int:
+        n = C.c_uint64()
+        check(self.lib.hvb_ctx_launch_count(self.handle, 1 if reset else 0, C.byref(n)))
+        return int(n.value)
+
+    def empty(self, shape, dtype) -> torch.Tensor:
+        return torch.empty(shape, dtype=dtype, device=self.device)
+
+    def to_device(self, arr: np.ndarray, non_blocking: bool = False) -> torch.Tensor:
+        t = torch.from_numpy(np.ascontiguousarray(arr))
+        return t.to(self.device, non_blocking=non_blocking)
+
+    def struct_to_device(self, arr: np.ndarray) -> torch.Tensor:
+        """Upload a numpy structured array as raw bytes."""
+        raw = np.ascontiguousarray(arr).view(np.uint8).reshape(-1)
+        return torch.from_numpy(raw.copy()).to(self.device)
+
+    # ------------------------------------------------------------------ K1
+    def letterbox_plan(self, n_frames: int, frame_h: int, frame_w: int, mode: int = _ffi.LB_WHOLE, imgsz: int = 640,
+                       auto: bool = True, stride: int = 32, slice_wh: Tuple[int, int] = (640, 640),
+                       overlap_wh: Tuple[int, int] = (128, 128)) -> "LetterboxPlan":
+        return LetterboxPlan(self, n_frames, frame_h, frame_w, mode, imgsz, auto, stride, slice_wh, overlap_wh)
+
+    # ------------------------------------------------------------------ K2a
+    @staticmethod
+    def _level_args(levels: Sequence[torch.Tensor]):
+        assert len(levels) == 3
+        ptrs = (C.c_void_p * 3)(*[lv.data_ptr() for lv in levels])
+        hs = (C.c_int32 * 3)(*[lv.shape[2] for lv in levels])
+        ws = (C.c_int32 * 3)(*[lv.shape[3] for lv in levels])
+        bs = (C.c_int64 * 3)(*[lv.stride(0) for lv in levels])
+        cs = (C.c_int64 * 3)(*[lv.stride(1) for lv in levels])
+        for lv in levels:
+            if lv.dtype != torch.float32:
+                raise TypeError("head tensors must be float32")
+            # anchors are row-major over (H, W): need stride(2) == W * stride(3)
+            if lv.stride(2) != lv.shape[3] * lv.stride(3):
+                raise ValueError("head tensor spatial dims must be jointly contiguous")
+        as_ = (C.c_int64 * 3)(*[lv.stride(3) for lv in levels])
+        return ptrs, hs, ws, bs, cs, as_
+
+    def decode_nms(self, levels: Sequence[torch.Tensor], nc: int, conf: float, iou: float = 0.7, max_det: int = 300,
+                   agnostic: bool = False, meta: Optional[np.ndarray] = None, n_slots: Optional[int] = None,
+                   out: Optional[Tuple[torch.Tensor, ...]] = None, check_overflow: bool = True):
+        """Returns (xyxy f32[n_slots,max_det,4], conf f32[n_slots,max_det], cls i32[n_slots,max_det], count i32[n_slots])."""
+        B = levels[0].shape[0]
+        if meta is None:
+            raise ValueError("meta (IMG_META per image) is required")
+        n_slots = n_slots if n_slots is not None else B
+        with self.lock:
+            self._enter()
+            meta_dev = meta if isinstance(meta, torch.Tensor) else self.struct_to_device(meta)
+            if out is None:
+                out = (self.empty((n_slots, max_det, 4), torch.float32), self.empty((n_slots, max_det), torch.float32),
+                       self.empty((n_slots, max_det), torch.int32), torch.zeros((n_slots,), dtype=torch.int32, device=self.device))
+            xyxy, cf, cl, cnt = out
+            args = self._level_args(levels)
+            check(self.lib.hvb_decode_nms(self.handle, *args, B, nc, conf, iou, max_det, int(agnostic), ptr(meta_dev),
+                                          ptr(xyxy), ptr(cf), ptr(cl), ptr(cnt)))
+            if check_overflow:
+                # images with more than 1024 candidates report -1: re-run those with the large tier
+                slots = meta["out_slot"] if isinstance(meta, np.ndarray) else None
+                cnt_h = cnt.cpu().numpy()
+                if (cnt_h < 0).any():
+                    if slots is None:
+                        raise _ffi.HvbError(_ffi.HVB_ERR_CAPACITY, "candidate overflow and meta not available on host")
+                    bad = np.nonzero(cnt_h[slots] < 0)[0].astype(np.int32)
+                    bad_dev = self.to_device(bad)
+                    check(self.lib.hvb_decode_nms_large(self.handle, *args, ptr(bad_dev), int(len(bad)), nc, conf, iou,
+                                                        max_det, int(agnostic), ptr(meta_dev), ptr(xyxy), ptr(cf), ptr(cl),
+                                                        ptr(cnt)))
+                    if (cnt.cpu().numpy() < 0).any():
+                        cap = C.c_int()
+                        self.lib.hvb_nms_capacity(C.byref(cap))
+                        raise _ffi.HvbError(_ffi.HVB_ERR_CAPACITY,
+                                            "more than %d candidates above conf in one image" % cap.value)
+        return xyxy, cf, cl, cnt
+
+    def decode_only(self, levels: Sequence[torch.Tensor], nc: int) -> torch.Tensor:
+        B = levels[0].shape[0]
+        A = sum(lv.shape[2] * lv.shape[3] for lv in levels)
+        with self.lock:
+            self._enter()
+            out = self.empty((B, 4 + nc, A), torch.float32)
+            check(self.lib.hvb_decode_only(self.handle, *self._level_args(levels), B, nc, ptr(out)))
+        return out
+
+    def nms_f32(self, boxes: torch.Tensor, scores: torch.Tensor, cls: Optional[torch.Tensor], iou: float,
+                max_det: int = 300, agnostic: bool = False) -> torch.Tensor:
+        n = boxes.shape[0]
+        with self.lock:
+            self._enter()
+            keep = self.empty((max_det,), torch.int32)
+            cnt = torch.zeros((1,), dtype=torch.int32, device=self.device)
+            check(self.lib.hvb_nms_f32(self.handle, ptr(boxes.contiguous()), ptr(scores.contiguous()),
+                                       ptr(cls.contiguous()) if cls is not None else ptr(None), n, iou, max_det,
+                                       int(agnostic or cls is None), ptr(keep), ptr(cnt)))
+            k = int(cnt.item())
+        return keep[:k]
+
+    # ------------------------------------------------------------------ K2b
+    def merge_nms(self, xyxy: torch.Tensor, conf: torch.Tensor, cls: Optional[torch.Tensor], seg_offsets: torch.Tensor,
+                  n_segments: int, n_total: int, iou: float, class_agnostic: bool = False) -> torch.Tensor:
+        with self.lock:
+            self._enter()
+            keep = torch.zeros((max(n_total, 1),), dtype=torch.uint8, device=self.device)
+            check(self.lib.hvb_merge_nms(self.handle, ptr(xyxy), ptr(conf), ptr(cls), ptr(seg_offsets), n_segments, n_total,
+                                         float(iou), int(class_agnostic), ptr(keep)))
+        return keep[:n_total]
+
+    def gather_tiles(self, xyxy, conf, cls, count, slot_off_xy: torch.Tensor, slots_per_frame: int, max_det: int):
+        n_slots = count.shape[0]
+        n_frames = n_slots // slots_per_frame
+        with self.lock:
+            self._enter()
+            cap = n_slots * max_det
+            o_xyxy = self.empty((cap, 4), torch.float64)
+            o_conf = self.empty((cap,), torch.float32)
+            o_cls = self.empty((cap,), torch.int32)
+            o_slot = self.empty((cap,), torch.int32)
+            seg = self.empty((n_frames + 1,), torch.int32)
+            check(self.lib.hvb_gather_tiles(self.handle, ptr(xyxy), ptr(conf), ptr(cls), ptr(count), ptr(slot_off_xy), n_slots,
+                                            slots_per_frame, max_det, ptr(o_xyxy), ptr(o_conf), ptr(o_cls), ptr(o_slot), ptr(seg)))
+        return o_xyxy, o_conf, o_cls, o_slot, seg
+
+    # ------------------------------------------------------------------ K3
+    def crops_from_boxes(self, xyxy: torch.Tensor, frame_idx: Optional[torch.Tensor], frame_h: int, frame_w: int) -> torch.Tensor:
+        n = xyxy.shape[0]
+        with self.lock:
+            self._enter()
+            out = self.empty((max(n, 1) * _ffi.CROP_DESC.itemsize,), torch.uint8)
+            check(self.lib.hvb_crops_from_boxes(self.handle, ptr(xyxy.contiguous()), ptr(frame_idx), n, frame_h, frame_w, ptr(out)))
+        return out
+
+    def color_features(self, pixels: torch.Tensor, crops: torch.Tensor, n: int, roi_mode: int = _ffi.ROI_HYBRID,
+                       want_raw: bool = False, out_feat: Optional[torch.Tensor] = None, feat_stride: int = 49):
+        with self.lock:
+            self._enter()
+            if out_feat is None:
+                out_feat = self.empty((n, 49), torch.float64)
+                feat_stride = 49
+            raw = self.empty((max(n, 1) * _ffi.COLOR_RAW.itemsize,), torch.uint8) if want_raw else None
+            check(self.lib.hvb_color_features(self.handle, ptr(pixels), ptr(crops), n, roi_mode, ptr(out_feat), feat_stride, ptr(raw)))
+        return (out_feat, raw) if want_raw else out_feat
+
+    def cvt_hsv_lab(self, bgr: torch.Tensor):
+        n_px = bgr.numel() // 3
+        with self.lock:
+            self._enter()
+            hsv = torch.empty_like(bgr)
+            lab = torch.empty_like(bgr)
+            check(self.lib.hvb_cvt_hsv_lab(self.handle, ptr(bgr), n_px, ptr(hsv), ptr(lab)))
+        return hsv, lab
+
+    def mnv3_preprocess(self, pixels: torch.Tensor, crops: torch.Tensor, n: int, roi_mode: int = _ffi.ROI_HYBRID,
+                        want_u8: bool = False):
+        with self.lock:
+            self._enter()
+            out = self.empty((n, 3, 128, 64), torch.float32)
+            u8 = self.empty((n, 128, 64, 3), torch.uint8) if want_u8 else None
+            valid = self.empty((max(n, 1),), torch.uint8)
+            check(self.lib.hvb_mnv3_preprocess(self.handle, ptr(pixels), ptr(crops), n, roi_mode, ptr(out), ptr(u8), ptr(valid)))
+        return (out, valid[:n], u8) if want_u8 else (out, valid[:n])
+
+    # ------------------------------------------------------------------ K4
+    def standardize(self, x: torch.Tensor):
+        n, d = x.shape
+        with self.lock:
+            self._enter()
+            mean = self.empty((d,), torch.float64)
+            scale = self.empty((d,), torch.float64)
+            xs = self.empty((n, d), torch.float64)
+            check(self.lib.hvb_standardize(self.handle, ptr(x.contiguous()), n, d, ptr(mean), ptr(scale), ptr(xs)))
+        return mean, scale, xs
+
+    def scale_transform(self, x: torch.Tensor, mean: torch.Tensor, scale: torch.Tensor) -> torch.Tensor:
+        n, d = x.shape
+        with self.lock:
+            self._enter()
+            xs = self.empty((n, d), torch.float64)
+            check(self.lib.hvb_scale_transform(self.handle, ptr(x.contiguous()), n, d, ptr(mean), ptr(scale), ptr(xs)))
+        return xs
+
+    def gram_affinity(self, x: torch.Tensor, gamma: float = 1.0, mode: int = 0, want_d2: bool = True, want_a: bool = True):
+        n, d = x.shape
+        with self.lock:
+            self._enter()
+            d2 = self.empty((n, n), torch.float64) if want_d2 else None
+            a = self.empty((n, n), torch.float64) if want_a else None
+            check(self.lib.hvb_gram_affinity(self.handle, ptr(x.contiguous()), n, d, float(gamma), mode, ptr(d2), ptr(a)))
+        return d2, a
+
+    def gram_tc(self, x: torch.Tensor) -> torch.Tensor:
+        n, d = x.shape
+        with self.lock:
+            self._enter()
+            g = self.empty((n, n), torch.float32)
+            check(self.lib.hvb_gram_tc(self.handle, ptr(x.contiguous()), n, d, ptr(g)))
+        return g
+
+    def iou_cost(self, a: torch.Tensor, b: torch.Tensor, scores: Optional[torch.Tensor], a_off: torch.Tensor,
+                 b_off: torch.Tensor, out_off: torch.Tensor, n_problems: int, max_na: int, max_nb: int, out_size: int,
+                 flags: int = 0):
+        with self.lock:
+            self._enter()
+            out = self.empty((max(out_size, 1),), torch.float64)
+            check(self.lib.hvb_iou_cost(self.handle, ptr(a), ptr(b), ptr(scores), ptr(a_off), ptr(b_off), ptr(out_off),
+                                        n_problems, max_na, max_nb, flags, ptr(out)))
+        return out
+
+    # ------------------------------------------------------------------ host-buffer entry points
+    def color_features_host(self, pixels: np.ndarray, crops: np.ndarray, roi_mode: int = _ffi.ROI_HYBRID, want_raw: bool = False):
+        n = len(crops)
+        feat = np.empty((n, 49), np.float64)
+        raw = np.zeros((n,), _ffi.COLOR_RAW) if want_raw else None
+        if n:
+            with self.lock:
+                self._enter()
+                check(self.lib.hvb_color_features_host(self.handle, ptr(pixels), pixels.nbytes, ptr(crops), n, roi_mode,
+                                                       ptr(feat), ptr(raw)))
+        return (feat, raw) if want_raw else feat
+
+    def mnv3_preprocess_host(self, pixels: np.ndarray, crops: np.ndarray, roi_mode: int = _ffi.ROI_HYBRID):
+        n = len(crops)
+        out = np.empty((n, 3, 128, 64), np.float32)
+        valid = np.zeros((n,), np.uint8)
+        if n:
+            with self.lock:
+                self._enter()
+                check(self.lib.hvb_mnv3_preprocess_host(self.handle, ptr(pixels), pixels.nbytes, ptr(crops), n, roi_mode,
+                                                        ptr(out), ptr(valid)))
+        return out, valid
+
+    def merge_nms_host(self, xyxy: np.ndarray, conf: np.ndarray, cls: Optional[np.ndarray], iou: float,
+                       class_agnostic: bool = False) -> np.ndarray:
+        n = len(xyxy)
+        keep = np.zeros((n,), np.uint8)
+        if n:
+            xyxy = np.ascontiguousarray(xyxy, np.float64)
+            conf = np.ascontiguousarray(conf, np.float32)
+            cls32 = np.ascontiguousarray(cls, np.int32) if cls is not None else None
+            with self.lock:
+                self._enter()
+                check(self.lib.hvb_merge_nms_host(self.handle, ptr(xyxy), ptr(conf), ptr(cls32), n, float(iou),
+                                                  int(class_agnostic), ptr(keep)))
+            if (keep == 0xFF).any():
+                raise _ffi.HvbError(_ffi.HVB_ERR_CAPACITY, "merge NMS segment exceeds the on-chip capacity")
+        return keep.astype(bool)
+
+    def iou_cost_host(self, a: np.ndarray, b: np.ndarray, scores: Optional[np.ndarray] = None) -> np.ndarray:
+        a, b = np.asarray(a), np.asarray(b)
+        flags = (1 if a.dtype == np.float32 else 0) | (2 if b.dtype == np.float32 else 0)
+        a = np.ascontiguousarray(a, np.float64).reshape(-1, 4)
+        b = np.ascontiguousarray(b, np.float64).reshape(-1, 4)
+        out = np.zeros((len(a), len(b)), np.float64)
+        if len(a) and len(b):
+            sc = np.ascontiguousarray(scores, np.float64) if scores is not None else None
+            with self.lock:
+                self._enter()
+                check(self.lib.hvb_iou_cost_host(self.handle, ptr(a), len(a), ptr(b), len(b), ptr(sc), flags, ptr(out)))
+        return out
+
+    def gram_affinity_host(self, x: np.ndarray, gamma: float = 1.0, mode: int = 0):
+        x = np.ascontiguousarray(x, np.float64)
+        n, d = x.shape
+        d2 = np.empty((n, n), np.float64)
+        a = np.empty((n, n), np.float64)
+        with self.lock:
+            self._enter()
+            check(self.lib.hvb_gram_affinity_host(self.handle, ptr(x), n, d, float(gamma), mode, ptr(d2), ptr(a)))
+        return d2, a
+
+
+class LetterboxPlan:
+    """hvb_lb_plan: geometry for a chunk of equally sized frames; `run` is one kernel launch."""
+
+    def __init__(self, ctx: Context, n_frames, frame_h, frame_w, mode, imgsz, auto, stride, slice_wh, overlap_wh):
+        self.ctx = ctx
+        self.n_frames, self.frame_h, self.frame_w, self.mode, self.imgsz = n_frames, frame_h, frame_w, mode, imgsz
+        h = C.c_void_p()
+        with ctx.lock:
+            check(ctx.lib.hvb_lb_plan_create(ctx.handle, n_frames, frame_h, frame_w, mode, imgsz, int(auto), stride,
+                                             slice_wh[0], slice_wh[1], overlap_wh[0], overlap_wh[1], C.byref(h)))
+        self.handle = h
+        n = C.c_int()
+        check(ctx.lib.hvb_lb_plan_num_classes(h, C.byref(n)))
+        self.classes = np.zeros((n.value,), _ffi.LB_CLASS)
+        for i in range(n.value):
+            check(ctx.lib.hvb_lb_plan_get_class(h, i, ptr(self.classes[i:i + 1])))
+        check(ctx.lib.hvb_lb_plan_num_tiles(h, C.byref(n)))
+        self.tiles = np.zeros((n.value,), _ffi.LB_TILE)
+        check(ctx.lib.hvb_lb_plan_get_tiles(h, ptr(self.tiles), n.value))
+        self.tiles_per_frame = n.value // n_frames
+        f = C.c_int64()
+        check(ctx.lib.hvb_lb_plan_out_floats(h, C.byref(f)))
+        self.out_floats = int(f.value)
+        r, w = C.c_int64(), C.c_int64()
+        check(ctx.lib.hvb_lb_plan_bytes(h, C.byref(r), C.byref(w)))
+        self.read_bytes, self.write_bytes = int(r.value), int(w.value)
+
+    def __del__(self):
+        try:
+            if getattr(self, "handle", None):
+                self.ctx.lib.hvb_lb_plan_destroy(self.handle)
+                self.handle = None
+        except Exception:
+            pass
+
+    def class_views(self, out: torch.Tensor) -> List[torch.Tensor]:
+        """Views of the flat output buffer as one [batch,3,out_h,out_w] tensor per shape class."""
+        views = []
+        for c in self.classes:
+            numel = int(c["batch"]) * 3 * int(c["out_h"]) * int(c["out_w"])
+            o = int(c["out_offset"])
+            views.append(out[o:o + numel].view(int(c["batch"]), 3, int(c["out_h"]), int(c["out_w"])))
+        return views
+
+    def run(self, frames: torch.Tensor, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+        """frames: uint8[n_frames, H, W, 3] on the context's GPU -> flat float32 buffer."""
+        assert frames.dtype == torch.uint8 and frames.is_contiguous()
+        assert tuple(frames.shape) == (self.n_frames, self.frame_h, self.frame_w, 3), frames.shape
+        with self.ctx.lock:
+            self.ctx._enter()
+            if out is None:
+                out = self.ctx.empty((self.out_floats,), torch.float32)
+            check(self.ctx.lib.hvb_lb_plan_run(self.handle, ptr(frames), ptr(out)))
+        return out
+
+    def run_u8(self, frames: torch.Tensor) -> torch.Tensor:
+        assert frames.dtype == torch.uint8 and frames.is_contiguous()
+        with self.ctx.lock:
+            self.ctx._enter()
+            out = self.ctx.empty((self.out_floats,), torch.uint8)
+            check(self.ctx.lib.hvb_lb_plan_run_u8(self.handle, ptr(frames), ptr(out)))
+        return out
+
+    def img_meta(self, cls: int, slot_of_tile=None) -> np.ndarray:
+        """IMG_META rows for the batch of shape class `cls`, in batch order.  out_slot defaults to
+        frame * tiles_per_frame + tile (slicer order), the layout hvb_gather_tiles expects."""
+        t = self.tiles[self.tiles["cls"] == cls]
+        t = t[np.argsort(t["batch_index"], kind="stable")]
+        m = np.zeros((len(t),), _ffi.IMG_META)
+        m["gain"], m["pad_x"], m["pad_y"] = t["gain"], t["pad_x"], t["pad_y"]
+        m["clip_w"], m["clip_h"] = t["src_w"], t["src_h"]
+        m["off_x"], m["off_y"] = t["src_x"], t["src_y"]
+        m["out_slot"] = t["frame"] * self.tiles_per_frame + t["tile"]
+        return m
+
+    def slot_offsets(self) -> np.ndarray:
+        """float32[n_slots, 2] tile offsets in slot order (frame-major, slicer tile order)."""
+        return np.stack([self.tiles["src_x"], self.tiles["src_y"]], 1).astype(np.float32)

@@ -1,0 +1,146 @@
+"""B200InferenceSlicer — drop-in for ``sv.InferenceSlicer`` on the puck path the reference documents
+(README.md:25, CLAUDE.md:55: 640-px slices, 0.2 overlap).
+
+Two ways to use it, same constructor surface as supervision's:
+
+  * compat:  ``B200InferenceSlicer(callback=fn, ...)(frame)`` — `fn(tile) -> Detections` is called per
+    tile on host views exactly like supervision does (thread_workers=1 order); move / merge / NMS
+    run through the K2b kernel.
+  * fast:    ``B200InferenceSlicer(detector=Detector(...), ...)(frame)`` or ``.run_batch(frames)`` —
+    tiles never exist on the host: K1b slices + letterboxes every tile of every frame in ONE launch
+    into per-shape-class NCHW batches, the YOLO forward runs per class batch, K2a decodes + NMSes
+    every tile, hvb_gather_tiles moves/merges per frame and K2b applies the cross-slice NMS.
+"""
+from __future__ import annotations
+
+from typing import Callable, List, Optional, Tuple
+
+import numpy as np
+import torch
+
+from . import _ffi
+from .detections import Detections, crop_image
+from .detect import Detector
+
+
+class OverlapFilter:
+    NONE = "none"
+    NON_MAX_SUPPRESSION = "non_max_suppression"
+    NON_MAX_MERGE = "non_max_merge"
+
+
+def generate_offsets(resolution_wh, slice_wh, overlap_ratio_wh, overlap_wh) -> np.ndarray:
+    """Tile rectangles int[n,4] — InferenceSlicer._generate_offset (clipped edge tiles, y-major)."""
+    sw, sh = slice_wh
+    W, H = resolution_wh
+    if overlap_wh is None:
+        ow, oh = int(overlap_ratio_wh[0] * sw), int(overlap_ratio_wh[1] * sh)
+    else:
+        ow, oh = overlap_wh
+    xs = np.arange(0, W, sw - ow)
+    ys = np.arange(0, H, sh - oh)
+    xmin, ymin = np.meshgrid(xs, ys)
+    xmax = np.clip(xmin + sw, 0, W)
+    ymax = np.clip(ymin + sh, 0, H)
+    return np.stack([xmin, ymin, xmax, ymax], -1).reshape(-1, 4)
+
+
+class B200InferenceSlicer:
+    def __init__(self, callback: Optional[Callable[[np.ndarray], Detections]] = None,
+                 slice_wh: Tuple[int, int] = (320, 320), overlap_ratio_wh: Optional[Tuple[float, float]] = (0.2, 0.2),
+                 overlap_wh: Optional[Tuple[int, int]] = None, overlap_filter: str = OverlapFilter.NON_MAX_SUPPRESSION,
+                 iou_threshold: float = 0.5, thread_workers: int = 1, *, detector: Optional[Detector] = None,
+                 tile_imgsz: int = 640, uniform_tiles: bool = False, class_agnostic: bool = False):
+        if callback is None and detector is None:
+            raise ValueError("either `callback` (compat path) or `detector` (device path) is required")
+        if overlap_filter == OverlapFilter.NON_MAX_MERGE:
+            raise NotImplementedError("NON_MAX_MERGE is not on the reference's path (it documents NMS)")
+        self.callback, self.detector = callback, detector
+        self.slice_wh, self.overlap_ratio_wh, self.overlap_wh = tuple(slice_wh), overlap_ratio_wh, overlap_wh
+        self.overlap_filter, self.iou_threshold = overlap_filter, iou_threshold
+        self.thread_workers = thread_workers          # accepted for signature parity; tiles run in slicer order
+        self.tile_imgsz, self.uniform_tiles, self.class_agnostic = tile_imgsz, uniform_tiles, class_agnostic
+
+    def _overlap(self) -> Tuple[int, int]:
+        if self.overlap_wh is not None:
+            return int(self.overlap_wh[0]), int(self.overlap_wh[1])
+        return int(self.overlap_ratio_wh[0] * self.slice_wh[0]), int(self.overlap_ratio_wh[1] * self.slice_wh[1])
+
+    # ------------------------------------------------------------------ compat path
+    def _call_with_callback(self, image: np.ndarray) -> Detections:
+        h, w = image.shape[:2]
+        offsets = generate_offsets((w, h), self.slice_wh, self.overlap_ratio_wh, self.overlap_wh)
+        parts = []
+        for off in offsets:
+            det = self.callback(crop_image(image, off))
+            if len(det):
+                shift = np.array([off[0], off[1], off[0], off[1]])
+                det = Detections(xyxy=det.xyxy + shift, confidence=det.confidence, class_id=det.class_id,
+                                 tracker_id=det.tracker_id, data=dict(det.data))
+            parts.append(det)
+        merged = Detections.merge(parts)
+        if self.overlap_filter == OverlapFilter.NONE or len(merged) == 0:
+            return merged
+        ctx = self.detector.ctx if self.detector is not None else None
+        if ctx is None:
+            from .runtime import get_context
+            ctx = get_context()
+        keep = ctx.merge_nms_host(merged.xyxy, merged.confidence, None if self.class_agnostic else merged.class_id,
+                                  self.iou_threshold, self.class_agnostic)
+        return merged[keep]
+
+    # ------------------------------------------------------------------ device path
+    def run_device(self, frames_dev: torch.Tensor):
+        """frames_dev uint8[n,H,W,3] -> (xyxy f64[total,4], conf f32, cls i32, keep u8, seg i32[n+1]) on device."""
+        det = self.detector
+        ctx = det.ctx
+        n, h, w, _ = frames_dev.shape
+        mode = _ffi.LB_SLICE_UNIFORM if self.uniform_tiles else _ffi.LB_SLICE_EXACT
+        plan = det.plan(n, h, w, mode, self.tile_imgsz, self.slice_wh, self._overlap())
+        views = plan.class_views(plan.run(frames_dev))
+        n_slots = n * plan.tiles_per_frame
+        out = (ctx.empty((n_slots, det.max_det, 4), torch.float32), ctx.empty((n_slots, det.max_det), torch.float32),
+               ctx.empty((n_slots, det.max_det), torch.int32), torch.zeros((n_slots,), dtype=torch.int32, device=ctx.device))
+        states = []
+        for c, x in enumerate(views):
+            heads = det.forward_heads(x)
+            meta_h, meta_d = det._meta_dev(plan, c)
+            *_, state = det._decode(heads, meta_h, meta_d, n_slots, out=out)
+            states.append(state)
+        xyxy, cf, cl, cnt = out
+        # overflow (> 1024 candidates in a tile) is rare: one small D2H of the counts decides
+        cnt_h = cnt.cpu().numpy()
+        if (cnt_h < 0).any():
+            for state in states:
+                cnt_h = det._retry_overflow(xyxy, cf, cl, cnt, state, cnt_h)
+        key = ("slot_off", id(plan))
+        if key not in det._meta:
+            det._meta[key] = ctx.to_device(plan.slot_offsets())
+        g_xyxy, g_conf, g_cls, g_slot, seg = ctx.gather_tiles(xyxy, cf, cl, cnt, det._meta[key], plan.tiles_per_frame, det.max_det)
+        total = int(np.maximum(cnt_h, 0).sum())
+        if self.overlap_filter == OverlapFilter.NONE or total == 0:
+            keep = torch.ones((total,), dtype=torch.uint8, device=ctx.device)
+        else:
+            keep = ctx.merge_nms(g_xyxy, g_conf, None if self.class_agnostic else g_cls, seg, n, total, self.iou_threshold,
+                                 self.class_agnostic)
+        return g_xyxy[:total], g_conf[:total], g_cls[:total], keep, seg
+
+    def run_batch(self, frames) -> List[Detections]:
+        det = self.detector
+        frames_dev = det.upload(frames)
+        xyxy, conf, cls, keep, seg = self.run_device(frames_dev)
+        xyxy_h, conf_h, cls_h, keep_h, seg_h = (t.cpu().numpy() for t in (xyxy, conf, cls, keep, seg))
+        if (keep_h == 0xFF).any():
+            raise _ffi.HvbError(_ffi.HVB_ERR_CAPACITY, "merged detections of one frame exceed the on-chip NMS capacity")
+        out = []
+        for f in range(len(seg_h) - 1):
+            lo, hi = int(seg_h[f]), int(seg_h[f + 1])
+            k = keep_h[lo:hi].astype(bool)
+            out.append(det._to_detections(xyxy_h[lo:hi][k], conf_h[lo:hi][k], cls_h[lo:hi][k]))
+            out[-1].xyxy = xyxy_h[lo:hi][k].copy()     # float64 like supervision's moved boxes
+        return out
+
+    def __call__(self, image: np.ndarray) -> Detections:
+        if self.callback is not None:
+            return self._call_with_callback(image)
+        return self.run_batch(image)[0]

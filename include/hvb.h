@@ -263,10 +263,12 @@ HVB_API int hvb_gram_tc(hvb_ctx* ctx, const double* x_dev, int n, int d, float* 
  * cost[t,d] = 1 - IoU(a[t], b[d])  (nan -> IoU 0), optionally 1 - IoU*score[d].  float64 like numpy.
  * Batched over independent problems (clips): problem p uses rows a_off[p]..a_off[p+1]-1 of a,
  * b_off[p]..b_off[p+1]-1 of b and writes a dense [na_p, nb_p] block at out_off[p].
+ * flags bit 0 / bit 1: the a / b boxes came from a float32 array — numpy then computes that side's
+ * area in float32 before promoting (detections are float32, Kalman track boxes float64).
  */
 HVB_API int hvb_iou_cost(hvb_ctx* ctx, const double* a_dev, const double* b_dev, const double* scores_dev,
                  const int32_t* a_off_dev, const int32_t* b_off_dev, const int64_t* out_off_dev,
-                 int n_problems, int max_na, int max_nb, double* out_dev);
+                 int n_problems, int max_na, int max_nb, int flags, double* out_dev);
 
 /* ---------------------------------------------------------------- host-buffer entry points
  * What a non-Python binding (cgo / JNI / N-API) would call: host in, host out, synchronous.
@@ -281,7 +283,7 @@ HVB_API int hvb_merge_nms_host(hvb_ctx* ctx, const double* xyxy_host, const floa
                        const int32_t* cls_host, int n, double iou_thres, int class_agnostic,
                        uint8_t* out_keep_host);
 HVB_API int hvb_iou_cost_host(hvb_ctx* ctx, const double* a_host, int na, const double* b_host, int nb,
-                      const double* scores_host /*or NULL*/, double* out_host /*[na,nb]*/);
+                      const double* scores_host /*or NULL*/, int flags, double* out_host /*[na,nb]*/);
 HVB_API int hvb_gram_affinity_host(hvb_ctx* ctx, const double* x_host, int n, int d, double gamma, int mode,
                            double* out_d2_host /*or NULL*/, double* out_a_host /*or NULL*/);
 

@@ -126,9 +126,11 @@ def run_slicer(image: np.ndarray, callback: Callable[[np.ndarray], Tuple[np.ndar
 
 # ------------------------------------------------------------------ ByteTrack matching costs
 def iou_distance(atlbrs: np.ndarray, btlbrs: np.ndarray) -> np.ndarray:
-    """1 - IoU(track tlbr, det tlbr) as float (matching.iou_distance)."""
-    a = np.asarray(atlbrs, dtype=float).reshape(-1, 4)
-    b = np.asarray(btlbrs, dtype=float).reshape(-1, 4)
+    """1 - box_iou_batch(np.asarray(atlbrs), np.asarray(btlbrs)) (matching.iou_distance).  The dtypes
+    are NOT unified first: detection boxes are float32 (their area is then computed in float32 by
+    numpy before promotion), Kalman track boxes float64."""
+    a = np.asarray(atlbrs).reshape(-1, 4)
+    b = np.asarray(btlbrs).reshape(-1, 4)
     if a.shape[0] == 0 or b.shape[0] == 0:
         return np.zeros((a.shape[0], b.shape[0]), dtype=float)
     return 1 - box_iou_batch(a, b)
