@@ -16,6 +16,7 @@ void hvb_set_error(const char* fmt, ...) {
 }
 
 int hvb_cuda_fail(cudaError_t e, const char* what, const char* file, int line) {
+    (void)cudaGetLastError();   // clear the non-sticky error state so it is not re-reported by a later launch check
     hvb_set_error("CUDA error %d (%s) at %s:%d in `%s`", (int)e, cudaGetErrorString(e), file, line, what);
     return (e == cudaErrorNoDevice || e == cudaErrorInsufficientDriver) ? HVB_ERR_NO_DEVICE : HVB_ERR_CUDA;
 }
@@ -133,7 +134,13 @@ int hvb_ctx_destroy(hvb_ctx* ctx) {
 
 int hvb_ctx_set_stream(hvb_ctx* ctx, void* cuda_stream) {
     if (!ctx) { hvb_set_error("null context"); return HVB_ERR_ARG; }
-    ctx->stream = cuda_stream ? (cudaStream_t)cuda_stream : ctx->own_stream;
+    ctx->stream = (cudaStream_t)cuda_stream;      // NULL is the legacy default stream (what torch uses by default)
+    return HVB_OK;
+}
+
+int hvb_ctx_use_own_stream(hvb_ctx* ctx) {
+    if (!ctx) { hvb_set_error("null context"); return HVB_ERR_ARG; }
+    ctx->stream = ctx->own_stream;
     return HVB_OK;
 }
 

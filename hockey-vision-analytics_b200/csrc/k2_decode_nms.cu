@@ -337,6 +337,10 @@ int fill_levels(Levels& L, const float* const level_dev[3], const int32_t level_
 
 template <typename K>
 int set_smem(K kernel, size_t bytes) {
+    if (bytes > 227 * 1024) {
+        hvb_set_error("NMS needs %zu bytes of shared memory (> 227 KB): lower max_det for images with more than 1024 candidates", bytes);
+        return HVB_ERR_CAPACITY;
+    }
     if (bytes > 48 * 1024) HVB_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes));
     return HVB_OK;
 }

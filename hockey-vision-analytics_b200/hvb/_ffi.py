@@ -53,6 +53,7 @@ PROTOTYPES = {
     "hvb_ctx_create": [_i, _pp],
     "hvb_ctx_destroy": [_vp],
     "hvb_ctx_set_stream": [_vp, _vp],
+    "hvb_ctx_use_own_stream": [_vp],
     "hvb_ctx_get_stream": [_vp, _pp],
     "hvb_ctx_synchronize": [_vp],
     "hvb_ctx_sm_count": [_vp, C.POINTER(_i)],

@@ -55,7 +55,8 @@ class HybridTeamClassifier:
         if trunk is None:
             from .models import build_trunk
             trunk = build_trunk(seed)
-        self.feature_extractor = trunk.to(self.ctx.device).eval()
+        import copy
+        self.feature_extractor = copy.deepcopy(trunk).to(self.ctx.device).eval()    # the caller's module stays where it is
         self.scaler = _Scaler()
         self.player_history: Dict[int, List[int]] = defaultdict(list)
         self.history_window = 15

@@ -55,7 +55,8 @@ HVB_API const char* hvb_last_error(void);
 HVB_API int hvb_device_count(int* out_count);                       /* never fails hard: count 0 without a GPU */
 HVB_API int hvb_ctx_create(int device, hvb_ctx** out_ctx);
 HVB_API int hvb_ctx_destroy(hvb_ctx* ctx);
-HVB_API int hvb_ctx_set_stream(hvb_ctx* ctx, void* cuda_stream);    /* NULL -> the context's own stream    */
+HVB_API int hvb_ctx_set_stream(hvb_ctx* ctx, void* cuda_stream);    /* cudaStream_t; NULL = the legacy default stream */
+HVB_API int hvb_ctx_use_own_stream(hvb_ctx* ctx);                   /* back to the context's private non-blocking stream (the initial state) */
 HVB_API int hvb_ctx_get_stream(hvb_ctx* ctx, void** out_stream);
 HVB_API int hvb_ctx_synchronize(hvb_ctx* ctx);
 HVB_API int hvb_ctx_sm_count(hvb_ctx* ctx, int* out_sms);

@@ -124,6 +124,6 @@ def test_nms_idempotent_property(ctx):
     rng = np.random.default_rng(9)
     boxes, scores = random_boxes(rng, 4000, 1920, 1080, 20, 120)
     tb, ts = torch.from_numpy(boxes).cuda(), torch.from_numpy(scores).cuda()
-    k1 = ctx.nms_f32(tb, ts, None, 0.5, 2048, True)
-    k2 = ctx.nms_f32(tb[k1.long()], ts[k1.long()], None, 0.5, 2048, True)
+    k1 = ctx.nms_f32(tb, ts, None, 0.5, 1024, True)
+    k2 = ctx.nms_f32(tb[k1.long()], ts[k1.long()], None, 0.5, 1024, True)
     assert np.array_equal(k2.cpu().numpy(), np.arange(len(k1)))

@@ -110,7 +110,10 @@ def test_slicer_device_path_matches_restated_inference_slicer(ctx):
                 cx, cy = self.rng.uniform(10, W - 10, k), self.rng.uniform(10, H - 10, k)
                 sz = self.rng.uniform(8, 30, k)
                 gt = np.stack([cx - sz, cy - sz, cx + sz, cy + sz], 1)
-                self.cache[key] = [torch.from_numpy(t) for t in planted_head(self.rng, lv, 1, gt, np.zeros(k, int), dup=2)]
+                # scores must be distinct ACROSS tiles too: supervision's np.flip(argsort) has no defined tie order
+                lo, hi = 0.45 + self.rng.uniform(0, 0.02), 0.95 + self.rng.uniform(0, 0.02)
+                self.cache[key] = [torch.from_numpy(t) for t in
+                                   planted_head(self.rng, lv, 1, gt, np.zeros(k, int), dup=2, conf_lo=lo, conf_hi=hi)]
             return self.cache[key]
 
         def forward(self, x):
