@@ -7,14 +7,18 @@
 // (on the host, once per geometry), horizontal fraction clamped at the borders, vertical indices
 // clamped with the fraction kept, the (>>4, >>16, +2 >>2) vertical rounding, and the 2x2
 // area-average shortcut when both scale factors are exactly 2.  The float stage reproduces
-// numpy/torch `x / 255` in float32 exactly with a reciprocal multiply plus two FMA corrections
-// (verified exhaustively for the 256 possible inputs).
+// numpy/torch `x / 255` in float32 exactly with ONE multiply: float(v) * 0x1.010102p-8 rounded
+// toward zero equals float(v) / 255 (round-to-nearest) for every v in [0, 255] (checked
+// exhaustively on the host and again by tests/test_gpu_letterbox.py).
 //
 // One launch covers a chunk of frames: grid = blocks_per_frame x n_frames.  Each CTA produces an
-// 8-row x 256-column block of one tile's output: it first stages the source bytes the block needs
-// into shared memory with coalesced 128-bit loads (the source rows are shared by the 3 output
-// planes, by neighbouring output pixels and by the two taps of neighbouring output rows), then
-// every thread produces 4 consecutive pixels x 3 planes and writes them with 128-bit stores.
+// 16-row x 256-column block of one tile's output.  It first stages the source pixels the block
+// needs into shared memory AS 32-BIT PIXEL WORDS (B | G<<8 | R<<16): 4-pixel groups are fetched
+// with three aligned 32-bit loads and re-packed with byte permutes into one 128-bit shared store,
+// so that afterwards one LDS.32 fetches a whole pixel.  The 2-tap horizontal filter of a channel is
+// then ONE dp2a (two 16-bit coefficients x two 8-bit samples) after a byte permute that pairs the
+// samples of the two taps; every thread owns ONE output column and walks down the 16 rows of the block,
+// reusing the horizontal result of a source row shared by consecutive output rows; a warp writes 128 contiguous bytes per plane per row.
 #include "hvb_common.cuh"
 
 #include <algorithm>
@@ -23,9 +27,9 @@
 
 namespace {
 
-constexpr int kTH = 8;          // output rows per CTA
+constexpr int kTH = 16;         // output rows per CTA
 constexpr int kTW = 256;        // output columns per CTA
-constexpr int kThreads = 256;   // 64 column groups of 4 px  x  4 row groups (2 rows each)
+constexpr int kThreads = 256;   // one thread per output column of the block
 
 enum { MODE_COPY = 0, MODE_LINEAR = 1, MODE_AREA2 = 2 };
 
@@ -36,179 +40,216 @@ struct LbJob {
     int32_t src_w, src_h, new_w, new_h, top, left, out_h, out_w;
     int32_t mode;
     int32_t xtab, ytab;  // offsets (entries) of this job's coefficient tables
-    int32_t pad_;
+    int32_t row_px;      // pixels from the tile origin to the end of the frame row
+    int32_t vec_ok;      // 4-pixel groups of this tile are 4-byte aligned in global memory
+    int32_t pad_[3];
 };
 
-struct XCoef { int32_t sx; int16_t a0, a1; };            // 8 bytes
-struct YCoef { int32_t r0, r1; int32_t b0, b1; };        // 16 bytes
+struct XCoef { int32_t sx; uint32_t apk; };              // apk = a0 | a1 << 16
+struct __align__(16) YCoef { int32_t r0, r1; int32_t b0, b1; };
 
 __device__ __forceinline__ float u8_over_255(int v) {
-    // float32(v) / 255.0f, correctly rounded: q = v*rcp; r = v - q*255; q += r*rcp
-    const float rcp = 1.0f / 255.0f;
-    float x = __int_as_float(0x4B000000 | v) - 8388608.0f;
-    float q = __fmul_rn(x, rcp);
-    float r = __fmaf_rn(-q, 255.0f, x);
-    return __fmaf_rn(r, rcp, q);
+    return __fmul_rz(__int2float_rn(v), 0x1.010102p-8f);   // == float(v) / 255.0f for 0 <= v <= 255
+}
+
+// Horizontal 2-tap filter of one source row for this thread's column: three dp2a, pre-shifted by 4
+// like OpenCV's vertical pass expects.
+__device__ __forceinline__ uint32_t lds32(uint32_t shared_byte_addr) {
+    uint32_t v;
+    asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(shared_byte_addr));
+    return v;
+}
+
+__device__ __forceinline__ void lb_hrow(uint32_t p0, uint32_t p1, uint32_t apk, uint32_t (&h)[3]) {
+    const uint32_t bg = __byte_perm(p0, p1, 0x5140), rr = __byte_perm(p0, p1, 0x0062);
+    h[0] = __dp2a_lo(apk, bg, 0u) >> 4;
+    h[1] = __dp2a_hi(apk, bg, 0u) >> 4;
+    h[2] = __dp2a_lo(apk, rr, 0u) >> 4;
 }
 
 template <bool U8OUT>
-__global__ void __launch_bounds__(kThreads)
+__device__ __forceinline__ void lb_store(float* __restrict__ tile_f32, uint8_t* __restrict__ tile_u8, int o, int plane,
+                                         int vb, int vg, int vr) {
+    if (U8OUT) {
+        uint8_t* p = tile_u8 + o * 3;
+        p[0] = (uint8_t)vb; p[1] = (uint8_t)vg; p[2] = (uint8_t)vr;
+    } else {                                   // planes are R,G,B = source channels 2,1,0
+        tile_f32[o] = u8_over_255(vr);
+        tile_f32[o + plane] = u8_over_255(vg);
+        tile_f32[o + 2 * plane] = u8_over_255(vb);
+    }
+}
+
+template <bool U8OUT>
+__global__ void __launch_bounds__(kThreads, 5)
 letterbox_kernel(const uint8_t* __restrict__ frames, int64_t frame_bytes, int32_t pitch,
                  const LbJob* __restrict__ jobs, const uint32_t* __restrict__ blk2job, int blocks_per_frame,
-                 const XCoef* __restrict__ xtab, const YCoef* __restrict__ ytab, int smem_row_stride,
+                 const XCoef* __restrict__ xtab, const YCoef* __restrict__ ytab, int smem_row_words,
                  float* __restrict__ out_f32, uint8_t* __restrict__ out_u8) {
-    extern __shared__ __align__(16) uint8_t smem[];
-    __shared__ int s_geo[8];   // sx_lo, sx_hi, sy_lo, sy_hi
+    extern __shared__ __align__(16) uint32_t spix[];      // [rows][smem_row_words] pixel words
+    __shared__ YCoef s_y[kTH];                            // vertical coefficients of the block's rows (smem-row relative)
 
     const int frame = blockIdx.x / blocks_per_frame;
     const uint32_t packed = __ldg(blk2job + (blockIdx.x - frame * blocks_per_frame));
-    const LbJob job = jobs[packed >> 24];
+    const LbJob& job = jobs[packed >> 24];
     const int oy0 = ((packed >> 12) & 0xfff) * kTH;
     const int ox0 = (packed & 0xfff) * kTW;
+    const int mode = job.mode, top = job.top, left = job.left, new_w = job.new_w, new_h = job.new_h;
+    const int out_w = job.out_w, out_h = job.out_h, src_w = job.src_w;
+    const XCoef* xt = xtab + job.xtab;
+    const YCoef* yt = ytab + job.ytab;
 
     // valid (non-padding) output window of this block, in resized-image coordinates
-    const int dy_lo = max(oy0 - job.top, 0), dy_hi = min(oy0 + kTH - job.top, job.new_h);     // [lo,hi)
-    const int dx_lo = max(ox0 - job.left, 0), dx_hi = min(ox0 + kTW - job.left, job.new_w);
+    const int dy_lo = max(oy0 - top, 0), dy_hi = min(oy0 + kTH - top, new_h);     // [lo,hi)
+    const int dx_lo = max(ox0 - left, 0), dx_hi = min(ox0 + kTW - left, new_w);
     const bool has_src = dy_lo < dy_hi && dx_lo < dx_hi;
 
-    if (threadIdx.x == 0 && has_src) {
-        int sx_lo, sx_hi, sy_lo, sy_hi;
-        if (job.mode == MODE_LINEAR) {
-            sx_lo = xtab[job.xtab + dx_lo].sx;
-            sx_hi = min(xtab[job.xtab + dx_hi - 1].sx + 1, job.src_w - 1);
-            sy_lo = ytab[job.ytab + dy_lo].r0;
-            sy_hi = ytab[job.ytab + dy_hi - 1].r1;
-        } else if (job.mode == MODE_AREA2) {
-            sx_lo = 2 * dx_lo; sx_hi = 2 * dx_hi - 1; sy_lo = 2 * dy_lo; sy_hi = 2 * dy_hi - 1;
-        } else {
-            sx_lo = dx_lo; sx_hi = dx_hi - 1; sy_lo = dy_lo; sy_hi = dy_hi - 1;
-        }
-        s_geo[0] = sx_lo; s_geo[1] = sx_hi; s_geo[2] = sy_lo; s_geo[3] = sy_hi;
-    }
-    __syncthreads();
-    const int sx_lo = s_geo[0], sx_hi = s_geo[1], sy_lo = s_geo[2], sy_hi = s_geo[3];
-    const uint8_t* src = frames + (int64_t)frame * frame_bytes + job.src_off;
-
-    // ---- stage source rows [sy_lo, sy_hi], bytes [sx_lo*3, (sx_hi+1)*3) with aligned 16-byte loads
+    // source window (every thread computes it: four broadcast loads, no barrier needed)
+    int gx_lo = 0, sx_hi = 0, sy_lo = 0, sy_hi = 0;
     if (has_src) {
-        const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-        const int span = (sx_hi - sx_lo + 1) * 3;
-        for (int r = sy_lo + warp; r <= sy_hi; r += kThreads / 32) {
-            const uint8_t* g = src + (int64_t)r * pitch + sx_lo * 3;
-            const int shift = (int)((uintptr_t)g & 15);
-            const uint4* g16 = reinterpret_cast<const uint4*>(g - shift);
-            uint4* s16 = reinterpret_cast<uint4*>(smem + (r - sy_lo) * smem_row_stride);
-            const int nchunk = (shift + span + 15) >> 4;
-            for (int c = lane; c < nchunk; c += 32) s16[c] = __ldg(g16 + c);
+        if (mode == MODE_LINEAR) {
+            gx_lo = xt[dx_lo].sx;
+            sx_hi = min(xt[dx_hi - 1].sx + 1, src_w - 1);
+            sy_lo = yt[dy_lo].r0;
+            sy_hi = yt[dy_hi - 1].r1;
+        } else if (mode == MODE_AREA2) {
+            gx_lo = 2 * dx_lo; sx_hi = 2 * dx_hi - 1; sy_lo = 2 * dy_lo; sy_hi = 2 * dy_hi - 1;
+        } else {
+            gx_lo = dx_lo; sx_hi = dx_hi - 1; sy_lo = dy_lo; sy_hi = dy_hi - 1;
         }
+        gx_lo &= ~3;
+    }
+
+    // ---- stage source rows [sy_lo, sy_hi], pixels [gx_lo, sx_hi] as pixel words: warp per row, lane per 4-pixel group
+    if (has_src) {
+        const uint8_t* src = frames + (int64_t)frame * frame_bytes + job.src_off + (int64_t)sy_lo * pitch + gx_lo * 3;
+        const int n_groups = ((sx_hi - gx_lo) >> 2) + 1;
+        const int n_rows = sy_hi - sy_lo + 1;
+        const int row_px = job.row_px - gx_lo;            // pixels available from gx_lo to the end of the frame row
+        const bool vec_ok = job.vec_ok != 0;
+        const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+        for (int r = warp; r < n_rows; r += kThreads / 32) {
+            const uint8_t* prow = src + r * pitch;
+            uint32_t* srow = spix + r * smem_row_words;
+            for (int g = lane; g < n_groups; g += 32) {
+                const uint8_t* p = prow + g * 12;
+                uint4 w;
+                if (vec_ok && 4 * g + 4 <= row_px) {
+                    const uint32_t* p32 = reinterpret_cast<const uint32_t*>(p);
+                    const uint32_t a = __ldg(p32), b = __ldg(p32 + 1), c = __ldg(p32 + 2);
+                    w.x = a & 0x00ffffffu;                           // B0 G0 R0
+                    w.y = __byte_perm(a, b, 0x0543) & 0x00ffffffu;   // a.b3 b.b0 b.b1
+                    w.z = __byte_perm(b, c, 0x0432) & 0x00ffffffu;   // b.b2 b.b3 c.b0
+                    w.w = c >> 8;                                    // c.b1 c.b2 c.b3
+                } else {
+                    uint32_t v[4];
+#pragma unroll
+                    for (int k = 0; k < 4; k++) {
+                        v[k] = 0;
+                        if (4 * g + k < row_px)
+                            v[k] = (uint32_t)__ldg(p + 3 * k) | ((uint32_t)__ldg(p + 3 * k + 1) << 8) | ((uint32_t)__ldg(p + 3 * k + 2) << 16);
+                    }
+                    w = make_uint4(v[0], v[1], v[2], v[3]);
+                }
+                *reinterpret_cast<uint4*>(srow + 4 * g) = w;
+            }
+        }
+    }
+    if (threadIdx.x < kTH) {
+        const int dy = oy0 + threadIdx.x - top;
+        YCoef yc{0, 0, 0, 0};
+        if (has_src && dy >= 0 && dy < new_h) {
+            if (mode == MODE_LINEAR) { yc = yt[dy]; yc.r0 -= sy_lo; yc.r1 -= sy_lo; }
+            else if (mode == MODE_AREA2) { yc.r0 = 2 * dy - sy_lo; yc.r1 = yc.r0 + 1; }
+            else { yc.r0 = dy - sy_lo; yc.r1 = yc.r0; }
+            yc.r0 *= 4 * smem_row_words; yc.r1 *= 4 * smem_row_words;      // byte offsets of the two source rows
+        }
+        s_y[threadIdx.x] = yc;
     }
     __syncthreads();
 
-    const int tx = threadIdx.x & 63, ty = threadIdx.x >> 6;
-    const int ox = ox0 + tx * 4;
-    if (ox >= job.out_w) return;
-    const int64_t plane = (int64_t)job.out_h * job.out_w;
+    // ---- one thread per output column, walking down the block's rows: the horizontal result of a
+    // source row is kept in registers and reused when the next output row needs the same row.
+    const int ox = ox0 + threadIdx.x;
+    if (ox >= out_w) return;
+    const int plane = out_h * out_w;
     const int64_t tile_base = job.out_off + (int64_t)frame * job.out_frame_stride;
+    float* tile_f32 = U8OUT ? nullptr : out_f32 + tile_base;
+    uint8_t* tile_u8 = U8OUT ? out_u8 + tile_base : nullptr;
 
-    // per-thread column coefficients (4 pixels)
-    int csx[4], ca0[4], ca1[4];
-    bool cvalid[4];
-#pragma unroll
-    for (int i = 0; i < 4; i++) {
-        int dx = ox + i - job.left;
-        cvalid[i] = dx >= 0 && dx < job.new_w && (ox + i) < job.out_w;
-        csx[i] = 0; ca0[i] = 0; ca1[i] = 0;
-        if (cvalid[i]) {
-            if (job.mode == MODE_LINEAR) {
-                XCoef xc = xtab[job.xtab + dx];
-                csx[i] = xc.sx; ca0[i] = xc.a0; ca1[i] = xc.a1;
-            } else if (job.mode == MODE_AREA2) {
-                csx[i] = 2 * dx;
-            } else {
-                csx[i] = dx;
-            }
+    const int dx = ox - left;
+    const bool cvalid = has_src && dx >= 0 && dx < new_w;
+    int i0 = 0, i1 = 0;
+    uint32_t apk = 0;
+    if (cvalid) {
+        if (mode == MODE_LINEAR) {
+            const XCoef xc = xt[dx];
+            i0 = xc.sx - gx_lo; i1 = min(xc.sx + 1, src_w - 1) - gx_lo; apk = xc.apk;
+        } else if (mode == MODE_AREA2) {
+            i0 = 2 * dx - gx_lo; i1 = i0 + 1;
+        } else {
+            i0 = dx - gx_lo;
         }
     }
+    const int oy_end = min(oy0 + kTH, out_h);
+    int o = oy0 * out_w + ox;
 
-#pragma unroll
-    for (int j = 0; j < kTH / 4; j++) {
-        const int oy = oy0 + ty + 4 * j;
-        if (oy >= job.out_h) break;
-        const int dy = oy - job.top;
-        const bool rvalid = dy >= 0 && dy < job.new_h;
-        int val[4][3];
-#pragma unroll
-        for (int i = 0; i < 4; i++) { val[i][0] = val[i][1] = val[i][2] = 114; }
+    if (!cvalid) {                                        // padding column (or a block without source pixels)
+        for (int oy = oy0; oy < oy_end; oy++, o += out_w) lb_store<U8OUT>(tile_f32, tile_u8, o, plane, 114, 114, 114);
+        return;
+    }
+    // rows of this block that carry image content: [ja, jb); the rest is 114 padding
+    const int ja = min(max(top - oy0, 0), oy_end - oy0), jb = max(min(top + new_h - oy0, oy_end - oy0), ja);
+    for (int j = 0; j < ja; j++) lb_store<U8OUT>(tile_f32, tile_u8, o + j * out_w, plane, 114, 114, 114);
+    for (int j = jb; j < oy_end - oy0; j++) lb_store<U8OUT>(tile_f32, tile_u8, o + j * out_w, plane, 114, 114, 114);
+    o += ja * out_w;
 
-        if (rvalid) {
-            if (job.mode == MODE_COPY) {
-                const uint8_t* row = smem + (dy - sy_lo) * smem_row_stride +
-                                     (int)((uintptr_t)(src + (int64_t)dy * pitch + sx_lo * 3) & 15);
-#pragma unroll
-                for (int i = 0; i < 4; i++)
-                    if (cvalid[i]) {
-                        const uint8_t* p = row + (csx[i] - sx_lo) * 3;
-                        val[i][0] = p[0]; val[i][1] = p[1]; val[i][2] = p[2];
-                    }
-            } else if (job.mode == MODE_AREA2) {
-                const int r0 = 2 * dy;
-                const uint8_t* row0 = smem + (r0 - sy_lo) * smem_row_stride +
-                                      (int)((uintptr_t)(src + (int64_t)r0 * pitch + sx_lo * 3) & 15);
-                const uint8_t* row1 = smem + (r0 + 1 - sy_lo) * smem_row_stride +
-                                      (int)((uintptr_t)(src + (int64_t)(r0 + 1) * pitch + sx_lo * 3) & 15);
-#pragma unroll
-                for (int i = 0; i < 4; i++)
-                    if (cvalid[i]) {
-                        const int o = (csx[i] - sx_lo) * 3;
-#pragma unroll
-                        for (int c = 0; c < 3; c++)
-                            val[i][c] = (row0[o + c] + row0[o + 3 + c] + row1[o + c] + row1[o + 3 + c] + 2) >> 2;
-                    }
-            } else {
-                const YCoef yc = ytab[job.ytab + dy];
-                const uint8_t* row0 = smem + (yc.r0 - sy_lo) * smem_row_stride +
-                                      (int)((uintptr_t)(src + (int64_t)yc.r0 * pitch + sx_lo * 3) & 15);
-                const uint8_t* row1 = smem + (yc.r1 - sy_lo) * smem_row_stride +
-                                      (int)((uintptr_t)(src + (int64_t)yc.r1 * pitch + sx_lo * 3) & 15);
-#pragma unroll
-                for (int i = 0; i < 4; i++)
-                    if (cvalid[i]) {
-                        const int o0 = (csx[i] - sx_lo) * 3;
-                        const int o1 = (min(csx[i] + 1, job.src_w - 1) - sx_lo) * 3;
-#pragma unroll
-                        for (int c = 0; c < 3; c++) {
-                            int h0 = row0[o0 + c] * ca0[i] + row0[o1 + c] * ca1[i];
-                            int h1 = row1[o0 + c] * ca0[i] + row1[o1 + c] * ca1[i];
-                            val[i][c] = (((yc.b0 * (h0 >> 4)) >> 16) + ((yc.b1 * (h1 >> 4)) >> 16) + 2) >> 2;
-                        }
-                    }
-            }
-        }
+    // raw shared-memory byte addresses of the two taps of this column (row offsets are added per row)
+    const uint32_t a0 = (uint32_t)__cvta_generic_to_shared(spix) + 4u * (uint32_t)i0;
+    const uint32_t a1 = (uint32_t)__cvta_generic_to_shared(spix) + 4u * (uint32_t)i1;
+    float* q0 = U8OUT ? nullptr : tile_f32 + o;             // R plane, then +plane, +2*plane
+    float* q1 = U8OUT ? nullptr : q0 + plane;
+    float* q2 = U8OUT ? nullptr : q1 + plane;
+    uint8_t* q8 = U8OUT ? tile_u8 + 3 * o : nullptr;
 
+    auto emit = [&](int vb, int vg, int vr) {
         if (U8OUT) {
-            uint8_t* o = out_u8 + tile_base + ((int64_t)oy * job.out_w + ox) * 3;
-#pragma unroll
-            for (int i = 0; i < 4; i++)
-                if (ox + i < job.out_w) { o[3 * i] = (uint8_t)val[i][0]; o[3 * i + 1] = (uint8_t)val[i][1]; o[3 * i + 2] = (uint8_t)val[i][2]; }
+            q8[0] = (uint8_t)vb; q8[1] = (uint8_t)vg; q8[2] = (uint8_t)vr;
+            q8 += 3 * out_w;
         } else {
-            // planes are R,G,B = source channels 2,1,0
-            float* o = out_f32 + tile_base + (int64_t)oy * job.out_w + ox;
-            const bool vec = (ox + 3 < job.out_w) && ((((uintptr_t)o) & 15) == 0) && ((plane & 3) == 0);
-#pragma unroll
-            for (int c = 0; c < 3; c++) {
-                float4 v;
-                v.x = u8_over_255(val[0][2 - c]); v.y = u8_over_255(val[1][2 - c]);
-                v.z = u8_over_255(val[2][2 - c]); v.w = u8_over_255(val[3][2 - c]);
-                float* oc = o + c * plane;
-                if (vec) {
-                    *reinterpret_cast<float4*>(oc) = v;
-                } else {
-                    if (ox + 0 < job.out_w) oc[0] = v.x;
-                    if (ox + 1 < job.out_w) oc[1] = v.y;
-                    if (ox + 2 < job.out_w) oc[2] = v.z;
-                    if (ox + 3 < job.out_w) oc[3] = v.w;
-                }
-            }
+            *q0 = u8_over_255(vr); *q1 = u8_over_255(vg); *q2 = u8_over_255(vb);
+            q0 += out_w; q1 += out_w; q2 += out_w;
+        }
+    };
+
+    if (mode == MODE_COPY) {
+#pragma unroll 4
+        for (int j = ja; j < jb; j++) {
+            const uint32_t p = lds32(a0 + (uint32_t)s_y[j].r0);
+            emit(p & 255, (p >> 8) & 255, p >> 16);
+        }
+    } else if (mode == MODE_AREA2) {
+#pragma unroll 4
+        for (int j = ja; j < jb; j++) {
+            const YCoef yc = s_y[j];
+            const uint32_t p00 = lds32(a0 + yc.r0), p01 = lds32(a1 + yc.r0), p10 = lds32(a0 + yc.r1), p11 = lds32(a1 + yc.r1);
+            // B and R ride in the two 16-bit lanes of one word, G in another
+            const uint32_t br = (p00 & 0x00ff00ffu) + (p01 & 0x00ff00ffu) + (p10 & 0x00ff00ffu) + (p11 & 0x00ff00ffu) + 0x00020002u;
+            const uint32_t gg = ((p00 >> 8) & 255) + ((p01 >> 8) & 255) + ((p10 >> 8) & 255) + ((p11 >> 8) & 255) + 2;
+            emit((br >> 2) & 255, gg >> 2, (br >> 18) & 255);
+        }
+    } else {
+#pragma unroll 4
+        for (int j = ja; j < jb; j++) {
+            const YCoef yc = s_y[j];
+            uint32_t h0[3], h1[3];
+            lb_hrow(lds32(a0 + yc.r0), lds32(a1 + yc.r0), apk, h0);
+            lb_hrow(lds32(a0 + yc.r1), lds32(a1 + yc.r1), apk, h1);
+            const uint32_t b0 = (uint32_t)yc.b0, b1 = (uint32_t)yc.b1;
+            // OpenCV vertical pass: ((b0*(H0>>4))>>16) + ((b1*(H1>>4))>>16) + 2 >> 2
+            emit((int)((((b0 * h0[0]) >> 16) + ((b1 * h1[0]) >> 16) + 2u) >> 2),
+                 (int)((((b0 * h0[1]) >> 16) + ((b1 * h1[1]) >> 16) + 2u) >> 2),
+                 (int)((((b0 * h0[2]) >> 16) + ((b1 * h1[2]) >> 16) + 2u) >> 2));
         }
     }
 }
@@ -343,7 +384,7 @@ int hvb_lb_plan_create(hvb_ctx* ctx, int n_frames, int frame_h, int frame_w, int
     std::vector<YCoef> yt;
     std::map<std::pair<int, int>, int> xkey, ykey;    // (src,dst) -> table offset
     std::vector<uint32_t> blk;
-    int max_rows = 1, max_span = 16;
+    int max_rows = 1, max_span = 4;
     for (int t = 0; t < T; t++) {
         const Geometry& g = geo[t];
         LbJob& j = jobs[t];
@@ -354,7 +395,9 @@ int hvb_lb_plan_create(hvb_ctx* ctx, int n_frames, int frame_h, int frame_w, int
         j.out_frame_stride = (int64_t)c.tiles_per_frame * tile_elems;
         j.src_w = srcs[t].w; j.src_h = srcs[t].h; j.new_w = g.new_w; j.new_h = g.new_h;
         j.top = g.top; j.left = g.left; j.out_h = g.out_h; j.out_w = g.out_w;
-        j.xtab = j.ytab = 0; j.pad_ = 0;
+        j.xtab = j.ytab = 0; j.pad_[0] = j.pad_[1] = j.pad_[2] = 0;
+        j.row_px = frame_w - srcs[t].x;
+        j.vec_ok = ((frame_w * 3) % 4 == 0 && j.src_off % 4 == 0 && ((int64_t)frame_h * frame_w * 3) % 4 == 0) ? 1 : 0;
         if (g.new_w == srcs[t].w && g.new_h == srcs[t].h) j.mode = MODE_COPY;
         else if (srcs[t].w == 2 * g.new_w && srcs[t].h == 2 * g.new_h) j.mode = MODE_AREA2;
         else {
@@ -364,7 +407,7 @@ int hvb_lb_plan_create(hvb_ctx* ctx, int n_frames, int frame_h, int frame_w, int
                 xkey[kx] = (int)xt.size();
                 std::vector<int> s, a0, a1;
                 linear_coeffs(srcs[t].w, g.new_w, true, s, a0, a1);
-                for (int d = 0; d < g.new_w; d++) xt.push_back({s[d], (int16_t)a0[d], (int16_t)a1[d]});
+                for (int d = 0; d < g.new_w; d++) xt.push_back({s[d], (uint32_t)a0[d] | ((uint32_t)a1[d] << 16)});
             }
             auto ky = std::make_pair(srcs[t].h, g.new_h);
             if (!ykey.count(ky)) {
@@ -382,10 +425,10 @@ int hvb_lb_plan_create(hvb_ctx* ctx, int n_frames, int frame_h, int frame_w, int
         // shared-memory need of the worst block of this job
         double sx = (double)srcs[t].w / g.new_w, sy = (double)srcs[t].h / g.new_h;
         int rows = (int)ceil(kTH * std::max(sy, 1e-9)) + 3;
-        int span = ((int)ceil(kTW * std::max(sx, 1e-9)) + 3) * 3;
-        if (j.mode == MODE_COPY) { rows = kTH; span = kTW * 3; }
+        int span = (int)ceil(kTW * std::max(sx, 1e-9)) + 3;            // source pixels per block row
+        if (j.mode == MODE_COPY) { rows = kTH; span = kTW; }
         max_rows = std::max(max_rows, std::min(rows, srcs[t].h));
-        max_span = std::max(max_span, std::min(span, srcs[t].w * 3));
+        max_span = std::max(max_span, std::min(span, srcs[t].w));
         const int by = hvb_div_up(g.out_h, kTH), bx = hvb_div_up(g.out_w, kTW);
         if (by > 4095 || bx > 4095) { delete p; hvb_set_error("output too large for the block table"); return HVB_ERR_CAPACITY; }
         for (int y = 0; y < by; y++)
@@ -398,8 +441,8 @@ int hvb_lb_plan_create(hvb_ctx* ctx, int n_frames, int frame_h, int frame_w, int
     p->read_bytes = std::min<int64_t>(p->read_bytes, (int64_t)frame_h * frame_w * 3) * n_frames;
     p->write_bytes *= n_frames;
     p->blocks_per_frame = (int)blk.size();
-    p->smem_row_stride = ((max_span + 16 + 15) / 16) * 16 + 16;
-    p->smem_bytes = p->smem_row_stride * max_rows;
+    p->smem_row_stride = ((max_span + 3 + 3) / 4) * 4 + 4;             // pixel words per staged row (group-aligned start)
+    p->smem_bytes = p->smem_row_stride * max_rows * 4;
     if (p->smem_bytes > ctx->max_smem_optin - 1024) {
         delete p;
         hvb_set_error("letterbox block needs %d bytes of shared memory (down-scale factor too large)", p->smem_bytes);
@@ -423,7 +466,7 @@ int hvb_lb_plan_create(hvb_ctx* ctx, int n_frames, int frame_h, int frame_w, int
         }
 
     // ---- upload
-    if (xt.empty()) xt.push_back({0, 0, 0});
+    if (xt.empty()) xt.push_back({0, 0u});
     if (yt.empty()) yt.push_back({0, 0, 0, 0});
     size_t o_jobs = 0;
     size_t o_blk = o_jobs + ((jobs.size() * sizeof(LbJob) + 255) & ~(size_t)255);
@@ -503,6 +546,7 @@ static int lb_run(hvb_lb_plan* p, const uint8_t* frames_dev, float* out_f32, uin
     hvb_ctx* ctx = p->ctx;
     HVB_CHECK_CTX(ctx);
     HVB_ARG(frames_dev && (out_f32 || out_u8), "null buffer");
+    HVB_ARG(((uintptr_t)frames_dev & 3) == 0, "frames_dev must be 4-byte aligned");
     const int grid = p->blocks_per_frame * p->n_frames;
     const int64_t frame_bytes = (int64_t)p->frame_h * p->frame_w * 3;
     if (out_u8)

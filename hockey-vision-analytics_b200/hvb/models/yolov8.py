@@ -162,3 +162,16 @@ def build_yolov8(scale: str = "n", nc: int = 80, seed: int = 0) -> YOLOv8:
 def level_shapes(h: int, w: int):
     """Head grid shapes for a letterboxed (h, w) input (both multiples of 32)."""
     return [(h // s, w // s) for s in (8, 16, 32)]
+
+
+def fuse_conv_bn(model: nn.Module) -> nn.Module:
+    """Fold every BatchNorm into its convolution, in place (what ultralytics' ``model.fuse()`` does
+    before inference, so the reference runs fused convolutions too).  Returns the model."""
+    from torch.nn.utils.fusion import fuse_conv_bn_eval
+    for m in model.modules():
+        if isinstance(m, ConvBnAct) and isinstance(m.bn, nn.BatchNorm2d):
+            m.conv = fuse_conv_bn_eval(m.conv.eval(), m.bn.eval())
+            m.bn = nn.Identity()
+    for p in model.parameters():
+        p.requires_grad_(False)
+    return model
