@@ -114,7 +114,8 @@ class CpuReferencePath:
         from hvb.models import build_trunk, build_yolov8
         from oracle import team_reference as tr
         self.torch = torch
-        self.yolo = build_yolov8("m", 2, 0)
+        from hvb.models.yolov8 import fuse_conv_bn
+        self.yolo = fuse_conv_bn(build_yolov8("m", 2, 0))        # ultralytics fuses conv+bn before inference
         self.trunk = build_trunk(0, calibrate=True)
         self.ref = tr.HybridReference(self.trunk)
         self.fitted = False
@@ -318,7 +319,7 @@ def run_hvb(args, rank, world):
                                    "team classification (K3a/K3b on 12 planted player boxes per frame, MobileNetV3-small fp32, "
                                    "K4a scale_transform, rule)",
                        "frames_per_step_per_gpu": F, "players_per_frame": PLAYERS, "team_boxes": "planted",
-                       "backbones": "torch fp32 (cudnn TF32 default for YOLO, TF32 off for MobileNetV3)",
+                       "backbones": "torch fp32, conv+bn fused, channels_last, cudnn.benchmark (cudnn TF32 default for YOLO, TF32 off for MobileNetV3)",
                        "l2": "inputs larger than L2 (%.0f MB frames + %.0f MB letterboxed per step)" % (frames.nbytes / 1e6, k1_bytes / 1e6),
                        "parallelism": "frame chunks sharded per GPU, no data-path collective; one NCCL feature all-gather at fit"},
             "e2e": {"value": fps_e2e, "unit": UNIT, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h)},

@@ -38,9 +38,14 @@ class Detector:
 
     def __init__(self, model: torch.nn.Module, device="cuda:0", imgsz: int = 1280, conf: float = 0.4, iou: float = 0.7,
                  max_det: int = 300, agnostic_nms: bool = False, class_names: Optional[Dict[int, str]] = None,
-                 autocast_dtype: Optional[torch.dtype] = None, channels_last: bool = False):
+                 autocast_dtype: Optional[torch.dtype] = None, channels_last: bool = False, fuse: bool = False):
         self.ctx: Context = get_context(device)
         self.device = self.ctx.device
+        if fuse:
+            # ultralytics folds BatchNorm into the convolutions before inference (model.fuse()); do the same
+            import copy
+            from .models.yolov8 import fuse_conv_bn
+            model = fuse_conv_bn(copy.deepcopy(model))
         self.model = model.to(self.device).eval()
         if channels_last:
             self.model = self.model.to(memory_format=torch.channels_last)
@@ -79,7 +84,14 @@ class Detector:
                     heads = self.model(x)
             else:
                 heads = self.model(x)
-        return [h.float().contiguous() for h in heads]
+        # K2a takes element strides, so channels-last heads are consumed in place (no NCHW copy)
+        out = []
+        for h in heads:
+            h = h.float()
+            if h.stride(2) != h.shape[3] * h.stride(3):
+                h = h.contiguous()
+            out.append(h)
+        return out
 
     def _meta_dev(self, plan: LetterboxPlan, cls: int) -> Tuple[np.ndarray, torch.Tensor]:
         key = (id(plan), cls)

@@ -24,11 +24,14 @@ from .slicer import B200InferenceSlicer
 
 class HotPath:
     def __init__(self, device="cuda:0", yolo_scale: str = "m", nc: int = 2, imgsz: int = 1280, conf: float = 0.4,
-                 seed: int = 0, trunk: Optional[torch.nn.Module] = None, affinity_mode: int = 0):
+                 seed: int = 0, trunk: Optional[torch.nn.Module] = None, affinity_mode: int = 0, fuse: bool = True,
+                 channels_last: bool = True, autocast_dtype: Optional[torch.dtype] = None):
         from .models import build_trunk, build_yolov8
         self.ctx = get_context(device)
+        torch.backends.cudnn.benchmark = True
         self.detector = Detector(build_yolov8(yolo_scale, nc, seed), device, imgsz=imgsz, conf=conf,
-                                 class_names={0: "player", 1: "goalie"})
+                                 class_names={0: "player", 1: "goalie"}, fuse=fuse, channels_last=channels_last,
+                                 autocast_dtype=autocast_dtype)
         self.classifier = HybridTeamClassifier(device=device, trunk=trunk if trunk is not None else build_trunk(seed, calibrate=True),
                                                affinity_mode=affinity_mode)
 
@@ -97,9 +100,12 @@ class SlicedPuckPath:
     """4K puck detection through the slicer: K1b -> YOLOv8n forward per shape class -> K2a -> gather -> K2b."""
 
     def __init__(self, device="cuda:0", yolo_scale: str = "n", nc: int = 1, conf: float = 0.4, seed: int = 0,
-                 uniform_tiles: bool = False, iou_threshold: float = 0.1):
+                 uniform_tiles: bool = False, iou_threshold: float = 0.1, fuse: bool = True, channels_last: bool = True,
+                 autocast_dtype: Optional[torch.dtype] = None):
         from .models import build_yolov8
-        self.detector = Detector(build_yolov8(yolo_scale, nc, seed), device, imgsz=640, conf=conf, class_names={0: "puck"})
+        torch.backends.cudnn.benchmark = True
+        self.detector = Detector(build_yolov8(yolo_scale, nc, seed), device, imgsz=640, conf=conf, class_names={0: "puck"},
+                                 fuse=fuse, channels_last=channels_last, autocast_dtype=autocast_dtype)
         self.slicer = B200InferenceSlicer(detector=self.detector, slice_wh=(640, 640), overlap_ratio_wh=(0.2, 0.2),
                                           iou_threshold=iou_threshold, tile_imgsz=640, uniform_tiles=uniform_tiles)
 

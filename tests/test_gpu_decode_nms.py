@@ -127,3 +127,16 @@ def test_nms_idempotent_property(ctx):
     k1 = ctx.nms_f32(tb, ts, None, 0.5, 1024, True)
     k2 = ctx.nms_f32(tb[k1.long()], ts[k1.long()], None, 0.5, 1024, True)
     assert np.array_equal(k2.cpu().numpy(), np.arange(len(k1)))
+
+
+def test_channels_last_heads_give_identical_results(ctx):
+    """K2a takes element strides: NHWC (channels_last) head tensors must decode to the same bits."""
+    levels = make_heads(21, 2, (736, 1280), 2)
+    meta = meta_for(2, (736, 1280), (1080, 1920))
+    a = ctx.decode_nms([l.cuda() for l in levels], 2, 0.4, 0.7, 300, False, meta=meta)
+    b = ctx.decode_nms([l.cuda().contiguous(memory_format=torch.channels_last) for l in levels], 2, 0.4, 0.7, 300, False, meta=meta)
+    cnt = a[3].cpu().numpy()
+    assert np.array_equal(cnt, b[3].cpu().numpy()) and cnt.min() > 0
+    for i in range(2):
+        for x, y in zip(a[:3], b[:3]):
+            assert torch.equal(x[i, :cnt[i]], y[i, :cnt[i]])
