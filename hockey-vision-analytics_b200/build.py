@@ -28,7 +28,10 @@ NVCC_FLAGS = [
     "-Xcompiler", "-fPIC,-O2,-fvisibility=hidden",
     "-Xptxas", "-v",
     "-I", INCLUDE, "-I", CSRC,
-]
+] + os.environ.get("HVB_NVCC_EXTRA", "").split()
+if os.environ.get("HVB_BUILD_TAG"):            # A/B variants: separate objects and library name
+    OBJ = OBJ + "_" + os.environ["HVB_BUILD_TAG"]
+    OUT = os.path.join(HERE, "hvb", "libhvb_%s.so" % os.environ["HVB_BUILD_TAG"])
 
 
 def _nvcc() -> str:

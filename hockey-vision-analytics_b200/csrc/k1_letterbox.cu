@@ -25,9 +25,16 @@
 #include <math.h>
 #include <map>
 
+#ifndef HVB_K1_MADHI
+#define HVB_K1_MADHI 0     /* IMAD.HI is half rate on sm_100: measured slower than IMAD + SHF */
+#endif
+
 namespace {
 
-constexpr int kTH = 16;         // output rows per CTA
+#ifndef HVB_K1_TH
+#define HVB_K1_TH 16
+#endif
+constexpr int kTH = HVB_K1_TH;  // output rows per CTA
 constexpr int kTW = 256;        // output columns per CTA
 constexpr int kThreads = 256;   // one thread per output column of the block
 
@@ -44,6 +51,17 @@ struct LbJob {
     int32_t vec_ok;      // 4-pixel groups of this tile are 4-byte aligned in global memory
     int32_t pad_[3];
 };
+
+struct __align__(16) LbBlock {     // one per CTA of a frame: which tile/rows/cols, and its source window (host-computed)
+    uint32_t packed;               // job << 24 | block_row << 12 | block_col
+    int32_t flags;                 // bit 0: block has source pixels; bit 1: aligned 4-pixel-group loads allowed
+    int32_t gx_lo, sy_lo;          // first staged pixel (multiple of 4) and row, tile-relative
+    int32_t n_rows, n_groups;      // staged rows and 4-pixel groups per row
+    int32_t row_px;                // pixels from gx_lo to the end of the frame row
+    int32_t pad_;
+    int64_t src_off;               // byte offset of pixel (gx_lo, sy_lo) inside frame 0
+    int64_t pad2_;
+};                                 // 48 bytes: everything the staging phase needs, one dependent load
 
 struct XCoef { int32_t sx; uint32_t apk; };              // apk = a0 | a1 << 16
 struct __align__(16) YCoef { int32_t r0, r1; int32_t b0, b1; };
@@ -80,17 +98,18 @@ __device__ __forceinline__ void lb_store(float* __restrict__ tile_f32, uint8_t* 
     }
 }
 
-template <bool U8OUT>
-__global__ void __launch_bounds__(kThreads, 5)
+template <bool U8OUT, int MINBLOCKS>
+__global__ void __launch_bounds__(kThreads, MINBLOCKS)
 letterbox_kernel(const uint8_t* __restrict__ frames, int64_t frame_bytes, int32_t pitch,
-                 const LbJob* __restrict__ jobs, const uint32_t* __restrict__ blk2job, int blocks_per_frame,
-                 const XCoef* __restrict__ xtab, const YCoef* __restrict__ ytab, int smem_row_words,
+                 const LbJob* __restrict__ jobs, const LbBlock* __restrict__ blk2job, int blocks_per_frame,
+                 const XCoef* __restrict__ xtab, const YCoef* __restrict__ ytab, int smem_row_words, int frames_aligned16,
                  float* __restrict__ out_f32, uint8_t* __restrict__ out_u8) {
     extern __shared__ __align__(16) uint32_t spix[];      // [rows][smem_row_words] pixel words
     __shared__ YCoef s_y[kTH];                            // vertical coefficients of the block's rows (smem-row relative)
 
     const int frame = blockIdx.x / blocks_per_frame;
-    const uint32_t packed = __ldg(blk2job + (blockIdx.x - frame * blocks_per_frame));
+    const LbBlock bd = blk2job[blockIdx.x - frame * blocks_per_frame];    // two 128-bit loads: everything staging needs
+    const uint32_t packed = bd.packed;
     const LbJob& job = jobs[packed >> 24];
     const int oy0 = ((packed >> 12) & 0xfff) * kTH;
     const int ox0 = (packed & 0xfff) * kTW;
@@ -98,61 +117,105 @@ letterbox_kernel(const uint8_t* __restrict__ frames, int64_t frame_bytes, int32_
     const int out_w = job.out_w, out_h = job.out_h, src_w = job.src_w;
     const XCoef* xt = xtab + job.xtab;
     const YCoef* yt = ytab + job.ytab;
-
-    // valid (non-padding) output window of this block, in resized-image coordinates
-    const int dy_lo = max(oy0 - top, 0), dy_hi = min(oy0 + kTH - top, new_h);     // [lo,hi)
-    const int dx_lo = max(ox0 - left, 0), dx_hi = min(ox0 + kTW - left, new_w);
-    const bool has_src = dy_lo < dy_hi && dx_lo < dx_hi;
-
-    // source window (every thread computes it: four broadcast loads, no barrier needed)
-    int gx_lo = 0, sx_hi = 0, sy_lo = 0, sy_hi = 0;
-    if (has_src) {
-        if (mode == MODE_LINEAR) {
-            gx_lo = xt[dx_lo].sx;
-            sx_hi = min(xt[dx_hi - 1].sx + 1, src_w - 1);
-            sy_lo = yt[dy_lo].r0;
-            sy_hi = yt[dy_hi - 1].r1;
-        } else if (mode == MODE_AREA2) {
-            gx_lo = 2 * dx_lo; sx_hi = 2 * dx_hi - 1; sy_lo = 2 * dy_lo; sy_hi = 2 * dy_hi - 1;
-        } else {
-            gx_lo = dx_lo; sx_hi = dx_hi - 1; sy_lo = dy_lo; sy_hi = dy_hi - 1;
-        }
-        gx_lo &= ~3;
-    }
+    // source window of this block (pixels [gx_lo, sx_hi], rows [sy_lo, sy_hi]); gx_lo is a multiple of 4
+    const bool has_src = (bd.flags & 1) != 0;
+    const int gx_lo = bd.gx_lo, sy_lo = bd.sy_lo;
 
     // ---- stage source rows [sy_lo, sy_hi], pixels [gx_lo, sx_hi] as pixel words: warp per row, lane per 4-pixel group
     if (has_src) {
-        const uint8_t* src = frames + (int64_t)frame * frame_bytes + job.src_off + (int64_t)sy_lo * pitch + gx_lo * 3;
-        const int n_groups = ((sx_hi - gx_lo) >> 2) + 1;
-        const int n_rows = sy_hi - sy_lo + 1;
-        const int row_px = job.row_px - gx_lo;            // pixels available from gx_lo to the end of the frame row
-        const bool vec_ok = job.vec_ok != 0;
-        const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-        for (int r = warp; r < n_rows; r += kThreads / 32) {
-            const uint8_t* prow = src + r * pitch;
-            uint32_t* srow = spix + r * smem_row_words;
-            for (int g = lane; g < n_groups; g += 32) {
-                const uint8_t* p = prow + g * 12;
+        const uint8_t* src = frames + (int64_t)frame * frame_bytes + bd.src_off;
+        const int n_groups = bd.n_groups, n_rows = bd.n_rows, row_px = bd.row_px;
+        const bool vec_ok = (bd.flags & 2) != 0;
+        if ((bd.flags & 4) && frames_aligned16) {
+            // 16-pixel groups: three 128-bit loads -> four 128-bit shared stores; up to 3 items per thread in flight
+            const int n16 = n_groups >> 2, n_items16 = n_rows * n16;
+            const float inv16 = 1.0f / (float)n16;
+            for (int it0 = threadIdx.x; it0 < n_items16; it0 += 3 * kThreads) {
+                uint4 q[3][3];
+                int soff[3];
+                bool live[3];
+#pragma unroll
+                for (int k = 0; k < 3; k++) {
+                    const int it = it0 + k * kThreads;
+                    live[k] = it < n_items16;
+                    int r = (int)((float)it * inv16);
+                    int g = it - r * n16;
+                    if (g < 0) { r--; g += n16; }
+                    if (g >= n16) { r++; g -= n16; }
+                    soff[k] = r * smem_row_words + 16 * g;
+                    if (live[k]) {
+                        const uint4* p128 = reinterpret_cast<const uint4*>(src + r * pitch + g * 48);
+                        q[k][0] = __ldg(p128); q[k][1] = __ldg(p128 + 1); q[k][2] = __ldg(p128 + 2);
+                    }
+                }
+#pragma unroll
+                for (int k = 0; k < 3; k++) {
+                    if (!live[k]) continue;
+                    const uint32_t w[12] = {q[k][0].x, q[k][0].y, q[k][0].z, q[k][0].w, q[k][1].x, q[k][1].y, q[k][1].z, q[k][1].w,
+                                            q[k][2].x, q[k][2].y, q[k][2].z, q[k][2].w};
+#pragma unroll
+                    for (int t = 0; t < 4; t++) {
+                        const uint32_t a = w[3 * t], b = w[3 * t + 1], c = w[3 * t + 2];
+                        uint4 o;
+                        o.x = a & 0x00ffffffu;
+                        o.y = __byte_perm(a, b, 0x0543) & 0x00ffffffu;
+                        o.z = __byte_perm(b, c, 0x0432) & 0x00ffffffu;
+                        o.w = c >> 8;
+                        *reinterpret_cast<uint4*>(spix + soff[k] + 4 * t) = o;
+                    }
+                }
+            }
+        } else {
+        // flat (row, group) work list, 4 items per thread per pass: all 12 global loads of a pass are
+        // issued before the first byte permute consumes one (memory-level parallelism hides DRAM latency)
+        const int n_items = n_rows * n_groups;
+        const float inv_groups = 1.0f / (float)n_groups;
+        for (int it0 = threadIdx.x; it0 < n_items; it0 += 4 * kThreads) {
+            uint32_t a[4], b[4], c[4];
+            int soff[4];
+            bool fast[4], live[4];
+            int poff[4];
+            int g4[4];
+#pragma unroll
+            for (int k = 0; k < 4; k++) {
+                const int it = it0 + k * kThreads;
+                live[k] = it < n_items;
+                int r = (int)((float)it * inv_groups);
+                int g = it - r * n_groups;
+                if (g < 0) { r--; g += n_groups; }
+                if (g >= n_groups) { r++; g -= n_groups; }
+                poff[k] = r * pitch + g * 12;
+                soff[k] = r * smem_row_words + 4 * g;
+                g4[k] = 4 * g;
+                fast[k] = live[k] && vec_ok && 4 * g + 4 <= row_px;
+                a[k] = b[k] = c[k] = 0;
+                if (fast[k]) {
+                    const uint32_t* p32 = reinterpret_cast<const uint32_t*>(src + poff[k]);
+                    a[k] = __ldg(p32); b[k] = __ldg(p32 + 1); c[k] = __ldg(p32 + 2);
+                }
+            }
+#pragma unroll
+            for (int k = 0; k < 4; k++) {
+                if (!live[k]) continue;
                 uint4 w;
-                if (vec_ok && 4 * g + 4 <= row_px) {
-                    const uint32_t* p32 = reinterpret_cast<const uint32_t*>(p);
-                    const uint32_t a = __ldg(p32), b = __ldg(p32 + 1), c = __ldg(p32 + 2);
-                    w.x = a & 0x00ffffffu;                           // B0 G0 R0
-                    w.y = __byte_perm(a, b, 0x0543) & 0x00ffffffu;   // a.b3 b.b0 b.b1
-                    w.z = __byte_perm(b, c, 0x0432) & 0x00ffffffu;   // b.b2 b.b3 c.b0
-                    w.w = c >> 8;                                    // c.b1 c.b2 c.b3
-                } else {
+                if (fast[k]) {
+                    w.x = a[k] & 0x00ffffffu;                              // B0 G0 R0
+                    w.y = __byte_perm(a[k], b[k], 0x0543) & 0x00ffffffu;   // a.b3 b.b0 b.b1
+                    w.z = __byte_perm(b[k], c[k], 0x0432) & 0x00ffffffu;   // b.b2 b.b3 c.b0
+                    w.w = c[k] >> 8;                                       // c.b1 c.b2 c.b3
+                } else {                                                   // unaligned tile or the end of a frame row
                     uint32_t v[4];
 #pragma unroll
-                    for (int k = 0; k < 4; k++) {
-                        v[k] = 0;
-                        if (4 * g + k < row_px)
-                            v[k] = (uint32_t)__ldg(p + 3 * k) | ((uint32_t)__ldg(p + 3 * k + 1) << 8) | ((uint32_t)__ldg(p + 3 * k + 2) << 16);
+                    for (int q = 0; q < 4; q++) {
+                        v[q] = 0;
+                        if (g4[k] + q < row_px)
+                            v[q] = (uint32_t)__ldg(src + poff[k] + 3 * q) | ((uint32_t)__ldg(src + poff[k] + 3 * q + 1) << 8) | ((uint32_t)__ldg(src + poff[k] + 3 * q + 2) << 16);
                     }
                     w = make_uint4(v[0], v[1], v[2], v[3]);
                 }
-                *reinterpret_cast<uint4*>(srow + 4 * g) = w;
+                *reinterpret_cast<uint4*>(spix + soff[k]) = w;
             }
+        }
         }
     }
     if (threadIdx.x < kTH) {
@@ -163,6 +226,7 @@ letterbox_kernel(const uint8_t* __restrict__ frames, int64_t frame_bytes, int32_
             else if (mode == MODE_AREA2) { yc.r0 = 2 * dy - sy_lo; yc.r1 = yc.r0 + 1; }
             else { yc.r0 = dy - sy_lo; yc.r1 = yc.r0; }
             yc.r0 *= 4 * smem_row_words; yc.r1 *= 4 * smem_row_words;      // byte offsets of the two source rows
+            yc.b0 <<= 16; yc.b1 <<= 16;                                    // so that umulhi(b, h) == (b * h) >> 16
         }
         s_y[threadIdx.x] = yc;
     }
@@ -245,11 +309,18 @@ letterbox_kernel(const uint8_t* __restrict__ frames, int64_t frame_bytes, int32_
             uint32_t h0[3], h1[3];
             lb_hrow(lds32(a0 + yc.r0), lds32(a1 + yc.r0), apk, h0);
             lb_hrow(lds32(a0 + yc.r1), lds32(a1 + yc.r1), apk, h1);
-            const uint32_t b0 = (uint32_t)yc.b0, b1 = (uint32_t)yc.b1;
-            // OpenCV vertical pass: ((b0*(H0>>4))>>16) + ((b1*(H1>>4))>>16) + 2 >> 2
-            emit((int)((((b0 * h0[0]) >> 16) + ((b1 * h1[0]) >> 16) + 2u) >> 2),
-                 (int)((((b0 * h0[1]) >> 16) + ((b1 * h1[1]) >> 16) + 2u) >> 2),
-                 (int)((((b0 * h0[2]) >> 16) + ((b1 * h1[2]) >> 16) + 2u) >> 2));
+            const uint32_t b0 = (uint32_t)yc.b0, b1 = (uint32_t)yc.b1;     // coefficients << 16
+            // OpenCV vertical pass: ((b0*(H0>>4))>>16) + ((b1*(H1>>4))>>16) + 2 >> 2, as two mad.hi per channel
+#if HVB_K1_MADHI
+            emit((int)((__umulhi(b1, h1[0]) + (__umulhi(b0, h0[0]) + 2u)) >> 2),
+                 (int)((__umulhi(b1, h1[1]) + (__umulhi(b0, h0[1]) + 2u)) >> 2),
+                 (int)((__umulhi(b1, h1[2]) + (__umulhi(b0, h0[2]) + 2u)) >> 2));
+#else
+            const uint32_t c0 = b0 >> 16, c1 = b1 >> 16;
+            emit((int)((((c0 * h0[0]) >> 16) + ((c1 * h1[0]) >> 16) + 2u) >> 2),
+                 (int)((((c0 * h0[1]) >> 16) + ((c1 * h1[1]) >> 16) + 2u) >> 2),
+                 (int)((((c0 * h0[2]) >> 16) + ((c1 * h1[2]) >> 16) + 2u) >> 2));
+#endif
         }
     }
 }
@@ -314,10 +385,11 @@ struct hvb_lb_plan {
     int tiles_per_frame = 0;
     int blocks_per_frame = 0;
     int smem_row_stride = 0, smem_bytes = 0;
+    bool resize_heavy = false;           // most output pixels come from LINEAR/AREA2 jobs
     int64_t out_elems = 0, read_bytes = 0, write_bytes = 0;
     void* dev = nullptr;                  // one allocation: jobs | blk2job | xtab | ytab
     LbJob* jobs_dev = nullptr;
-    uint32_t* blk2job_dev = nullptr;
+    LbBlock* blk2job_dev = nullptr;
     XCoef* xtab_dev = nullptr;
     YCoef* ytab_dev = nullptr;
 };
@@ -383,7 +455,7 @@ int hvb_lb_plan_create(hvb_ctx* ctx, int n_frames, int frame_h, int frame_w, int
     std::vector<XCoef> xt;
     std::vector<YCoef> yt;
     std::map<std::pair<int, int>, int> xkey, ykey;    // (src,dst) -> table offset
-    std::vector<uint32_t> blk;
+    std::vector<LbBlock> blk;
     int max_rows = 1, max_span = 4;
     for (int t = 0; t < T; t++) {
         const Geometry& g = geo[t];
@@ -422,17 +494,52 @@ int hvb_lb_plan_create(hvb_ctx* ctx, int n_frames, int frame_h, int frame_w, int
             }
             j.xtab = xkey[kx]; j.ytab = ykey[ky];
         }
-        // shared-memory need of the worst block of this job
-        double sx = (double)srcs[t].w / g.new_w, sy = (double)srcs[t].h / g.new_h;
-        int rows = (int)ceil(kTH * std::max(sy, 1e-9)) + 3;
-        int span = (int)ceil(kTW * std::max(sx, 1e-9)) + 3;            // source pixels per block row
-        if (j.mode == MODE_COPY) { rows = kTH; span = kTW; }
-        max_rows = std::max(max_rows, std::min(rows, srcs[t].h));
-        max_span = std::max(max_span, std::min(span, srcs[t].w));
+        // block list of this job with each block's source window; shared-memory need = the worst block
         const int by = hvb_div_up(g.out_h, kTH), bx = hvb_div_up(g.out_w, kTW);
         if (by > 4095 || bx > 4095) { delete p; hvb_set_error("output too large for the block table"); return HVB_ERR_CAPACITY; }
         for (int y = 0; y < by; y++)
-            for (int x = 0; x < bx; x++) blk.push_back(((uint32_t)t << 24) | ((uint32_t)y << 12) | (uint32_t)x);
+            for (int x = 0; x < bx; x++) {
+                LbBlock b{};
+                b.packed = ((uint32_t)t << 24) | ((uint32_t)y << 12) | (uint32_t)x;
+                const int oy0 = y * kTH, ox0 = x * kTW;
+                const int dy_lo = std::max(oy0 - g.top, 0), dy_hi = std::min(oy0 + kTH - g.top, g.new_h);
+                const int dx_lo = std::max(ox0 - g.left, 0), dx_hi = std::min(ox0 + kTW - g.left, g.new_w);
+                if (dy_lo < dy_hi && dx_lo < dx_hi) {
+                    int sx_hi, sy_hi;
+                    if (j.mode == MODE_LINEAR) {
+                        b.gx_lo = xt[j.xtab + dx_lo].sx;
+                        sx_hi = std::min(xt[j.xtab + dx_hi - 1].sx + 1, srcs[t].w - 1);
+                        b.sy_lo = yt[j.ytab + dy_lo].r0;
+                        sy_hi = yt[j.ytab + dy_hi - 1].r1;
+                    } else if (j.mode == MODE_AREA2) {
+                        b.gx_lo = 2 * dx_lo; sx_hi = 2 * dx_hi - 1; b.sy_lo = 2 * dy_lo; sy_hi = 2 * dy_hi - 1;
+                    } else {
+                        b.gx_lo = dx_lo; sx_hi = dx_hi - 1; b.sy_lo = dy_lo; sy_hi = dy_hi - 1;
+                    }
+                    b.gx_lo &= ~3;
+                    b.flags = 1 | (j.vec_ok ? 2 : 0);
+                    // 16-pixel (48-byte) groups when every row start of the window is 16-byte aligned and the
+                    // widened window stays inside the frame row
+                    {
+                        const int g16 = b.gx_lo & ~15;
+                        const int n16 = ((sx_hi - g16) >> 4) + 1;
+                        const int64_t off16 = j.src_off + (int64_t)g16 * 3;
+                        if ((frame_w * 3) % 16 == 0 && off16 % 16 == 0 && ((int64_t)frame_h * frame_w * 3) % 16 == 0 &&
+                            g16 + 16 * n16 <= j.row_px) {
+                            b.gx_lo = g16;
+                            b.flags |= 4;
+                            sx_hi = g16 + 16 * n16 - 1;
+                        }
+                    }
+                    b.n_rows = sy_hi - b.sy_lo + 1;
+                    b.n_groups = ((sx_hi - b.gx_lo) >> 2) + 1;
+                    b.row_px = j.row_px - b.gx_lo;
+                    b.src_off = j.src_off + (int64_t)b.sy_lo * frame_w * 3 + (int64_t)b.gx_lo * 3;
+                    max_rows = std::max(max_rows, b.n_rows);
+                    max_span = std::max(max_span, 4 * b.n_groups);
+                }
+                blk.push_back(b);
+            }
 
         p->read_bytes += (int64_t)srcs[t].w * srcs[t].h * 3;
         p->write_bytes += (int64_t)3 * g.out_h * g.out_w * 4;
@@ -441,7 +548,16 @@ int hvb_lb_plan_create(hvb_ctx* ctx, int n_frames, int frame_h, int frame_w, int
     p->read_bytes = std::min<int64_t>(p->read_bytes, (int64_t)frame_h * frame_w * 3) * n_frames;
     p->write_bytes *= n_frames;
     p->blocks_per_frame = (int)blk.size();
-    p->smem_row_stride = ((max_span + 3 + 3) / 4) * 4 + 4;             // pixel words per staged row (group-aligned start)
+    {
+        int64_t px_resize = 0, px_all = 0;
+        for (int t = 0; t < T; t++) {
+            const int64_t px = (int64_t)geo[t].out_h * geo[t].out_w;
+            px_all += px;
+            if (jobs[t].mode != MODE_COPY) px_resize += px;
+        }
+        p->resize_heavy = 2 * px_resize > px_all;
+    }
+    p->smem_row_stride = max_span + 4;                                 // pixel words per staged row (whole 4-pixel groups)
     p->smem_bytes = p->smem_row_stride * max_rows * 4;
     if (p->smem_bytes > ctx->max_smem_optin - 1024) {
         delete p;
@@ -470,12 +586,12 @@ int hvb_lb_plan_create(hvb_ctx* ctx, int n_frames, int frame_h, int frame_w, int
     if (yt.empty()) yt.push_back({0, 0, 0, 0});
     size_t o_jobs = 0;
     size_t o_blk = o_jobs + ((jobs.size() * sizeof(LbJob) + 255) & ~(size_t)255);
-    size_t o_x = o_blk + ((blk.size() * sizeof(uint32_t) + 255) & ~(size_t)255);
+    size_t o_x = o_blk + ((blk.size() * sizeof(LbBlock) + 255) & ~(size_t)255);
     size_t o_y = o_x + ((xt.size() * sizeof(XCoef) + 255) & ~(size_t)255);
     size_t total = o_y + yt.size() * sizeof(YCoef);
     std::vector<uint8_t> host(total, 0);
     memcpy(host.data() + o_jobs, jobs.data(), jobs.size() * sizeof(LbJob));
-    memcpy(host.data() + o_blk, blk.data(), blk.size() * sizeof(uint32_t));
+    memcpy(host.data() + o_blk, blk.data(), blk.size() * sizeof(LbBlock));
     memcpy(host.data() + o_x, xt.data(), xt.size() * sizeof(XCoef));
     memcpy(host.data() + o_y, yt.data(), yt.size() * sizeof(YCoef));
     cudaError_t e = cudaMalloc(&p->dev, total);
@@ -483,12 +599,13 @@ int hvb_lb_plan_create(hvb_ctx* ctx, int n_frames, int frame_h, int frame_w, int
     e = cudaMemcpy(p->dev, host.data(), total, cudaMemcpyHostToDevice);
     if (e != cudaSuccess) { cudaFree(p->dev); delete p; return hvb_cuda_fail(e, "cudaMemcpy(plan)", __FILE__, __LINE__); }
     p->jobs_dev = (LbJob*)((uint8_t*)p->dev + o_jobs);
-    p->blk2job_dev = (uint32_t*)((uint8_t*)p->dev + o_blk);
+    p->blk2job_dev = (LbBlock*)((uint8_t*)p->dev + o_blk);
     p->xtab_dev = (XCoef*)((uint8_t*)p->dev + o_x);
     p->ytab_dev = (YCoef*)((uint8_t*)p->dev + o_y);
     if (p->smem_bytes > 48 * 1024) {
-        HVB_CUDA(cudaFuncSetAttribute(letterbox_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, p->smem_bytes));
-        HVB_CUDA(cudaFuncSetAttribute(letterbox_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, p->smem_bytes));
+        HVB_CUDA(cudaFuncSetAttribute(letterbox_kernel<false, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, p->smem_bytes));
+        HVB_CUDA(cudaFuncSetAttribute(letterbox_kernel<false, 5>, cudaFuncAttributeMaxDynamicSharedMemorySize, p->smem_bytes));
+        HVB_CUDA(cudaFuncSetAttribute(letterbox_kernel<true, 5>, cudaFuncAttributeMaxDynamicSharedMemorySize, p->smem_bytes));
     }
     *out_plan = p;
     return HVB_OK;
@@ -549,14 +666,21 @@ static int lb_run(hvb_lb_plan* p, const uint8_t* frames_dev, float* out_f32, uin
     HVB_ARG(((uintptr_t)frames_dev & 3) == 0, "frames_dev must be 4-byte aligned");
     const int grid = p->blocks_per_frame * p->n_frames;
     const int64_t frame_bytes = (int64_t)p->frame_h * p->frame_w * 3;
+    const int al16 = (((uintptr_t)frames_dev & 15) == 0) ? 1 : 0;
+    // Resize-heavy plans (whole-frame letterbox) run best with 64 registers / 4 CTAs per SM; copy-dominated
+    // slice plans with 51 registers / 5 CTAs per SM (measured on B200, see profiles/).
     if (out_u8)
-        letterbox_kernel<true><<<grid, kThreads, p->smem_bytes, ctx->stream>>>(
+        letterbox_kernel<true, 5><<<grid, kThreads, p->smem_bytes, ctx->stream>>>(
             frames_dev, frame_bytes, p->frame_w * 3, p->jobs_dev, p->blk2job_dev, p->blocks_per_frame, p->xtab_dev,
-            p->ytab_dev, p->smem_row_stride, nullptr, out_u8);
+            p->ytab_dev, p->smem_row_stride, al16, nullptr, out_u8);
+    else if (p->resize_heavy)
+        letterbox_kernel<false, 4><<<grid, kThreads, p->smem_bytes, ctx->stream>>>(
+            frames_dev, frame_bytes, p->frame_w * 3, p->jobs_dev, p->blk2job_dev, p->blocks_per_frame, p->xtab_dev,
+            p->ytab_dev, p->smem_row_stride, al16, out_f32, nullptr);
     else
-        letterbox_kernel<false><<<grid, kThreads, p->smem_bytes, ctx->stream>>>(
+        letterbox_kernel<false, 5><<<grid, kThreads, p->smem_bytes, ctx->stream>>>(
             frames_dev, frame_bytes, p->frame_w * 3, p->jobs_dev, p->blk2job_dev, p->blocks_per_frame, p->xtab_dev,
-            p->ytab_dev, p->smem_row_stride, out_f32, nullptr);
+            p->ytab_dev, p->smem_row_stride, al16, out_f32, nullptr);
     HVB_LAUNCHED(ctx);
     return HVB_OK;
 }

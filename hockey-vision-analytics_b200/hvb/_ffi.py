@@ -12,7 +12,7 @@ import threading
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libhvb.so")
+LIB_PATH = os.environ.get("HVB_LIB") or os.path.join(_HERE, "libhvb.so")     # HVB_LIB: A/B kernel variants
 
 
 class HvbError(RuntimeError):

@@ -1,0 +1,136 @@
+"""Per-kernel timings of libhvb at the BASELINE config sizes (CUDA events around back-to-back
+launches on torch's current stream).  Prints one JSON line per kernel; used for profiles/*.md.
+
+    python tools/kernel_bench.py [--reps 20]
+"""
+import argparse
+import json
+import os
+import sys
+
+import numpy as np
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, os.path.join(ROOT, "hockey-vision-analytics_b200"))
+from hvb import _ffi  # noqa: E402
+from hvb.runtime import get_context  # noqa: E402
+from hvb.synth import planted_head, random_boxes, rink_frame  # noqa: E402
+
+PEAK = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))["hbm_gbs"] if os.path.exists(os.path.join(ROOT, "MEASURED_PEAKS.json")) else 6650.0
+
+
+def timed(fn, reps):
+    fn(); torch.cuda.synchronize()
+    a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    a.record()
+    for _ in range(reps):
+        fn()
+    b.record(); torch.cuda.synchronize()
+    return a.elapsed_time(b) / reps
+
+
+def report(name, ms, nbytes=None, flops=None, **kw):
+    d = {"kernel": name, "us": round(1e3 * ms, 2)}
+    if nbytes:
+        d["algorithmic_MB"] = round(nbytes / 1e6, 3)
+        d["GB_per_s"] = round(nbytes / (ms / 1e3) / 1e9, 1)
+        d["frac_hbm_peak"] = round(d["GB_per_s"] / PEAK, 3)
+    if flops:
+        d["TFLOP_per_s"] = round(flops / (ms / 1e3) / 1e12, 2)
+    d.update(kw)
+    print(json.dumps(d), flush=True)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--reps", type=int, default=20)
+    args = ap.parse_args()
+    ctx = get_context(0)
+    rng = np.random.default_rng(0)
+    R = args.reps
+
+    # K1a / K1b
+    for tag, n, h, w, mode, imgsz in (("K1a 1080p->736x1280 x16", 16, 1080, 1920, _ffi.LB_WHOLE, 1280),
+                                      ("K1a 1080p->736x1280 x64", 64, 1080, 1920, _ffi.LB_WHOLE, 1280),
+                                      ("K1a 720p->384x640 x64 (2x area path)", 64, 720, 1280, _ffi.LB_WHOLE, 640),
+                                      ("K1b 4K sliced exact x4", 4, 2160, 3840, _ffi.LB_SLICE_EXACT, 640),
+                                      ("K1b 4K sliced uniform x8", 8, 2160, 3840, _ffi.LB_SLICE_UNIFORM, 640)):
+        frames = torch.from_numpy(rng.integers(0, 256, (n, h, w, 3), dtype=np.uint8)).cuda()
+        plan = ctx.letterbox_plan(n, h, w, mode, imgsz)
+        out = plan.run(frames)
+        report(tag, timed(lambda: plan.run(frames, out), R), plan.read_bytes + plan.write_bytes)
+        del frames, out
+
+    # K2a: C2 (1080p, nc=2, 16 images), C4-like (640x640 tiles, nc=1, 160 images)
+    for tag, B, hw, nc, n_gt in (("K2a decode+NMS C2 736x1280 nc=2 x16", 16, (736, 1280), 2, 12),
+                                 ("K2a decode+NMS tiles 640x640 nc=1 x160", 160, (640, 640), 1, 3)):
+        lv = [(hw[0] // s, hw[1] // s) for s in (8, 16, 32)]
+        one = []
+        for _ in range(4):
+            cx, cy = rng.uniform(60, hw[1] - 60, n_gt), rng.uniform(60, hw[0] - 60, n_gt)
+            bw, bh = rng.uniform(20, 100, n_gt), rng.uniform(30, 200, n_gt)
+            gt = np.stack([cx - bw / 2, cy - bh / 2, cx + bw / 2, cy + bh / 2], 1)
+            one.append(planted_head(rng, lv, nc, gt, rng.integers(0, nc, n_gt)))
+        levels = [torch.from_numpy(np.stack([one[i % 4][l] for i in range(B)])).cuda() for l in range(3)]
+        meta = np.zeros((B,), _ffi.IMG_META)
+        meta["gain"], meta["clip_w"], meta["clip_h"], meta["out_slot"] = 1.0, hw[1], hw[0], np.arange(B)
+        meta_d = ctx.struct_to_device(meta)
+        outs = ctx.decode_nms(levels, nc, 0.4, 0.7, 300, False, meta=meta)
+        A = sum(a * b for a, b in lv)
+        report(tag, timed(lambda: ctx.decode_nms(levels, nc, 0.4, 0.7, 300, False, meta=meta_d, out=outs, check_overflow=False), R),
+               B * A * nc * 4, full_head_MB=round(B * A * (64 + nc) * 4 / 1e6, 2), kept=int(outs[3].sum().item()))
+    # K2b: 64 frames x ~120 merged detections
+    n_seg, per = 64, 120
+    boxes = np.concatenate([random_boxes(rng, per, 3840, 2160, 10, 40, np.float64)[0] for _ in range(n_seg)])
+    conf = rng.permutation(np.linspace(0.3, 0.99, n_seg * per)).astype(np.float32)
+    cls = np.zeros(n_seg * per, np.int32)
+    seg = (np.arange(n_seg + 1) * per).astype(np.int32)
+    bd, cd_, kd, sd = [torch.from_numpy(x).cuda() for x in (boxes, conf, cls, seg)]
+    report("K2b merge NMS 64 frames x 120 dets", timed(lambda: ctx.merge_nms(bd, cd_, kd, sd, n_seg, n_seg * per, 0.1), R),
+           n_seg * per * 40)
+
+    # K3a / K3b: 12 crops per 1080p frame, 64 frames
+    nf = 64
+    frs, bxs, fidx = [], [], []
+    for i in range(nf):
+        f, b, _, _ = rink_frame(rng, 1080, 1920, 12)
+        frs.append(f); bxs.append(b); fidx.append(np.full(len(b), i, np.int32))
+    frames = torch.from_numpy(np.stack(frs)).cuda()
+    bx = torch.from_numpy(np.concatenate(bxs).astype(np.float32)).cuda()
+    fi = torch.from_numpy(np.concatenate(fidx)).cuda()
+    m = bx.shape[0]
+    cd = ctx.crops_from_boxes(bx, fi, 1080, 1920)
+    desc = cd.cpu().numpy().view(_ffi.CROP_DESC)[:m]
+    roi_px = sum((int(h * 0.6) - int(h * 0.1)) * (int(w * 0.8) - int(w * 0.2)) if (h >= 40 and w >= 20) else h * w
+                 for h, w in zip(desc["h"], desc["w"]))
+    feat = ctx.empty((m, 49), torch.float64)
+    report("K3a colour features %d crops" % m, timed(lambda: ctx.color_features(frames, cd, m, out_feat=feat), R),
+           roi_px * 3 + m * 392, roi_kpx_per_crop=round(roi_px / m / 1e3, 2))
+    report("K3b MobileNetV3 prep %d crops" % m, timed(lambda: ctx.mnv3_preprocess(frames, cd, m), R), roi_px * 3 + m * 98304)
+    report("crops_from_boxes %d" % m, timed(lambda: ctx.crops_from_boxes(bx, fi, 1080, 1920), R))
+
+    # K4a: standardise + affinity, tensor-core Gram
+    for n in (250, 2000, 8192):
+        x = torch.from_numpy(rng.normal(0, 1, (n, 625))).cuda()
+        mean, scale, xs = ctx.standardize(x)
+        report("K4a standardize N=%d" % n, timed(lambda: ctx.standardize(x), R), n * 625 * 8 * 3)
+        report("K4a gram tcgen05 N=%d (3xTF32, K'=1920)" % n, timed(lambda: ctx.gram_tc(xs), R), flops=2.0 * n * n * 1920,
+               useful_TFLOP_per_s=None)
+        if n <= 2000:
+            report("K4a affinity mode0 (tcgen05+refine) N=%d" % n, timed(lambda: ctx.gram_affinity(xs, 1.0, 0), max(R // 4, 2)), flops=2.0 * n * n * 625)
+            report("K4a affinity mode1 (fp64) N=%d" % n, timed(lambda: ctx.gram_affinity(xs, 1.0, 1), max(R // 4, 2)), flops=3.0 * n * n * 625)
+
+    # K4b: 8 clips x (40 tracks x 40 detections)
+    T = D = 40
+    P = 8
+    a = torch.from_numpy(np.concatenate([random_boxes(rng, T, 1920, 1080, 40, 200, np.float64)[0] for _ in range(P)])).cuda()
+    b = torch.from_numpy(np.concatenate([random_boxes(rng, D, 1920, 1080, 40, 200, np.float64)[0] for _ in range(P)])).cuda()
+    ao = torch.from_numpy((np.arange(P + 1) * T).astype(np.int32)).cuda()
+    bo = torch.from_numpy((np.arange(P + 1) * D).astype(np.int32)).cuda()
+    oo = torch.from_numpy((np.arange(P) * T * D).astype(np.int64)).cuda()
+    report("K4b IoU cost 8 clips x 40x40", timed(lambda: ctx.iou_cost(a, b, None, ao, bo, oo, P, T, D, P * T * D, 2), R), P * (T + D) * 32 + P * T * D * 8)
+
+
+if __name__ == "__main__":
+    main()
