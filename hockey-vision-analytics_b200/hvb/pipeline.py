@@ -96,6 +96,55 @@ class HotPath:
         return res
 
 
+    def process_stream(self, chunks):
+        """Pipelined host API: `chunks` yields (frames uint8[n,H,W,3] pinned torch tensor or numpy, team_boxes
+        float32[M,4], team_frame_idx int32[M]) per step; results are yielded in order.  The H2D copy of chunk
+        i+1 runs on a side stream while chunk i computes (two device frame buffers, guarded by events), so a
+        step's copy is hidden behind the previous step's kernels instead of serialising with them."""
+        dev = self.ctx.device
+        copy_stream = torch.cuda.Stream(device=dev)
+        main = torch.cuda.current_stream(dev)
+        bufs, free_ev = [None, None], [None, None]
+
+        def stage(i, item):
+            frames, tb, ti = item
+            src = frames if isinstance(frames, torch.Tensor) else torch.from_numpy(np.ascontiguousarray(frames)).pin_memory()
+            slot = i & 1
+            if bufs[slot] is None or bufs[slot].shape != src.shape:
+                bufs[slot] = torch.empty(src.shape, dtype=torch.uint8, device=dev)
+            with torch.cuda.stream(copy_stream):
+                if free_ev[slot] is not None:
+                    copy_stream.wait_event(free_ev[slot])            # previous user of this buffer is done
+                bufs[slot].copy_(src, non_blocking=True)
+                tbd = torch.from_numpy(np.ascontiguousarray(tb, np.float32)).pin_memory().to(dev, non_blocking=True)
+                tid = torch.from_numpy(np.ascontiguousarray(ti, np.int32)).pin_memory().to(dev, non_blocking=True)
+                ready = torch.cuda.Event()
+                ready.record(copy_stream)
+            return slot, tbd, tid, ready, src
+
+        def finish(staged):
+            slot, tbd, tid, ready, _keep = staged
+            main.wait_event(ready)
+            tbd.record_stream(main); tid.record_stream(main)
+            out = self.process_chunk_device(bufs[slot], tbd, tid)
+            ev = torch.cuda.Event()
+            ev.record(main)
+            free_ev[slot] = ev
+            cnt = out["count"].cpu().numpy()
+            res = dict(count=cnt, xyxy=out["xyxy"].cpu().numpy(), conf=out["conf"].cpu().numpy(), cls=out["cls"].cpu().numpy())
+            res["team"] = self.rule(out["team_tail"].cpu().numpy())
+            return res
+
+        pending = None
+        for i, item in enumerate(chunks):
+            staged = stage(i, item)
+            if pending is not None:
+                yield finish(pending)
+            pending = staged
+        if pending is not None:
+            yield finish(pending)
+
+
 class SlicedPuckPath:
     """4K puck detection through the slicer: K1b -> YOLOv8n forward per shape class -> K2a -> gather -> K2b."""
 

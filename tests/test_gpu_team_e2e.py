@@ -173,3 +173,26 @@ def test_detector_whole_frame_matches_restated_path(ctx):
     if len(rx):
         assert np.abs(got.confidence - rc).max() <= 1e-6 and np.abs(got.xyxy - rx).max() <= 1e-3
     assert len(det.detect_players(frame)) <= len(got)
+
+
+def test_pipelined_stream_equals_chunk_api(ctx):
+    """HotPath.process_stream (H2D of chunk i+1 overlapped with chunk i) returns what process_chunk returns."""
+    from hvb.pipeline import HotPath
+    from hvb.synth import rink_frame
+    path = HotPath("cuda:0", "n", 2, 640, 0.4, seed=0)
+    rng = np.random.default_rng(0)
+    chunks = []
+    for _ in range(3):
+        fr, bx, fi = [], [], []
+        for i in range(2):
+            f, b, _, _ = rink_frame(rng, 540, 960, 6, 0.5)
+            fr.append(f); bx.append(b); fi.append(np.full(len(b), i, np.int32))
+        chunks.append((np.stack(fr), np.concatenate(bx).astype(np.float32), np.concatenate(fi)))
+    fd = torch.from_numpy(chunks[0][0]).cuda()
+    path.fit_from_frames(fd, torch.from_numpy(chunks[0][1]).cuda(), torch.from_numpy(chunks[0][2]).cuda())
+    ref = [path.process_chunk(*c) for c in chunks]
+    got = list(path.process_stream(iter(chunks)))
+    assert len(got) == 3
+    for a, b in zip(ref, got):
+        assert np.array_equal(a["team"], b["team"]) and np.array_equal(a["count"], b["count"])
+        assert len(a["team"]) == 12
