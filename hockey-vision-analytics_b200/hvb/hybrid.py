@@ -145,7 +145,8 @@ class HybridTeamClassifier:
         raw_h = raw.cpu().numpy().view(_ffi.COLOR_RAW)[: len(crops)]
         self.fit_features(feats, positions, raw_h)
 
-    def fit_features(self, feats: torch.Tensor, positions=None, raw_stats: Optional[np.ndarray] = None) -> None:
+    def fit_features(self, feats: torch.Tensor, positions=None, raw_stats: Optional[np.ndarray] = None,
+                     cluster: bool = True) -> None:
         """Fit from a float64[N,625] device feature matrix (e.g. gathered from several GPUs)."""
         ctx = self.ctx
         n = feats.shape[0]
@@ -162,6 +163,10 @@ class HybridTeamClassifier:
             xs = torch.cat([xs, ctx.to_device(pn.astype(np.float64))], 1).contiguous()
         self.features_normalized_ = xs
         _, a = ctx.gram_affinity(xs, 1.0, self.affinity_mode, want_d2=False, want_a=True)
+        if not cluster:                      # scaler + affinity only (multi-GPU ranks other than the one that clusters)
+            self.affinity_matrix_dev_ = a
+            self.clusterer = "affinity-only"
+            return
         self.affinity_matrix_ = a.cpu().numpy()
         import warnings
         from sklearn.cluster import SpectralClustering
