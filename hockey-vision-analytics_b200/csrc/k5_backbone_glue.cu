@@ -1,0 +1,301 @@
+// K5 — the element-wise glue between the library convolutions of the YOLOv8 / MobileNetV3 forwards
+// (reached from hockey/main.py:179-184 and common/team_hybrid.py:73-81).  PyTorch runs the
+// convolutions; everything between two convolutions is one pass over HBM here instead of the 3-6
+// passes eager PyTorch makes (broadcast bias add, SiLU, residual add, chunk copy, cat, upsample):
+//
+//   bias_act_kernel       y = act(conv_raw + bias) (+ residual), written to up to two destinations
+//                         (a contiguous NHWC tensor for the next convolution and/or a channel slice
+//                         of a concat buffer) — ultralytics Conv.forward_fuse, Bottleneck.forward,
+//                         and the torch.cat of C2f.forward / SPPF.forward / Detect.forward
+//   concat_nhwc_kernel    channel concat of up to four NHWC sources, each optionally nearest-
+//                         upsampled by 2^s — nn.Upsample(2,'nearest') + Concat of the yolov8.yaml neck
+//   stem_conv_kernel      layer 0: 3x3 stride-2 convolution of the NCHW letterbox output (K1) straight
+//                         to NHWC with bias + SiLU — exact fp32 FMA, weights as kernel parameters
+//                         (constant bank operands), one block = 128 output pixels of one row
+//
+// All three are HBM-bound streaming kernels: 128-bit accesses, 4 independent vectors in flight per
+// thread, grid sized to the data.  Layout everywhere: NHWC ("channels_last") float32.
+#include "hvb_common.cuh"
+
+namespace {
+
+enum { ACT_NONE = 0, ACT_SILU = 1, ACT_RELU = 2, ACT_HSWISH = 3 };
+
+template <int ACT>
+__device__ __forceinline__ float act_fn(float v) {
+    if (ACT == ACT_SILU) return __fdiv_rn(v, __fadd_rn(1.0f, expf(-v)));          // x / (1 + exp(-x)), as torch's silu kernel
+    if (ACT == ACT_RELU) return fmaxf(v, 0.0f);
+    if (ACT == ACT_HSWISH) return __fdiv_rn(__fmul_rn(v, fminf(fmaxf(__fadd_rn(v, 3.0f), 0.0f), 6.0f)), 6.0f);
+    return v;
+}
+
+template <int V> struct Vec;
+template <> struct Vec<4> { typedef float4 T; };
+template <> struct Vec<2> { typedef float2 T; };
+template <> struct Vec<1> { typedef float T; };
+
+template <int V> __device__ __forceinline__ void vload(const float* p, float (&r)[V]) {
+    typename Vec<V>::T t = *reinterpret_cast<const typename Vec<V>::T*>(p);
+    const float* f = reinterpret_cast<const float*>(&t);
+#pragma unroll
+    for (int i = 0; i < V; ++i) r[i] = f[i];
+}
+template <int V> __device__ __forceinline__ void vstore(float* p, const float (&r)[V]) {
+    typename Vec<V>::T t;
+    float* f = reinterpret_cast<float*>(&t);
+#pragma unroll
+    for (int i = 0; i < V; ++i) f[i] = r[i];
+    *reinterpret_cast<typename Vec<V>::T*>(p) = t;
+}
+
+struct EpiArgs {
+    const float* x;        // [npix, C] raw convolution output (NHWC, dense)
+    const float* bias;     // [C] or null
+    const float* res;      // [npix, C] dense residual or null
+    float* out1;           // out1[p*ld1 + off1 + c], all C channels (may alias x), or null
+    float* out2;           // out2[p*ld2 + off2 + (c - c2_begin)] for c in [c2_begin, c2_begin + c2_count), or null
+    int64_t ld1, off1, ld2, off2;
+    uint32_t total;        // npix * C / V
+    uint32_t cv;           // C / V
+    int c2_begin, c2_count;
+};
+
+constexpr int EPI_THREADS = 256;
+constexpr int EPI_UNROLL = 4;
+
+template <int V, int ACT>
+__global__ void __launch_bounds__(EPI_THREADS)
+bias_act_kernel(const EpiArgs a) {
+    const uint32_t base = blockIdx.x * (EPI_THREADS * EPI_UNROLL) + threadIdx.x;
+    float v[EPI_UNROLL][V], r[EPI_UNROLL][V];
+    uint32_t idx[EPI_UNROLL];
+#pragma unroll
+    for (int u = 0; u < EPI_UNROLL; ++u) {
+        idx[u] = base + u * EPI_THREADS;
+        if (idx[u] < a.total) vload<V>(a.x + (size_t)idx[u] * V, v[u]);
+    }
+    if (a.res) {
+#pragma unroll
+        for (int u = 0; u < EPI_UNROLL; ++u)
+            if (idx[u] < a.total) vload<V>(a.res + (size_t)idx[u] * V, r[u]);
+    }
+#pragma unroll
+    for (int u = 0; u < EPI_UNROLL; ++u) {
+        if (idx[u] >= a.total) continue;
+        const uint32_t p = idx[u] / a.cv;
+        const int c = (int)(idx[u] - p * a.cv) * V;
+        float b[V];
+        if (a.bias) vload<V>(a.bias + c, b);
+#pragma unroll
+        for (int i = 0; i < V; ++i) {
+            float t = a.bias ? __fadd_rn(v[u][i], b[i]) : v[u][i];
+            t = act_fn<ACT>(t);
+            if (a.res) t = __fadd_rn(r[u][i], t);                                   // Bottleneck: x + cv2(cv1(x))
+            v[u][i] = t;
+        }
+        if (a.out1) vstore<V>(a.out1 + (size_t)p * a.ld1 + a.off1 + c, v[u]);
+        if (a.out2) {
+            const int c2 = c - a.c2_begin;
+            if (c2 >= 0 && c2 < a.c2_count) vstore<V>(a.out2 + (size_t)p * a.ld2 + a.off2 + c2, v[u]);
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+struct CatArgs {
+    const float* src[4];
+    int c[4];              // channels of each source
+    int shift[4];          // source spatial size = (H >> shift, W >> shift)
+    int nsrc;
+    int H, W, ctot;        // output [n, H, W, ctot]
+    float* out;
+};
+
+template <int V>
+__global__ void __launch_bounds__(256)
+concat_nhwc_kernel(const CatArgs a) {
+    const int row = blockIdx.x;                       // n * H + y
+    const int n = row / a.H, y = row - n * a.H;
+    const uint32_t cv = a.ctot / V;
+    const uint32_t rowlen = (uint32_t)a.W * cv;
+    float* orow = a.out + (size_t)row * a.W * a.ctot;
+    for (uint32_t j = blockIdx.y * 256 + threadIdx.x; j < rowlen; j += gridDim.y * 256) {
+        const uint32_t x = j / cv;
+        int c = (int)(j - x * cv) * V;
+        const int c_out = c;
+        int s = 0;
+        while (s + 1 < a.nsrc && c >= a.c[s]) { c -= a.c[s]; ++s; }
+        const int sh = a.shift[s];
+        const int hs = a.H >> sh, ws = a.W >> sh;
+        const float* p = a.src[s] + (((size_t)n * hs + (y >> sh)) * ws + (x >> sh)) * a.c[s] + c;
+        float t[V];
+        vload<V>(p, t);
+        vstore<V>(orow + (size_t)x * a.ctot + c_out, t);
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// Stem: out[n, oy, ox, co] = silu(bias[co] + sum_{ci,ky,kx} w[co][ci][ky][kx] * in[n, ci, 2oy-1+ky, 2ox-1+kx])
+// Input NCHW (what K1 writes), zero padding 1.  Weights arrive as kernel parameters, i.e. in the
+// constant bank: with the loops fully unrolled every FFMA takes its weight as a c[0][..] operand, so
+// the inner loop is 27 shared-memory loads + 27*CO FFMAs per pixel and no weight traffic at all.
+constexpr int STEM_PX = 128;                 // output pixels (one row segment) per block = threads per block
+template <int CO> struct StemParams { float w[27 * CO]; float b[CO]; };   // w index: ((ci*3+ky)*3+kx)*CO + co
+
+template <int CO>
+__global__ void __launch_bounds__(STEM_PX)
+stem_conv_kernel(const float* __restrict__ in, float* __restrict__ out, int H, int W, int OH, int OW,
+                 const __grid_constant__ StemParams<CO> prm) {
+    __shared__ float s_in[3][3][2 * STEM_PX + 2];            // [ci][ky][input column - (2*ox0 - 1)]
+    __shared__ __align__(16) float s_out[STEM_PX * (CO + 1)]; // +1: conflict-free transposed read
+    const int n = blockIdx.z, oy = blockIdx.y, ox0 = blockIdx.x * STEM_PX;
+    const int ix0 = 2 * ox0 - 1;
+    const int ncols = min(2 * STEM_PX + 1, 2 * (OW - ox0) + 1);
+    for (int i = threadIdx.x; i < 9 * (2 * STEM_PX + 2); i += STEM_PX) {
+        const int plane = i / (2 * STEM_PX + 2), col = i - plane * (2 * STEM_PX + 2);
+        const int ci = plane / 3, ky = plane - ci * 3;
+        const int iy = 2 * oy - 1 + ky, ix = ix0 + col;
+        float v = 0.0f;
+        if (col < ncols && iy >= 0 && iy < H && ix >= 0 && ix < W)
+            v = __ldg(in + (((size_t)n * 3 + ci) * H + iy) * W + ix);
+        s_in[ci][ky][col] = v;
+    }
+    __syncthreads();
+    const int t = threadIdx.x;
+    float acc[CO];
+#pragma unroll
+    for (int co = 0; co < CO; ++co) acc[co] = prm.b[co];
+#pragma unroll
+    for (int ci = 0; ci < 3; ++ci)
+#pragma unroll
+        for (int ky = 0; ky < 3; ++ky)
+#pragma unroll
+            for (int kx = 0; kx < 3; ++kx) {
+                const float x = s_in[ci][ky][2 * t + kx];
+#pragma unroll
+                for (int co = 0; co < CO; ++co) acc[co] = __fmaf_rn(prm.w[((ci * 3 + ky) * 3 + kx) * CO + co], x, acc[co]);
+            }
+#pragma unroll
+    for (int co = 0; co < CO; ++co) s_out[t * (CO + 1) + co] = act_fn<ACT_SILU>(acc[co]);
+    __syncthreads();
+    // the block's 128 x CO outputs are one contiguous NHWC run: coalesced stores
+    const int npx = min(STEM_PX, OW - ox0);
+    float* o = out + (((size_t)n * OH + oy) * OW + ox0) * CO;
+    for (int i = threadIdx.x; i < npx * CO; i += STEM_PX) {
+        const int px = i / CO, co = i - px * CO;
+        o[i] = s_out[px * (CO + 1) + co];
+    }
+}
+
+template <int V>
+int launch_bias_act(hvb_ctx* ctx, const EpiArgs& a, int act) {
+    const uint32_t per_block = EPI_THREADS * EPI_UNROLL;
+    const uint32_t grid = (a.total + per_block - 1) / per_block;
+    switch (act) {
+        case ACT_NONE: bias_act_kernel<V, ACT_NONE><<<grid, EPI_THREADS, 0, ctx->stream>>>(a); break;
+        case ACT_SILU: bias_act_kernel<V, ACT_SILU><<<grid, EPI_THREADS, 0, ctx->stream>>>(a); break;
+        case ACT_RELU: bias_act_kernel<V, ACT_RELU><<<grid, EPI_THREADS, 0, ctx->stream>>>(a); break;
+        case ACT_HSWISH: bias_act_kernel<V, ACT_HSWISH><<<grid, EPI_THREADS, 0, ctx->stream>>>(a); break;
+        default: hvb_set_error("hvb_bias_act: unknown activation %d", act); return HVB_ERR_ARG;
+    }
+    HVB_LAUNCHED(ctx);
+    return HVB_OK;
+}
+
+template <int CO>
+int launch_stem(hvb_ctx* ctx, const float* in, const float* w_host, const float* b_host, int n, int h, int w, float* out) {
+    StemParams<CO> prm;
+    // PyTorch weight layout [CO][3][3][3] (co, ci, ky, kx) -> tap-major so one tap's CO weights are adjacent
+    for (int co = 0; co < CO; ++co)
+        for (int k = 0; k < 27; ++k) prm.w[k * CO + co] = w_host[co * 27 + k];
+    for (int co = 0; co < CO; ++co) prm.b[co] = b_host ? b_host[co] : 0.0f;
+    const int oh = (h - 1) / 2 + 1, ow = (w - 1) / 2 + 1;           // floor((h + 2 - 3) / 2) + 1
+    dim3 grid((ow + STEM_PX - 1) / STEM_PX, oh, n);
+    stem_conv_kernel<CO><<<grid, STEM_PX, 0, ctx->stream>>>(in, out, h, w, oh, ow, prm);
+    HVB_LAUNCHED(ctx);
+    return HVB_OK;
+}
+
+inline bool aligned_to(const void* p, int bytes) { return ((uintptr_t)p % bytes) == 0; }
+
+}  // namespace
+
+extern "C" {
+
+int hvb_bias_act(hvb_ctx* ctx, const float* x_dev, const float* bias_dev, const float* residual_dev, int64_t npix,
+                 int channels, int act, float* out1_dev, int64_t out1_ld, int64_t out1_off, float* out2_dev,
+                 int64_t out2_ld, int64_t out2_off, int c2_begin, int c2_count) {
+    HVB_CHECK_CTX(ctx);
+    HVB_ARG(npix >= 0 && channels > 0, "bad sizes");
+    if (npix == 0) return HVB_OK;
+    HVB_ARG(x_dev && (out1_dev || out2_dev), "null pointer");
+    HVB_ARG(!out1_dev || (out1_ld >= channels && out1_off >= 0 && out1_off + channels <= out1_ld), "out1 slice outside its row");
+    HVB_ARG(!out2_dev || (c2_begin >= 0 && c2_count > 0 && c2_begin + c2_count <= channels && out2_off >= 0 &&
+                          out2_off + c2_count <= out2_ld), "out2 slice outside its row");
+    HVB_ARG(npix * (int64_t)channels < ((int64_t)1 << 32) - 4096, "tensor too large for one launch");
+    EpiArgs a;
+    a.x = x_dev; a.bias = bias_dev; a.res = residual_dev; a.out1 = out1_dev; a.out2 = out2_dev;
+    a.ld1 = out1_ld; a.off1 = out1_off; a.ld2 = out2_ld; a.off2 = out2_off;
+    a.c2_begin = c2_begin; a.c2_count = out2_dev ? c2_count : 0;
+    // widest vector every address involved is aligned to
+    auto ok = [&](int v) {
+        if (channels % v) return false;
+        if (!aligned_to(x_dev, 4 * v) || (bias_dev && !aligned_to(bias_dev, 4 * v)) || (residual_dev && !aligned_to(residual_dev, 4 * v))) return false;
+        if (out1_dev && (!aligned_to(out1_dev, 4 * v) || out1_ld % v || out1_off % v)) return false;
+        if (out2_dev && (!aligned_to(out2_dev, 4 * v) || out2_ld % v || out2_off % v || c2_begin % v || c2_count % v)) return false;
+        return true;
+    };
+    const int v = ok(4) ? 4 : ok(2) ? 2 : 1;
+    a.cv = (uint32_t)(channels / v);
+    a.total = (uint32_t)(npix * channels / v);
+    if (v == 4) return launch_bias_act<4>(ctx, a, act);
+    if (v == 2) return launch_bias_act<2>(ctx, a, act);
+    return launch_bias_act<1>(ctx, a, act);
+}
+
+int hvb_concat_nhwc(hvb_ctx* ctx, const float* const src_dev[4], const int32_t src_channels[4], const int32_t src_shift[4],
+                    int n_src, int n, int h, int w, float* out_dev) {
+    HVB_CHECK_CTX(ctx);
+    HVB_ARG(n_src >= 1 && n_src <= 4 && n >= 0 && h > 0 && w > 0 && out_dev, "bad arguments");
+    if (n == 0) return HVB_OK;
+    CatArgs a;
+    a.nsrc = n_src; a.H = h; a.W = w; a.out = out_dev; a.ctot = 0;
+    int v = 4;
+    for (int s = 0; s < 4; ++s) { a.src[s] = nullptr; a.c[s] = 0; a.shift[s] = 0; }
+    for (int s = 0; s < n_src; ++s) {
+        HVB_ARG(src_dev[s] && src_channels[s] > 0 && src_shift[s] >= 0 && src_shift[s] < 8, "bad source");
+        HVB_ARG((h % (1 << src_shift[s])) == 0 && (w % (1 << src_shift[s])) == 0, "output size not a multiple of the upsample factor");
+        a.src[s] = src_dev[s]; a.c[s] = src_channels[s]; a.shift[s] = src_shift[s];
+        a.ctot += src_channels[s];
+        while (v > 1 && (src_channels[s] % v || !aligned_to(src_dev[s], 4 * v))) v >>= 1;
+    }
+    while (v > 1 && !aligned_to(out_dev, 4 * v)) v >>= 1;
+    const int64_t rows = (int64_t)n * h;
+    HVB_ARG(rows < ((int64_t)1 << 31), "n*h exceeds the grid's x extent; split the batch");
+    const uint32_t rowlen = (uint32_t)w * (a.ctot / v);
+    int gy = (int)((rowlen + 255) / 256);
+    if (gy > 64) gy = 64;
+    dim3 grid((unsigned)rows, gy);
+    if (v == 4) concat_nhwc_kernel<4><<<grid, 256, 0, ctx->stream>>>(a);
+    else if (v == 2) concat_nhwc_kernel<2><<<grid, 256, 0, ctx->stream>>>(a);
+    else concat_nhwc_kernel<1><<<grid, 256, 0, ctx->stream>>>(a);
+    HVB_LAUNCHED(ctx);
+    return HVB_OK;
+}
+
+int hvb_stem_conv(hvb_ctx* ctx, const float* in_nchw_dev, const float* weight_host, const float* bias_host, int n, int h,
+                  int w, int c_out, float* out_nhwc_dev) {
+    HVB_CHECK_CTX(ctx);
+    HVB_ARG(in_nchw_dev && weight_host && out_nhwc_dev && n >= 0 && h > 0 && w > 0, "bad arguments");
+    if (n == 0) return HVB_OK;
+    HVB_ARG(n <= 65535 && (h + 1) / 2 <= 65535, "grid extent");
+    switch (c_out) {
+        case 16: return launch_stem<16>(ctx, in_nchw_dev, weight_host, bias_host, n, h, w, out_nhwc_dev);
+        case 32: return launch_stem<32>(ctx, in_nchw_dev, weight_host, bias_host, n, h, w, out_nhwc_dev);
+        case 48: return launch_stem<48>(ctx, in_nchw_dev, weight_host, bias_host, n, h, w, out_nhwc_dev);
+        case 64: return launch_stem<64>(ctx, in_nchw_dev, weight_host, bias_host, n, h, w, out_nhwc_dev);
+        default: hvb_set_error("hvb_stem_conv: c_out must be 16/32/48/64 (YOLOv8 n/s/m/l), got %d", c_out); return HVB_ERR_UNSUPPORTED;
+    }
+}
+
+}  // extern "C"

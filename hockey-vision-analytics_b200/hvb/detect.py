@@ -38,7 +38,8 @@ class Detector:
 
     def __init__(self, model: torch.nn.Module, device="cuda:0", imgsz: int = 1280, conf: float = 0.4, iou: float = 0.7,
                  max_det: int = 300, agnostic_nms: bool = False, class_names: Optional[Dict[int, str]] = None,
-                 autocast_dtype: Optional[torch.dtype] = None, channels_last: bool = False, fuse: bool = False):
+                 autocast_dtype: Optional[torch.dtype] = None, channels_last: bool = False, fuse: bool = False,
+                 glue: Optional[bool] = None):
         self.ctx: Context = get_context(device)
         self.device = self.ctx.device
         if fuse:
@@ -51,6 +52,14 @@ class Detector:
             self.model = self.model.to(memory_format=torch.channels_last)
         self.channels_last = channels_last
         self.nc = int(model.nc)
+        # K5: run everything between the convolutions (bias, SiLU, residual, concat, upsample, layer 0) in libhvb
+        from .models.yolov8 import YOLOv8
+        if glue is None:
+            glue = fuse and channels_last and autocast_dtype is None and isinstance(model, YOLOv8)
+        self.runner = None
+        if glue:
+            from .models.fused import FusedYOLOv8
+            self.runner = FusedYOLOv8(self.model, self.ctx)
         self.imgsz, self.conf, self.iou, self.max_det, self.agnostic = imgsz, conf, iou, max_det, agnostic_nms
         self.autocast_dtype = autocast_dtype
         self.class_names = class_names or {i: str(i) for i in range(self.nc)}
@@ -76,6 +85,8 @@ class Detector:
 
     def forward_heads(self, x: torch.Tensor) -> List[torch.Tensor]:
         """Backbone forward (PyTorch).  Returns the 3 raw head tensors as contiguous float32 NCHW."""
+        if self.runner is not None:
+            return self.runner(x)
         with torch.no_grad():
             if self.channels_last:
                 x = x.contiguous(memory_format=torch.channels_last)

@@ -48,7 +48,7 @@ class _Scaler:
 
 class HybridTeamClassifier:
     def __init__(self, device: str = "cuda:0", n_clusters: int = 2, trunk: Optional[torch.nn.Module] = None,
-                 seed: int = 0, affinity_mode: int = 0):
+                 seed: int = 0, affinity_mode: int = 0, fold_batchnorm: bool = True):
         self.ctx: Context = get_context(device)
         self.device = device
         self.n_clusters = n_clusters
@@ -57,6 +57,9 @@ class HybridTeamClassifier:
             trunk = build_trunk(seed)
         import copy
         self.feature_extractor = copy.deepcopy(trunk).to(self.ctx.device).eval()    # the caller's module stays where it is
+        if fold_batchnorm:
+            from .models.mnv3 import fold_bn
+            fold_bn(self.feature_extractor)
         self.scaler = _Scaler()
         self.player_history: Dict[int, List[int]] = defaultdict(list)
         self.history_window = 15

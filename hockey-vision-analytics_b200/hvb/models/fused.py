@@ -1,0 +1,152 @@
+"""YOLOv8 forward with the convolutions in PyTorch (cuDNN) and everything between them in libhvb (K5).
+
+Eager PyTorch spends ~2/3 of a YOLOv8m forward outside the convolutions: a broadcast bias add and a
+SiLU pass per layer, `.contiguous()` copies of `chunk` views, `torch.cat`, `nn.Upsample`.  Here each
+convolution is called without bias and followed by ONE `hvb_bias_act` pass that adds the bias, applies
+SiLU, adds the Bottleneck residual and writes the result both where the next convolution reads it and
+into its slice of the C2f / SPPF / Detect concat buffer; the neck's Upsample+Concat is one
+`hvb_concat_nhwc` pass; layer 0 reads K1's NCHW output directly (`hvb_stem_conv`).
+
+The layer graph is ultralytics 8.3.148 `yolov8.yaml` (the model the reference loads at
+hockey/main.py:77 and runs at :179-184), same as hvb.models.yolov8.YOLOv8 whose (conv+bn folded)
+weights this runner borrows.  Returns the three raw Detect tensors [B, 64+nc, H_i, W_i], channels-last.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from typing import List
+
+import numpy as np
+import torch
+import torch.nn.functional as F
+
+from .. import _ffi
+from .yolov8 import YOLOv8, ConvBnAct, C2f, SPPF, fuse_conv_bn
+
+_SILU, _NONE = 1, 0
+CL = torch.channels_last
+
+
+class _Conv:
+    """One folded convolution: channels-last weight, bias kept separate for the K5 epilogue."""
+
+    def __init__(self, conv: torch.nn.Conv2d, device):
+        self.w = conv.weight.detach().to(device).contiguous(memory_format=CL)
+        b = conv.bias.detach() if conv.bias is not None else torch.zeros(conv.out_channels)
+        self.b = b.to(device).float().contiguous()
+        self.stride, self.padding, self.cout = conv.stride, conv.padding, conv.out_channels
+
+    def raw(self, x):
+        y = torch.conv2d(x, self.w, None, self.stride, self.padding)
+        if not y.is_contiguous(memory_format=CL):           # K5 kernels address dense NHWC
+            y = y.contiguous(memory_format=CL)
+        return y
+
+
+class FusedYOLOv8:
+    def __init__(self, model: YOLOv8, ctx, stem_kernel: bool = True):
+        import copy
+        m = copy.deepcopy(model).eval()
+        if any(isinstance(x.bn, torch.nn.BatchNorm2d) for x in m.modules() if isinstance(x, ConvBnAct)):
+            m = fuse_conv_bn(m)
+        self.ctx, self.nc, self.m = ctx, int(model.nc), m
+        dev = ctx.device
+        self.convs = {}
+        for mod in m.modules():
+            if isinstance(mod, torch.nn.Conv2d):
+                self.convs[mod] = _Conv(mod, dev)
+        self.stem_w = m.b0.conv.weight.detach().float().cpu().contiguous().numpy()
+        self.stem_b = m.b0.conv.bias.detach().float().cpu().contiguous().numpy()
+        self.use_stem = stem_kernel and self.stem_w.shape[0] in (16, 32, 48, 64)
+        self._lib, self._h = ctx.lib, ctx.handle
+
+    # ------------------------------------------------------------------ primitives (ctx lock is held by forward)
+    def _epi(self, x, bias, act=_SILU, res=None, out1=None, off1=0, out2=None, off2=0, c2b=0, c2n=0, inplace=True):
+        npix, c = x.shape[0] * x.shape[2] * x.shape[3], x.shape[1]
+        if out1 is None and inplace:
+            out1 = x
+        p = lambda t: C.c_void_p(t.data_ptr()) if t is not None else C.c_void_p(0)
+        _ffi.check(self._lib.hvb_bias_act(self._h, p(x), p(bias), p(res), npix, c, act,
+                                          p(out1), out1.shape[1] if out1 is not None else 0, off1,
+                                          p(out2), out2.shape[1] if out2 is not None else 0, off2, c2b, c2n))
+        return out1 if out1 is not None else out2
+
+    def _buf(self, n, c, h, w):
+        return torch.empty((n, c, h, w), dtype=torch.float32, device=self.ctx.device, memory_format=CL)
+
+    def _cba(self, mod: ConvBnAct, x):
+        k = self.convs[mod.conv]
+        return self._epi(k.raw(x), k.b)
+
+    def _c2f(self, mod: C2f, x):
+        c, nb = mod.c, len(mod.m)
+        n, _, h, w = x.shape
+        cat = self._buf(n, (2 + nb) * c, h, w)
+        k = self.convs[mod.cv1.conv]
+        y = self._buf(n, c, h, w)
+        # cv1: both halves into the concat buffer, second half also dense for the first Bottleneck
+        self._epi(k.raw(x), k.b, out1=cat, off1=0, out2=y, off2=0, c2b=c, c2n=c)
+        for i, bt in enumerate(mod.m):
+            a = self._cba(bt.cv1, y)
+            k2 = self.convs[bt.cv2.conv]
+            r = k2.raw(a)
+            res = y if bt.add else None
+            if i == nb - 1:
+                self._epi(r, k2.b, res=res, out1=cat, off1=(2 + i) * c)
+            else:
+                y = self._epi(r, k2.b, res=res, out1=r, out2=cat, off2=(2 + i) * c, c2b=0, c2n=c)
+        return self._cba(mod.cv2, cat)
+
+    def _sppf(self, mod: SPPF, x):
+        y = [self._cba(mod.cv1, x)]
+        for _ in range(3):
+            y.append(mod.m(y[-1]))
+        return self._cba(mod.cv2, self._cat(y, [0, 0, 0, 0]))
+
+    def _cat(self, srcs, shifts):
+        n = srcs[0].shape[0]
+        h, w = srcs[0].shape[2] << shifts[0], srcs[0].shape[3] << shifts[0]
+        out = self._buf(n, sum(t.shape[1] for t in srcs), h, w)
+        k = len(srcs)
+        ptrs = (C.c_void_p * 4)(*([t.data_ptr() for t in srcs] + [0] * (4 - k)))
+        chans = (C.c_int32 * 4)(*([t.shape[1] for t in srcs] + [0] * (4 - k)))
+        shs = (C.c_int32 * 4)(*(list(shifts) + [0] * (4 - k)))
+        _ffi.check(self._lib.hvb_concat_nhwc(self._h, ptrs, chans, shs, k, n, h, w, C.c_void_p(out.data_ptr())))
+        return out
+
+    def _detect(self, feats):
+        det, outs = self.m.detect, []
+        for i, x in enumerate(feats):
+            n, _, h, w = x.shape
+            head = self._buf(n, 64 + self.nc, h, w)
+            for branch, off in ((det.cv2[i], 0), (det.cv3[i], 64)):
+                t = self._cba(branch[1], self._cba(branch[0], x))
+                k = self.convs[branch[2]]
+                self._epi(k.raw(t), k.b, act=_NONE, out1=head, off1=off)
+            outs.append(head)
+        return outs
+
+    # ------------------------------------------------------------------ forward
+    @torch.no_grad()
+    def __call__(self, x: torch.Tensor) -> List[torch.Tensor]:
+        """x: float32 [B,3,H,W] NCHW-contiguous (K1's output), H and W multiples of 32."""
+        m, ctx = self.m, self.ctx
+        with ctx.lock:
+            ctx._enter()
+            if self.use_stem and x.is_contiguous():
+                n, _, h, w = x.shape
+                y = self._buf(n, self.stem_w.shape[0], (h - 1) // 2 + 1, (w - 1) // 2 + 1)
+                _ffi.check(self._lib.hvb_stem_conv(self._h, C.c_void_p(x.data_ptr()), C.c_void_p(self.stem_w.ctypes.data),
+                                                   C.c_void_p(self.stem_b.ctypes.data), n, h, w, self.stem_w.shape[0],
+                                                   C.c_void_p(y.data_ptr())))
+            else:
+                y = self._cba(m.b0, x.contiguous(memory_format=CL))
+            y = self._c2f(m.b2, self._cba(m.b1, y))
+            p3 = self._c2f(m.b4, self._cba(m.b3, y))
+            p4 = self._c2f(m.b6, self._cba(m.b5, p3))
+            p5 = self._sppf(m.b9, self._c2f(m.b8, self._cba(m.b7, p4)))
+            h12 = self._c2f(m.h12, self._cat([p5, p4], [1, 0]))
+            h15 = self._c2f(m.h15, self._cat([h12, p3], [1, 0]))
+            h18 = self._c2f(m.h18, self._cat([self._cba(m.h16, h15), h12], [0, 0]))
+            h21 = self._c2f(m.h21, self._cat([self._cba(m.h19, h18), p5], [0, 0]))
+            return self._detect([h15, h18, h21])

@@ -45,3 +45,21 @@ def calibrate_bn(trunk: nn.Module, seed: int = 0, batches: int = 4, batch: int =
     trunk.eval()
     for m, mom in saved.items():
         m.momentum = mom
+
+
+def fold_bn(trunk: nn.Module) -> nn.Module:
+    """Fold every eval-mode BatchNorm2d that directly follows a Conv2d inside an nn.Sequential into that
+    convolution, in place (torchvision's Conv2dNormActivation blocks).  Same function up to fp32
+    rounding (~1e-7 relative), 34 fewer passes over the activations per forward."""
+    from torch.nn.utils.fusion import fuse_conv_bn_eval
+    for mod in list(trunk.modules()):
+        if isinstance(mod, nn.Sequential):
+            names = list(mod._modules.keys())
+            for a, b in zip(names, names[1:]):
+                conv, bn = mod._modules[a], mod._modules[b]
+                if isinstance(conv, nn.Conv2d) and isinstance(bn, nn.BatchNorm2d):
+                    mod._modules[a] = fuse_conv_bn_eval(conv.eval(), bn.eval())
+                    mod._modules[b] = nn.Identity()
+    for p in trunk.parameters():
+        p.requires_grad_(False)
+    return trunk

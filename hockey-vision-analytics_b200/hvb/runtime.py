@@ -271,6 +271,73 @@ class Context:
                                         n_problems, max_na, max_nb, flags, ptr(out)))
         return out
 
+    # ------------------------------------------------------------------ K5 (backbone glue; NHWC float32)
+    ACT = {"none": 0, "silu": 1, "relu": 2, "hardswish": 3}
+
+    @staticmethod
+    def _nhwc(t: torch.Tensor) -> Tuple[int, int]:
+        """(pixels, channels) of a [N,C,H,W] tensor stored channels-last (dense NHWC)."""
+        if t.dtype != torch.float32 or t.dim() != 4 or not t.is_contiguous(memory_format=torch.channels_last):
+            raise ValueError("expected a float32 channels_last [N,C,H,W] tensor, got %s %s" % (t.dtype, tuple(t.stride())))
+        return t.shape[0] * t.shape[2] * t.shape[3], t.shape[1]
+
+    def bias_act(self, x: torch.Tensor, bias: Optional[torch.Tensor], act: str = "silu", residual: Optional[torch.Tensor] = None,
+                 out1: Optional[torch.Tensor] = None, out1_off: int = 0, out2: Optional[torch.Tensor] = None,
+                 out2_off: int = 0, c2_begin: int = 0, c2_count: Optional[int] = None, write_out1: bool = True) -> torch.Tensor:
+        """y = act(x + bias) (+ residual) in one pass; y -> out1[:, out1_off:out1_off+C] (default: in place on x)
+        and, for channels [c2_begin, c2_begin+c2_count), -> out2[:, out2_off:...].  Returns out1 (or out2)."""
+        npix, c = self._nhwc(x)
+        if out1 is None and write_out1:
+            out1 = x
+        for t in (residual, out1, out2):
+            if t is not None and self._nhwc(t)[0] != npix:
+                raise ValueError("pixel count mismatch")
+        if residual is not None and residual.shape[1] != c:
+            raise ValueError("residual channel mismatch")
+        c2 = (c if c2_count is None else c2_count) if out2 is not None else 0
+        with self.lock:
+            self._enter()
+            check(self.lib.hvb_bias_act(self.handle, ptr(x), ptr(bias), ptr(residual), npix, c, self.ACT[act],
+                                        ptr(out1), out1.shape[1] if out1 is not None else 0, out1_off,
+                                        ptr(out2), out2.shape[1] if out2 is not None else 0, out2_off, c2_begin, c2))
+        return out1 if out1 is not None else out2
+
+    def concat_nhwc(self, sources: Sequence[torch.Tensor], shifts: Optional[Sequence[int]] = None,
+                    out: Optional[torch.Tensor] = None) -> torch.Tensor:
+        """Channel concat of up to 4 channels-last tensors; source i is nearest-upsampled by 2**shifts[i]."""
+        shifts = list(shifts) if shifts is not None else [0] * len(sources)
+        n = sources[0].shape[0]
+        h, w = sources[0].shape[2] << shifts[0], sources[0].shape[3] << shifts[0]
+        for t, s in zip(sources, shifts):
+            self._nhwc(t)
+            if (t.shape[0], t.shape[2] << s, t.shape[3] << s) != (n, h, w):
+                raise ValueError("concat sources disagree on the output size")
+        ctot = sum(t.shape[1] for t in sources)
+        with self.lock:
+            self._enter()
+            if out is None:
+                out = torch.empty((n, ctot, h, w), dtype=torch.float32, device=self.device, memory_format=torch.channels_last)
+            k = len(sources)
+            srcs = (C.c_void_p * 4)(*([t.data_ptr() for t in sources] + [0] * (4 - k)))
+            chans = (C.c_int32 * 4)(*([t.shape[1] for t in sources] + [0] * (4 - k)))
+            shs = (C.c_int32 * 4)(*(shifts + [0] * (4 - k)))
+            check(self.lib.hvb_concat_nhwc(self.handle, srcs, chans, shs, k, n, h, w, ptr(out)))
+        return out
+
+    def stem_conv(self, x_nchw: torch.Tensor, weight_host: np.ndarray, bias_host: Optional[np.ndarray]) -> torch.Tensor:
+        """Layer 0 (3->C, 3x3, stride 2, pad 1) + bias + SiLU: NCHW float32 in, channels-last out."""
+        n, ci, h, w = x_nchw.shape
+        if ci != 3 or x_nchw.dtype != torch.float32 or not x_nchw.is_contiguous():
+            raise ValueError("stem_conv expects a dense float32 [N,3,H,W] tensor")
+        co = int(weight_host.shape[0])
+        assert weight_host.dtype == np.float32 and weight_host.shape == (co, 3, 3, 3) and weight_host.flags.c_contiguous
+        with self.lock:
+            self._enter()
+            out = torch.empty((n, co, (h - 1) // 2 + 1, (w - 1) // 2 + 1), dtype=torch.float32, device=self.device,
+                              memory_format=torch.channels_last)
+            check(self.lib.hvb_stem_conv(self.handle, ptr(x_nchw), ptr(weight_host), ptr(bias_host), n, h, w, co, ptr(out)))
+        return out
+
     # ------------------------------------------------------------------ host-buffer entry points
     def color_features_host(self, pixels: np.ndarray, crops: np.ndarray, roi_mode: int = _ffi.ROI_HYBRID, want_raw: bool = False):
         n = len(crops)

@@ -271,6 +271,30 @@ HVB_API int hvb_iou_cost(hvb_ctx* ctx, const double* a_dev, const double* b_dev,
                  const int32_t* a_off_dev, const int32_t* b_off_dev, const int64_t* out_off_dev,
                  int n_problems, int max_na, int max_nb, int flags, double* out_dev);
 
+/* ---------------------------------------------------------------- K5: backbone glue
+ * The element-wise work BETWEEN the library convolutions of the YOLOv8 forward the reference runs at
+ * hockey/main.py:179-184 (ultralytics nn/modules: Conv.forward_fuse = act(conv(x)+b), Bottleneck's
+ * x + cv2(cv1(x)), the torch.cat of C2f / SPPF / Detect, nn.Upsample + Concat of the neck) and of the
+ * MobileNetV3 forward at common/team_hybrid.py:73-81.  Tensors are float32 NHWC ("channels_last").
+ *
+ * hvb_bias_act:  y[p,c] = act(x[p,c] + bias[c]) (+ residual[p,c]);  act: 0 none, 1 SiLU, 2 ReLU, 3 hardswish.
+ *   x_dev is the dense [npix, channels] raw convolution output; y goes to out1 (all channels, row pitch
+ *   out1_ld floats, starting at channel out1_off of each row; may alias x_dev) and/or to out2 (only
+ *   channels [c2_begin, c2_begin+c2_count), written at out2_off of rows of pitch out2_ld) — i.e. the
+ *   contiguous tensor the next convolution reads and the slice of a concat buffer, in one pass.
+ * hvb_concat_nhwc: out[n,y,x,:] = cat_s src_s[n, y >> shift_s, x >> shift_s, :]  (nearest 2^shift upsample).
+ * hvb_stem_conv: layer 0 (3 -> c_out, 3x3, stride 2, pad 1) + bias + SiLU, reading K1's NCHW output and
+ *   writing NHWC; exact fp32.  weight_host: float32[c_out,3,3,3] (PyTorch layout), bias_host: [c_out] or NULL;
+ *   both are host pointers (they travel as kernel parameters).  c_out in {16,32,48,64}.
+ */
+HVB_API int hvb_bias_act(hvb_ctx* ctx, const float* x_dev, const float* bias_dev, const float* residual_dev,
+                 int64_t npix, int channels, int act, float* out1_dev, int64_t out1_ld, int64_t out1_off,
+                 float* out2_dev, int64_t out2_ld, int64_t out2_off, int c2_begin, int c2_count);
+HVB_API int hvb_concat_nhwc(hvb_ctx* ctx, const float* const src_dev[4], const int32_t src_channels[4],
+                    const int32_t src_shift[4], int n_src, int n, int h, int w, float* out_dev);
+HVB_API int hvb_stem_conv(hvb_ctx* ctx, const float* in_nchw_dev, const float* weight_host, const float* bias_host,
+                  int n, int h, int w, int c_out, float* out_nhwc_dev);
+
 /* ---------------------------------------------------------------- host-buffer entry points
  * What a non-Python binding (cgo / JNI / N-API) would call: host in, host out, synchronous.
  * They stage through context-owned pinned + device scratch and run the same kernels. */

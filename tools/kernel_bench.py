@@ -131,6 +131,33 @@ def main():
     oo = torch.from_numpy((np.arange(P) * T * D).astype(np.int64)).cuda()
     report("K4b IoU cost 8 clips x 40x40", timed(lambda: ctx.iou_cost(a, b, None, ao, bo, oo, P, T, D, P * T * D, 2), R), P * (T + D) * 32 + P * T * D * 8)
 
+    # K5 backbone glue at the YOLOv8m / 1080p (736x1280 input) layer sizes, 32 frames per launch
+    CL = torch.channels_last
+    nb = 32
+    for tag, c, h, w in (("layer0 out 48ch 368x640", 48, 368, 640), ("layer1 out 96ch 184x320", 96, 184, 320),
+                         ("bottleneck 48ch 184x320", 48, 184, 320), ("p3 192ch 92x160", 192, 92, 160)):
+        x = torch.randn(nb, c, h, w, device="cuda").contiguous(memory_format=CL)
+        b = torch.randn(c, device="cuda")
+        r = torch.randn(nb, c, h, w, device="cuda").contiguous(memory_format=CL)
+        nbytes = x.numel() * 4
+        report("K5 bias+SiLU in place x%d %s" % (nb, tag), timed(lambda: ctx.bias_act(x, b, "silu"), R), 2 * nbytes)
+        report("K5 bias+SiLU+residual x%d %s" % (nb, tag), timed(lambda: ctx.bias_act(x, b, "silu", residual=r), R), 3 * nbytes)
+        cat = torch.empty(nb, 2 * c, h, w, device="cuda").contiguous(memory_format=CL)
+        report("K5 bias+SiLU -> dense + concat slice x%d %s" % (nb, tag),
+               timed(lambda: ctx.bias_act(x, b, "silu", out1=x, out2=cat, out2_off=c, c2_begin=0, c2_count=c), R), 3 * nbytes)
+        del x, r, cat
+    p5 = torch.randn(nb, 576, 23, 40, device="cuda").contiguous(memory_format=CL)
+    p4 = torch.randn(nb, 384, 46, 80, device="cuda").contiguous(memory_format=CL)
+    out = ctx.concat_nhwc([p5, p4], [1, 0])
+    report("K5 upsample2x+concat x%d (576@23x40, 384@46x80)" % nb, timed(lambda: ctx.concat_nhwc([p5, p4], [1, 0], out=out), R),
+           p5.numel() * 4 + p4.numel() * 4 + out.numel() * 4)
+    xin = torch.rand(nb, 3, 736, 1280, device="cuda")
+    wst = (np.random.default_rng(0).standard_normal((48, 3, 3, 3)) * 0.2).astype(np.float32)
+    bst = np.zeros((48,), np.float32)
+    ms = timed(lambda: ctx.stem_conv(xin, wst, bst), R)
+    report("K5 stem conv 3->48 s2 + SiLU x%d 736x1280" % nb, ms, xin.numel() * 4 + nb * 48 * 368 * 640 * 4,
+           flops=2 * 27 * 48 * nb * 368 * 640)
+
 
 if __name__ == "__main__":
     main()
