@@ -9,8 +9,14 @@
 // true float32 /255 and Normalize a true (x-mean)/std (IEEE division); the BGR crop goes through
 // the RGB statistics unswapped, like the reference.
 //
-// One CTA per crop (persistent loop).  Coefficients and the uint8 intermediate live in shared
-// memory; tall ROIs are processed in output-row blocks so that the intermediate window always fits.
+// One CTA per crop.  Coefficients and the uint8 intermediate live in shared memory; tall ROIs are
+// processed in output-row blocks so that the intermediate window always fits.  Two instantiations of
+// the same kernel body share the work: the FAST one (<= 8 taps per sample, i.e. ROI up to 192 x 384 px —
+// every player crop of a 1080p/4K rink frame — 128 intermediate rows, ~35 KB shared memory; four CTAs
+// are resident per SM, so the per-crop chain load -> sync -> filter -> sync -> store of one CTA hides
+// behind the others) and the GENERAL one (<= 48 taps, 87 KB) which only touches the crops the fast
+// one skipped.  ToTensor + Normalize are a 3 x 256-entry table built once per CTA with the exact
+// float32 divisions, so the store loop does one shared-memory lookup per value.
 #include "hvb_common.cuh"
 #include "hvb_roi.cuh"
 
@@ -18,18 +24,21 @@ namespace {
 
 constexpr int kThreads = 256;
 constexpr int kOutW = 64, kOutH = 128;
-constexpr int kKMax = 48;               // max taps per output sample (ROI up to ~1400 x 2900 px)
-constexpr int kInterRows = 256;         // rows of the uint8 intermediate held in shared memory
 constexpr int kPrecision = 22;
 
-struct Smem {
+// KMAX: max taps per output sample; ROWS: rows of the uint8 intermediate held in shared memory
+template <int KMAX, int ROWS>
+struct SmemT {
     int bh[kOutW][2];                   // horizontal bounds: xmin, n
     int bv[kOutH][2];
-    int kh[kOutW * kKMax];
-    int kv[kOutH * kKMax];
-    uint8_t inter[kInterRows * kOutW * 3];
+    int kh[kOutW * KMAX];
+    int kv[kOutH * KMAX];
+    float lut[3][256];                  // ((v / 255) - mean[c]) / std[c], exact float32 divisions
+    uint8_t inter[ROWS * kOutW * 3];
     int blk[4];
 };
+constexpr int kFastK = 8, kFastRows = 128;        // ROI up to 192 x 384 px (scale <= 3 per axis)
+constexpr int kGenK = 48, kGenRows = 256;         // ROI up to ~1400 x 2900 px
 
 // Pillow precompute_coeffs + normalize_coeffs_8bpc for output sample `o` (bilinear, support 1).
 __device__ void pil_coeffs(int in_size, int out_size, int o, int ksize, int* bounds, int* kk) {
@@ -73,27 +82,27 @@ __device__ __forceinline__ int clip8(int v) {
     return min(max(v, 0), 255);
 }
 
-__device__ __forceinline__ void write_out(float* __restrict__ out, uint8_t* __restrict__ out_u8, int y, int x, int v0, int v1, int v2) {
-    const float mean[3] = {0.485f, 0.456f, 0.406f};
-    const float stdv[3] = {0.229f, 0.224f, 0.225f};
+__device__ __forceinline__ void write_out(const float (*lut)[256], float* __restrict__ out, uint8_t* __restrict__ out_u8, int y, int x, int v0, int v1, int v2) {
     const int v[3] = {v0, v1, v2};
 #pragma unroll
-    for (int c = 0; c < 3; c++) {
-        float t = __fdiv_rn((float)v[c], 255.0f);
-        out[(c * kOutH + y) * kOutW + x] = __fdiv_rn(__fsub_rn(t, mean[c]), stdv[c]);
-    }
+    for (int c = 0; c < 3; c++) out[(c * kOutH + y) * kOutW + x] = lut[c][v[c]];
     if (out_u8) {
         uint8_t* o = out_u8 + (y * kOutW + x) * 3;
         o[0] = (uint8_t)v0; o[1] = (uint8_t)v1; o[2] = (uint8_t)v2;
     }
 }
 
+// FAST = true: handles the crops that fit the small tables and skips the rest; FAST = false: the complement.
+template <int KMAX, int ROWS, bool FAST>
 __global__ void __launch_bounds__(kThreads)
 mnv3_prep_kernel(const uint8_t* __restrict__ pixels, const hvb_crop_desc* __restrict__ crops, int n, int roi_mode,
                  float* __restrict__ out, uint8_t* __restrict__ out_u8, uint8_t* __restrict__ out_valid) {
     extern __shared__ __align__(16) uint8_t smem_raw[];
+    typedef SmemT<KMAX, ROWS> Smem;
     Smem& S = *reinterpret_cast<Smem*>(smem_raw);
+    constexpr int kKMax = KMAX, kInterRows = ROWS;
 
+    bool lut_ready = false;
     for (int ci = blockIdx.x; ci < n; ci += gridDim.x) {
         const hvb_crop_desc cd = crops[ci];
         const hvb_rect rc = hvb_roi_rect(cd.h, cd.w, roi_mode);
@@ -102,6 +111,18 @@ mnv3_prep_kernel(const uint8_t* __restrict__ pixels, const hvb_crop_desc* __rest
         uint8_t* o8 = out_u8 ? out_u8 + (int64_t)ci * kOutH * kOutW * 3 : nullptr;
         const int ksh = (rw > 0) ? pil_ksize(rw, kOutW) : 1, ksv = (rh > 0) ? pil_ksize(rh, kOutH) : 1;
         const bool vfirst = rh > 100 * rw;
+        // the fast instantiation owns: empty ROIs, and ROIs within its tap budget that resize horizontally first
+        const bool fast_case = rw <= 0 || rh <= 0 || (ksh <= kFastK && ksv <= kFastK && !vfirst);
+        if (fast_case != FAST) continue;
+        if (!lut_ready) {
+            const float mean[3] = {0.485f, 0.456f, 0.406f};
+            const float stdv[3] = {0.229f, 0.224f, 0.225f};
+            for (int i = threadIdx.x; i < 3 * 256; i += kThreads) {
+                const int c = i >> 8, v = i & 255;
+                S.lut[c][v] = __fdiv_rn(__fsub_rn(__fdiv_rn((float)v, 255.0f), mean[c]), stdv[c]);   // ToTensor, Normalize
+            }
+            lut_ready = true;                       // visible after the __syncthreads below
+        }
         const bool ok = rw > 0 && rh > 0 && ksh <= kKMax && ksv <= kKMax && (!vfirst || rw * kOutH * 3 <= (int)sizeof(S.inter));
         if (!ok) {
             // empty ROI: the reference's `except:` path (zero feature row); too-large ROI: flagged 0xFF
@@ -156,7 +177,7 @@ mnv3_prep_kernel(const uint8_t* __restrict__ pixels, const hvb_crop_desc* __rest
                         const int kk = k[t];
                         s0 += src[t * kOutW * 3] * kk; s1 += src[t * kOutW * 3 + 1] * kk; s2 += src[t * kOutW * 3 + 2] * kk;
                     }
-                    write_out(o, o8, y, x, clip8(s0), clip8(s1), clip8(s2));
+                    write_out(S.lut, o, o8, y, x, clip8(s0), clip8(s1), clip8(s2));
                 }
                 __syncthreads();
                 y0 = y1;
@@ -188,7 +209,7 @@ mnv3_prep_kernel(const uint8_t* __restrict__ pixels, const hvb_crop_desc* __rest
                     const int kk = k[x];
                     s0 += src[3 * x] * kk; s1 += src[3 * x + 1] * kk; s2 += src[3 * x + 2] * kk;
                 }
-                write_out(o, o8, y, xx, clip8(s0), clip8(s1), clip8(s2));
+                write_out(S.lut, o, o8, y, xx, clip8(s0), clip8(s1), clip8(s2));
             }
             __syncthreads();
         }
@@ -206,11 +227,19 @@ int hvb_mnv3_preprocess(hvb_ctx* ctx, const uint8_t* pixels_dev, const hvb_crop_
     HVB_ARG(roi_mode >= 0 && roi_mode <= 2, "bad roi_mode");
     if (n == 0) return HVB_OK;
     HVB_ARG(pixels_dev && crops_dev && out_dev, "null pointer");
-    static_assert(sizeof(Smem) < 200 * 1024, "smem budget");
-    HVB_CUDA(cudaFuncSetAttribute(mnv3_prep_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(Smem)));
-    const int grid = n < ctx->sm_count * 2 ? n : ctx->sm_count * 2;
-    mnv3_prep_kernel<<<grid, kThreads, sizeof(Smem), ctx->stream>>>(pixels_dev, crops_dev, n, roi_mode, out_dev, out_u8_dev,
-                                                                     out_valid_dev);
+    typedef SmemT<kFastK, kFastRows> SmemFast;
+    typedef SmemT<kGenK, kGenRows> SmemGen;
+    static_assert(sizeof(SmemFast) <= 37 * 1024 && sizeof(SmemGen) < 200 * 1024, "smem budget");
+    auto fast = mnv3_prep_kernel<kFastK, kFastRows, true>;
+    auto gen = mnv3_prep_kernel<kGenK, kGenRows, false>;
+    HVB_CUDA(cudaFuncSetAttribute(gen, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(SmemGen)));
+    // fast pass: one CTA per crop up to the four CTAs (64 registers x 256 threads) resident per SM
+    const int gfast = n < ctx->sm_count * 4 ? n : ctx->sm_count * 4;
+    fast<<<gfast, kThreads, sizeof(SmemFast), ctx->stream>>>(pixels_dev, crops_dev, n, roi_mode, out_dev, out_u8_dev, out_valid_dev);
+    HVB_LAUNCHED(ctx);
+    // general pass: only the crops the fast pass skipped (usually none: its CTAs read the descriptors and exit)
+    const int ggen = n < ctx->sm_count ? n : ctx->sm_count;
+    gen<<<ggen, kThreads, sizeof(SmemGen), ctx->stream>>>(pixels_dev, crops_dev, n, roi_mode, out_dev, out_u8_dev, out_valid_dev);
     HVB_LAUNCHED(ctx);
     return HVB_OK;
 }

@@ -93,7 +93,7 @@ PROTOTYPES = {
     "hvb_gram_affinity": [_vp, _vp, _i, _i, _d, _i, _vp, _vp],
     "hvb_gram_tc": [_vp, _vp, _i, _i, _vp],
     "hvb_iou_cost": [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _vp],
-    "hvb_bias_act": [_vp, _vp, _vp, _vp, _i64, _i, _i, _vp, _i64, _i64, _vp, _i64, _i64, _i, _i],
+    "hvb_bias_act": [_vp, _vp, _vp, _vp, _i64, _i, _i, _vp, _i64, _i64, _vp, _i64, _i64, _i, _i, _i, _i],
     "hvb_concat_nhwc": [_vp, _vp, _vp, _vp, _i, _i, _i, _i, _vp],
     "hvb_stem_conv": [_vp, _vp, _vp, _vp, _i, _i, _i, _i, _vp],
     "hvb_color_features_host": [_vp, _vp, _sz, _vp, _i, _i, _vp, _vp],

@@ -4,8 +4,10 @@ Eager PyTorch spends ~2/3 of a YOLOv8m forward outside the convolutions: a broad
 SiLU pass per layer, `.contiguous()` copies of `chunk` views, `torch.cat`, `nn.Upsample`.  Here each
 convolution is called without bias and followed by ONE `hvb_bias_act` pass that adds the bias, applies
 SiLU, adds the Bottleneck residual and writes the result both where the next convolution reads it and
-into its slice of the C2f / SPPF / Detect concat buffer; the neck's Upsample+Concat is one
-`hvb_concat_nhwc` pass; layer 0 reads K1's NCHW output directly (`hvb_stem_conv`).
+into its slice of the C2f / Detect concat buffer; the neck's Upsample + Concat never run as passes of
+their own either (the producing epilogue writes the 2x2-replicated pixels straight into the concat
+buffer); SPPF's four-way concat is one `hvb_concat_nhwc` pass; layer 0 reads K1's NCHW output directly
+(`hvb_stem_conv`).
 
 The layer graph is ultralytics 8.3.148 `yolov8.yaml` (the model the reference loads at
 hockey/main.py:77 and runs at :179-184), same as hvb.models.yolov8.YOLOv8 whose (conv+bn folded)
@@ -61,24 +63,28 @@ class FusedYOLOv8:
         self._lib, self._h = ctx.lib, ctx.handle
 
     # ------------------------------------------------------------------ primitives (ctx lock is held by forward)
-    def _epi(self, x, bias, act=_SILU, res=None, out1=None, off1=0, out2=None, off2=0, c2b=0, c2n=0, inplace=True):
+    # A "dest" says where the LAST epilogue of a block writes: dict(out1=, off1=, out2=, off2=, up2=).  out1 None = in
+    # place (dense, for a following convolution); a concat-buffer slice as out1/out2 makes torch.cat / Upsample free.
+    def _epi(self, x, bias, act=_SILU, res=None, out1=None, off1=0, out2=None, off2=0, c2b=0, c2n=None, up2=False):
         npix, c = x.shape[0] * x.shape[2] * x.shape[3], x.shape[1]
-        if out1 is None and inplace:
+        if out1 is None:
             out1 = x
+        if c2n is None:
+            c2n = c
         p = lambda t: C.c_void_p(t.data_ptr()) if t is not None else C.c_void_p(0)
-        _ffi.check(self._lib.hvb_bias_act(self._h, p(x), p(bias), p(res), npix, c, act,
-                                          p(out1), out1.shape[1] if out1 is not None else 0, off1,
-                                          p(out2), out2.shape[1] if out2 is not None else 0, off2, c2b, c2n))
-        return out1 if out1 is not None else out2
+        uh, uw = (x.shape[2], x.shape[3]) if (up2 and out2 is not None) else (0, 0)
+        _ffi.check(self._lib.hvb_bias_act(self._h, p(x), p(bias), p(res), npix, c, act, p(out1), out1.shape[1], off1,
+                                          p(out2), out2.shape[1] if out2 is not None else 0, off2, c2b, c2n, uh, uw))
+        return out1
 
     def _buf(self, n, c, h, w):
         return torch.empty((n, c, h, w), dtype=torch.float32, device=self.ctx.device, memory_format=CL)
 
-    def _cba(self, mod: ConvBnAct, x):
+    def _cba(self, mod: ConvBnAct, x, dest=None):
         k = self.convs[mod.conv]
-        return self._epi(k.raw(x), k.b)
+        return self._epi(k.raw(x), k.b, **(dest or {}))
 
-    def _c2f(self, mod: C2f, x):
+    def _c2f(self, mod: C2f, x, dest=None):
         c, nb = mod.c, len(mod.m)
         n, _, h, w = x.shape
         cat = self._buf(n, (2 + nb) * c, h, w)
@@ -95,13 +101,13 @@ class FusedYOLOv8:
                 self._epi(r, k2.b, res=res, out1=cat, off1=(2 + i) * c)
             else:
                 y = self._epi(r, k2.b, res=res, out1=r, out2=cat, off2=(2 + i) * c, c2b=0, c2n=c)
-        return self._cba(mod.cv2, cat)
+        return self._cba(mod.cv2, cat, dest)
 
-    def _sppf(self, mod: SPPF, x):
+    def _sppf(self, mod: SPPF, x, dest=None):
         y = [self._cba(mod.cv1, x)]
         for _ in range(3):
             y.append(mod.m(y[-1]))
-        return self._cba(mod.cv2, self._cat(y, [0, 0, 0, 0]))
+        return self._cba(mod.cv2, self._cat(y, [0, 0, 0, 0]), dest)
 
     def _cat(self, srcs, shifts):
         n = srcs[0].shape[0]
@@ -131,22 +137,34 @@ class FusedYOLOv8:
     def __call__(self, x: torch.Tensor) -> List[torch.Tensor]:
         """x: float32 [B,3,H,W] NCHW-contiguous (K1's output), H and W multiples of 32."""
         m, ctx = self.m, self.ctx
+        n, _, h, w = x.shape
+        if h % 32 or w % 32:
+            raise ValueError("input height/width must be multiples of 32, got %dx%d" % (h, w))
+        cout = lambda mod: mod.cv2.conv.out_channels
+        c3, c4, c5, c12 = cout(m.b4), cout(m.b6), cout(m.b9), cout(m.h12)
+        c16, c19 = m.h16.conv.out_channels, m.h19.conv.out_channels
         with ctx.lock:
             ctx._enter()
+            # the four neck Concat inputs exist only as these buffers: producers write their slices directly
+            cat12 = self._buf(n, c5 + c4, h // 16, w // 16)          # [Upsample(p5), p4]
+            cat15 = self._buf(n, c12 + c3, h // 8, w // 8)           # [Upsample(h12), p3]
+            cat18 = self._buf(n, c16 + c12, h // 16, w // 16)        # [h16(h15), h12]
+            cat21 = self._buf(n, c19 + c5, h // 32, w // 32)         # [h19(h18), p5]
             if self.use_stem and x.is_contiguous():
-                n, _, h, w = x.shape
-                y = self._buf(n, self.stem_w.shape[0], (h - 1) // 2 + 1, (w - 1) // 2 + 1)
+                y = self._buf(n, self.stem_w.shape[0], h // 2, w // 2)
                 _ffi.check(self._lib.hvb_stem_conv(self._h, C.c_void_p(x.data_ptr()), C.c_void_p(self.stem_w.ctypes.data),
                                                    C.c_void_p(self.stem_b.ctypes.data), n, h, w, self.stem_w.shape[0],
                                                    C.c_void_p(y.data_ptr())))
             else:
                 y = self._cba(m.b0, x.contiguous(memory_format=CL))
             y = self._c2f(m.b2, self._cba(m.b1, y))
-            p3 = self._c2f(m.b4, self._cba(m.b3, y))
-            p4 = self._c2f(m.b6, self._cba(m.b5, p3))
-            p5 = self._sppf(m.b9, self._c2f(m.b8, self._cba(m.b7, p4)))
-            h12 = self._c2f(m.h12, self._cat([p5, p4], [1, 0]))
-            h15 = self._c2f(m.h15, self._cat([h12, p3], [1, 0]))
-            h18 = self._c2f(m.h18, self._cat([self._cba(m.h16, h15), h12], [0, 0]))
-            h21 = self._c2f(m.h21, self._cat([self._cba(m.h19, h18), p5], [0, 0]))
+            p3 = self._c2f(m.b4, self._cba(m.b3, y), dict(out2=cat15, off2=c12))
+            p4 = self._c2f(m.b6, self._cba(m.b5, p3), dict(out2=cat12, off2=c5))
+            self._sppf(m.b9, self._c2f(m.b8, self._cba(m.b7, p4)), dict(out1=cat21, off1=c19, out2=cat12, off2=0, up2=True))
+            self._c2f(m.h12, cat12, dict(out1=cat18, off1=c16, out2=cat15, off2=0, up2=True))
+            h15 = self._c2f(m.h15, cat15)
+            self._cba(m.h16, h15, dict(out1=cat18, off1=0))
+            h18 = self._c2f(m.h18, cat18)
+            self._cba(m.h19, h18, dict(out1=cat21, off1=0))
+            h21 = self._c2f(m.h21, cat21)
             return self._detect([h15, h18, h21])

@@ -98,13 +98,17 @@ class HotPath:
 
     def process_stream(self, chunks):
         """Pipelined host API: `chunks` yields (frames uint8[n,H,W,3] pinned torch tensor or numpy, team_boxes
-        float32[M,4], team_frame_idx int32[M]) per step; results are yielded in order.  The H2D copy of chunk
-        i+1 runs on a side stream while chunk i computes (two device frame buffers, guarded by events), so a
-        step's copy is hidden behind the previous step's kernels instead of serialising with them."""
+        float32[M,4], team_frame_idx int32[M]) per step; results are yielded in order, one step behind.
+
+        Three things overlap: the H2D copy of chunk i (side stream, two device frame buffers guarded by
+        events), the kernels of chunk i-1 (main stream), and the host reading chunk i-1's results (asynchronous
+        D2H into pinned buffers + an event).  The host only ever blocks on the *previous* chunk, so the GPU
+        always has the next chunk's work queued behind the current one."""
         dev = self.ctx.device
         copy_stream = torch.cuda.Stream(device=dev)
         main = torch.cuda.current_stream(dev)
         bufs, free_ev = [None, None], [None, None]
+        pinned_out = [dict(), dict(), dict()]
 
         def stage(i, item):
             frames, tb, ti = item
@@ -122,7 +126,7 @@ class HotPath:
                 ready.record(copy_stream)
             return slot, tbd, tid, ready, src
 
-        def finish(staged):
+        def launch(i, staged):
             slot, tbd, tid, ready, _keep = staged
             main.wait_event(ready)
             tbd.record_stream(main); tid.record_stream(main)
@@ -130,19 +134,33 @@ class HotPath:
             ev = torch.cuda.Event()
             ev.record(main)
             free_ev[slot] = ev
-            cnt = out["count"].cpu().numpy()
-            res = dict(count=cnt, xyxy=out["xyxy"].cpu().numpy(), conf=out["conf"].cpu().numpy(), cls=out["cls"].cpu().numpy())
-            res["team"] = self.rule(out["team_tail"].cpu().numpy())
+            host = pinned_out[i % 3]
+            for k in ("count", "xyxy", "conf", "cls", "team_tail"):
+                t = out[k]
+                if k not in host or host[k].shape != t.shape or host[k].dtype != t.dtype:
+                    host[k] = torch.empty(t.shape, dtype=t.dtype).pin_memory()
+                host[k].copy_(t, non_blocking=True)
+            done = torch.cuda.Event()
+            done.record(main)
+            return host, done, _keep
+
+        def collect(item):
+            host, done, _keep = item
+            done.synchronize()
+            cnt = host["count"].numpy().copy()
+            if (cnt < 0).any():
+                raise _ffi.HvbError(_ffi.HVB_ERR_CAPACITY, "candidate overflow in the chunked path; lower the chunk's conf pressure")
+            res = dict(count=cnt, xyxy=host["xyxy"].numpy().copy(), conf=host["conf"].numpy().copy(), cls=host["cls"].numpy().copy())
+            res["team"] = self.rule(host["team_tail"].numpy())
             return res
 
-        pending = None
+        inflight = []
         for i, item in enumerate(chunks):
-            staged = stage(i, item)
-            if pending is not None:
-                yield finish(pending)
-            pending = staged
-        if pending is not None:
-            yield finish(pending)
+            inflight.append(launch(i, stage(i, item)))
+            if len(inflight) > 1:
+                yield collect(inflight.pop(0))
+        while inflight:
+            yield collect(inflight.pop(0))
 
 
 class SlicedPuckPath:

@@ -283,15 +283,17 @@ class Context:
 
     def bias_act(self, x: torch.Tensor, bias: Optional[torch.Tensor], act: str = "silu", residual: Optional[torch.Tensor] = None,
                  out1: Optional[torch.Tensor] = None, out1_off: int = 0, out2: Optional[torch.Tensor] = None,
-                 out2_off: int = 0, c2_begin: int = 0, c2_count: Optional[int] = None, write_out1: bool = True) -> torch.Tensor:
+                 out2_off: int = 0, c2_begin: int = 0, c2_count: Optional[int] = None, write_out1: bool = True,
+                 out2_upsample2: bool = False) -> torch.Tensor:
         """y = act(x + bias) (+ residual) in one pass; y -> out1[:, out1_off:out1_off+C] (default: in place on x)
         and, for channels [c2_begin, c2_begin+c2_count), -> out2[:, out2_off:...].  Returns out1 (or out2)."""
         npix, c = self._nhwc(x)
         if out1 is None and write_out1:
             out1 = x
         for t in (residual, out1, out2):
-            if t is not None and self._nhwc(t)[0] != npix:
+            if t is not None and self._nhwc(t)[0] != (4 * npix if (t is out2 and out2_upsample2) else npix):
                 raise ValueError("pixel count mismatch")
+        uh, uw = (x.shape[2], x.shape[3]) if (out2 is not None and out2_upsample2) else (0, 0)
         if residual is not None and residual.shape[1] != c:
             raise ValueError("residual channel mismatch")
         c2 = (c if c2_count is None else c2_count) if out2 is not None else 0
@@ -299,7 +301,7 @@ class Context:
             self._enter()
             check(self.lib.hvb_bias_act(self.handle, ptr(x), ptr(bias), ptr(residual), npix, c, self.ACT[act],
                                         ptr(out1), out1.shape[1] if out1 is not None else 0, out1_off,
-                                        ptr(out2), out2.shape[1] if out2 is not None else 0, out2_off, c2_begin, c2))
+                                        ptr(out2), out2.shape[1] if out2 is not None else 0, out2_off, c2_begin, c2, uh, uw))
         return out1 if out1 is not None else out2
 
     def concat_nhwc(self, sources: Sequence[torch.Tensor], shifts: Optional[Sequence[int]] = None,

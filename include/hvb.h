@@ -282,6 +282,8 @@ HVB_API int hvb_iou_cost(hvb_ctx* ctx, const double* a_dev, const double* b_dev,
  *   out1_ld floats, starting at channel out1_off of each row; may alias x_dev) and/or to out2 (only
  *   channels [c2_begin, c2_begin+c2_count), written at out2_off of rows of pitch out2_ld) — i.e. the
  *   contiguous tensor the next convolution reads and the slice of a concat buffer, in one pass.
+ *   out2_up2_h/w > 0: the rows of x are the pixels of [n, h, w] images and out2 is a [n, 2h, 2w] tensor;
+ *   every pixel is written to its 2x2 nearest-upsampled positions (nn.Upsample(2) + Concat of the neck).
  * hvb_concat_nhwc: out[n,y,x,:] = cat_s src_s[n, y >> shift_s, x >> shift_s, :]  (nearest 2^shift upsample).
  * hvb_stem_conv: layer 0 (3 -> c_out, 3x3, stride 2, pad 1) + bias + SiLU, reading K1's NCHW output and
  *   writing NHWC; exact fp32.  weight_host: float32[c_out,3,3,3] (PyTorch layout), bias_host: [c_out] or NULL;
@@ -289,7 +291,8 @@ HVB_API int hvb_iou_cost(hvb_ctx* ctx, const double* a_dev, const double* b_dev,
  */
 HVB_API int hvb_bias_act(hvb_ctx* ctx, const float* x_dev, const float* bias_dev, const float* residual_dev,
                  int64_t npix, int channels, int act, float* out1_dev, int64_t out1_ld, int64_t out1_off,
-                 float* out2_dev, int64_t out2_ld, int64_t out2_off, int c2_begin, int c2_count);
+                 float* out2_dev, int64_t out2_ld, int64_t out2_off, int c2_begin, int c2_count,
+                 int out2_up2_h, int out2_up2_w);
 HVB_API int hvb_concat_nhwc(hvb_ctx* ctx, const float* const src_dev[4], const int32_t src_channels[4],
                     const int32_t src_shift[4], int n_src, int n, int h, int w, float* out_dev);
 HVB_API int hvb_stem_conv(hvb_ctx* ctx, const float* in_nchw_dev, const float* weight_host, const float* bias_host,

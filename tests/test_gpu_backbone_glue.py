@@ -82,6 +82,25 @@ def test_bias_act_detect_head_layout(ctx):
     assert torch.equal(head.cpu(), ref)                          # a plain fp32 add: bit-exact
 
 
+def test_bias_act_upsampled_destination_is_upsample_plus_concat(ctx):
+    """The neck: Concat([Upsample(2)(p5), p4]) — p5's epilogue writes the 2x2-replicated pixels into the
+    concat buffer and its own dense copy into another concat slice, in the same pass."""
+    g = torch.Generator().manual_seed(2)
+    c5, c4 = 32, 20
+    raw = torch.randn(2, c5, 6, 10, generator=g)
+    b = torch.randn(c5, generator=g)
+    p4 = torch.randn(2, c4, 12, 20, generator=g)
+    p5 = F.silu(raw + b.view(1, -1, 1, 1))
+    cat12 = torch.zeros((2, c5 + c4, 12, 20)).cuda().contiguous(memory_format=CL)
+    cat12[:, c5:] = p4.cuda()
+    cat21 = torch.full((2, 8 + c5, 6, 10), 3.0).cuda().contiguous(memory_format=CL)
+    ctx.bias_act(nhwc(raw), b.cuda(), "silu", out1=cat21, out1_off=8, out2=cat12, out2_off=0, out2_upsample2=True)
+    ref12 = torch.cat([F.interpolate(p5, scale_factor=2, mode="nearest"), p4], 1)
+    torch.testing.assert_close(cat12.cpu(), ref12, rtol=1e-6, atol=1e-6)
+    torch.testing.assert_close(cat21[:, 8:].cpu(), p5, rtol=1e-6, atol=1e-6)
+    assert (cat21[:, :8] == 3.0).all()
+
+
 def test_bias_act_rejects_bad_slices(ctx):
     from hvb._ffi import HvbError
     x = torch.zeros((1, 8, 4, 4)).cuda().contiguous(memory_format=CL)

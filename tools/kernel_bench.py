@@ -21,6 +21,9 @@ PEAK = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))["hbm_gbs"] if 
 
 
 def timed(fn, reps):
+    if reps <= 0:                       # --profile: exactly one launch of everything (ncu captures), no timing
+        fn(); torch.cuda.synchronize()
+        return 1.0
     fn(); torch.cuda.synchronize()
     a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     a.record()
@@ -45,118 +48,146 @@ def report(name, ms, nbytes=None, flops=None, **kw):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--reps", type=int, default=20)
+    ap.add_argument("--only", default="", help="comma-separated sections: k1,k2,k3,k4,k4b,k5")
+    ap.add_argument("--profile", action="store_true", help="one launch per kernel configuration, no timing (for ncu)")
     args = ap.parse_args()
+    if args.profile:
+        args.reps = 0
+    only = set(args.only.split(",")) if args.only else None
+
+    def want(tag):
+        return only is None or tag in only
     ctx = get_context(0)
     rng = np.random.default_rng(0)
     R = args.reps
 
-    # K1a / K1b
-    for tag, n, h, w, mode, imgsz in (("K1a 1080p->736x1280 x16", 16, 1080, 1920, _ffi.LB_WHOLE, 1280),
-                                      ("K1a 1080p->736x1280 x64", 64, 1080, 1920, _ffi.LB_WHOLE, 1280),
-                                      ("K1a 720p->384x640 x64 (2x area path)", 64, 720, 1280, _ffi.LB_WHOLE, 640),
-                                      ("K1b 4K sliced exact x4", 4, 2160, 3840, _ffi.LB_SLICE_EXACT, 640),
-                                      ("K1b 4K sliced uniform x8", 8, 2160, 3840, _ffi.LB_SLICE_UNIFORM, 640)):
-        frames = torch.from_numpy(rng.integers(0, 256, (n, h, w, 3), dtype=np.uint8)).cuda()
-        plan = ctx.letterbox_plan(n, h, w, mode, imgsz)
-        out = plan.run(frames)
-        report(tag, timed(lambda: plan.run(frames, out), R), plan.read_bytes + plan.write_bytes)
-        del frames, out
+    def sec_k1():
+        # K1a / K1b
+        for tag, n, h, w, mode, imgsz in (("K1a 1080p->736x1280 x16", 16, 1080, 1920, _ffi.LB_WHOLE, 1280),
+                                          ("K1a 1080p->736x1280 x64", 64, 1080, 1920, _ffi.LB_WHOLE, 1280),
+                                          ("K1a 720p->384x640 x64 (2x area path)", 64, 720, 1280, _ffi.LB_WHOLE, 640),
+                                          ("K1b 4K sliced exact x4", 4, 2160, 3840, _ffi.LB_SLICE_EXACT, 640),
+                                          ("K1b 4K sliced uniform x8", 8, 2160, 3840, _ffi.LB_SLICE_UNIFORM, 640)):
+            frames = torch.from_numpy(rng.integers(0, 256, (n, h, w, 3), dtype=np.uint8)).cuda()
+            plan = ctx.letterbox_plan(n, h, w, mode, imgsz)
+            out = plan.run(frames)
+            report(tag, timed(lambda: plan.run(frames, out), R), plan.read_bytes + plan.write_bytes)
+            del frames, out
 
-    # K2a: C2 (1080p, nc=2, 16 images), C4-like (640x640 tiles, nc=1, 160 images)
-    for tag, B, hw, nc, n_gt in (("K2a decode+NMS C2 736x1280 nc=2 x16", 16, (736, 1280), 2, 12),
-                                 ("K2a decode+NMS tiles 640x640 nc=1 x160", 160, (640, 640), 1, 3)):
-        lv = [(hw[0] // s, hw[1] // s) for s in (8, 16, 32)]
-        one = []
-        for _ in range(4):
-            cx, cy = rng.uniform(60, hw[1] - 60, n_gt), rng.uniform(60, hw[0] - 60, n_gt)
-            bw, bh = rng.uniform(20, 100, n_gt), rng.uniform(30, 200, n_gt)
-            gt = np.stack([cx - bw / 2, cy - bh / 2, cx + bw / 2, cy + bh / 2], 1)
-            one.append(planted_head(rng, lv, nc, gt, rng.integers(0, nc, n_gt)))
-        levels = [torch.from_numpy(np.stack([one[i % 4][l] for i in range(B)])).cuda() for l in range(3)]
-        meta = np.zeros((B,), _ffi.IMG_META)
-        meta["gain"], meta["clip_w"], meta["clip_h"], meta["out_slot"] = 1.0, hw[1], hw[0], np.arange(B)
-        meta_d = ctx.struct_to_device(meta)
-        outs = ctx.decode_nms(levels, nc, 0.4, 0.7, 300, False, meta=meta)
-        A = sum(a * b for a, b in lv)
-        report(tag, timed(lambda: ctx.decode_nms(levels, nc, 0.4, 0.7, 300, False, meta=meta_d, out=outs, check_overflow=False), R),
-               B * A * nc * 4, full_head_MB=round(B * A * (64 + nc) * 4 / 1e6, 2), kept=int(outs[3].sum().item()))
-    # K2b: 64 frames x ~120 merged detections
-    n_seg, per = 64, 120
-    boxes = np.concatenate([random_boxes(rng, per, 3840, 2160, 10, 40, np.float64)[0] for _ in range(n_seg)])
-    conf = rng.permutation(np.linspace(0.3, 0.99, n_seg * per)).astype(np.float32)
-    cls = np.zeros(n_seg * per, np.int32)
-    seg = (np.arange(n_seg + 1) * per).astype(np.int32)
-    bd, cd_, kd, sd = [torch.from_numpy(x).cuda() for x in (boxes, conf, cls, seg)]
-    report("K2b merge NMS 64 frames x 120 dets", timed(lambda: ctx.merge_nms(bd, cd_, kd, sd, n_seg, n_seg * per, 0.1), R),
-           n_seg * per * 40)
+    def sec_k2():
+        # K2a: C2 (1080p, nc=2, 16 images), C4-like (640x640 tiles, nc=1, 160 images)
+        for tag, B, hw, nc, n_gt in (("K2a decode+NMS C2 736x1280 nc=2 x16", 16, (736, 1280), 2, 12),
+                                     ("K2a decode+NMS tiles 640x640 nc=1 x160", 160, (640, 640), 1, 3)):
+            lv = [(hw[0] // s, hw[1] // s) for s in (8, 16, 32)]
+            one = []
+            for _ in range(4):
+                cx, cy = rng.uniform(60, hw[1] - 60, n_gt), rng.uniform(60, hw[0] - 60, n_gt)
+                bw, bh = rng.uniform(20, 100, n_gt), rng.uniform(30, 200, n_gt)
+                gt = np.stack([cx - bw / 2, cy - bh / 2, cx + bw / 2, cy + bh / 2], 1)
+                one.append(planted_head(rng, lv, nc, gt, rng.integers(0, nc, n_gt)))
+            levels = [torch.from_numpy(np.stack([one[i % 4][l] for i in range(B)])).cuda() for l in range(3)]
+            meta = np.zeros((B,), _ffi.IMG_META)
+            meta["gain"], meta["clip_w"], meta["clip_h"], meta["out_slot"] = 1.0, hw[1], hw[0], np.arange(B)
+            meta_d = ctx.struct_to_device(meta)
+            outs = ctx.decode_nms(levels, nc, 0.4, 0.7, 300, False, meta=meta)
+            A = sum(a * b for a, b in lv)
+            report(tag, timed(lambda: ctx.decode_nms(levels, nc, 0.4, 0.7, 300, False, meta=meta_d, out=outs, check_overflow=False), R),
+                   B * A * nc * 4, full_head_MB=round(B * A * (64 + nc) * 4 / 1e6, 2), kept=int(outs[3].sum().item()))
+        # K2b: 64 frames x ~120 merged detections
+        n_seg, per = 64, 120
+        boxes = np.concatenate([random_boxes(rng, per, 3840, 2160, 10, 40, np.float64)[0] for _ in range(n_seg)])
+        conf = rng.permutation(np.linspace(0.3, 0.99, n_seg * per)).astype(np.float32)
+        cls = np.zeros(n_seg * per, np.int32)
+        seg = (np.arange(n_seg + 1) * per).astype(np.int32)
+        bd, cd_, kd, sd = [torch.from_numpy(x).cuda() for x in (boxes, conf, cls, seg)]
+        report("K2b merge NMS 64 frames x 120 dets", timed(lambda: ctx.merge_nms(bd, cd_, kd, sd, n_seg, n_seg * per, 0.1), R),
+               n_seg * per * 40)
 
-    # K3a / K3b: 12 crops per 1080p frame, 64 frames
-    nf = 64
-    frs, bxs, fidx = [], [], []
-    for i in range(nf):
-        f, b, _, _ = rink_frame(rng, 1080, 1920, 12)
-        frs.append(f); bxs.append(b); fidx.append(np.full(len(b), i, np.int32))
-    frames = torch.from_numpy(np.stack(frs)).cuda()
-    bx = torch.from_numpy(np.concatenate(bxs).astype(np.float32)).cuda()
-    fi = torch.from_numpy(np.concatenate(fidx)).cuda()
-    m = bx.shape[0]
-    cd = ctx.crops_from_boxes(bx, fi, 1080, 1920)
-    desc = cd.cpu().numpy().view(_ffi.CROP_DESC)[:m]
-    roi_px = sum((int(h * 0.6) - int(h * 0.1)) * (int(w * 0.8) - int(w * 0.2)) if (h >= 40 and w >= 20) else h * w
-                 for h, w in zip(desc["h"], desc["w"]))
-    feat = ctx.empty((m, 49), torch.float64)
-    report("K3a colour features %d crops" % m, timed(lambda: ctx.color_features(frames, cd, m, out_feat=feat), R),
-           roi_px * 3 + m * 392, roi_kpx_per_crop=round(roi_px / m / 1e3, 2))
-    report("K3b MobileNetV3 prep %d crops" % m, timed(lambda: ctx.mnv3_preprocess(frames, cd, m), R), roi_px * 3 + m * 98304)
-    report("crops_from_boxes %d" % m, timed(lambda: ctx.crops_from_boxes(bx, fi, 1080, 1920), R))
+    def sec_k3():
+        # K3a / K3b: 12 crops per 1080p frame, 64 frames
+        nf = 64
+        frs, bxs, fidx = [], [], []
+        for i in range(nf):
+            f, b, _, _ = rink_frame(rng, 1080, 1920, 12)
+            frs.append(f); bxs.append(b); fidx.append(np.full(len(b), i, np.int32))
+        frames = torch.from_numpy(np.stack(frs)).cuda()
+        bx = torch.from_numpy(np.concatenate(bxs).astype(np.float32)).cuda()
+        fi = torch.from_numpy(np.concatenate(fidx)).cuda()
+        m = bx.shape[0]
+        cd = ctx.crops_from_boxes(bx, fi, 1080, 1920)
+        desc = cd.cpu().numpy().view(_ffi.CROP_DESC)[:m]
+        roi_px = sum((int(h * 0.6) - int(h * 0.1)) * (int(w * 0.8) - int(w * 0.2)) if (h >= 40 and w >= 20) else h * w
+                     for h, w in zip(desc["h"], desc["w"]))
+        feat = ctx.empty((m, 49), torch.float64)
+        report("K3a colour features %d crops" % m, timed(lambda: ctx.color_features(frames, cd, m, out_feat=feat), R),
+               roi_px * 3 + m * 392, roi_kpx_per_crop=round(roi_px / m / 1e3, 2))
+        report("K3b MobileNetV3 prep %d crops" % m, timed(lambda: ctx.mnv3_preprocess(frames, cd, m), R), roi_px * 3 + m * 98304)
+        report("crops_from_boxes %d" % m, timed(lambda: ctx.crops_from_boxes(bx, fi, 1080, 1920), R))
 
-    # K4a: standardise + affinity, tensor-core Gram
-    for n in (250, 2000, 8192):
-        x = torch.from_numpy(rng.normal(0, 1, (n, 625))).cuda()
-        mean, scale, xs = ctx.standardize(x)
-        report("K4a standardize N=%d" % n, timed(lambda: ctx.standardize(x), R), n * 625 * 8 * 3)
-        report("K4a gram tcgen05 N=%d (3xTF32, K'=1920)" % n, timed(lambda: ctx.gram_tc(xs), R), flops=2.0 * n * n * 1920,
-               useful_TFLOP_per_s=None)
-        if n <= 2000:
-            report("K4a affinity mode0 (tcgen05+refine) N=%d" % n, timed(lambda: ctx.gram_affinity(xs, 1.0, 0), max(R // 4, 2)), flops=2.0 * n * n * 625)
-            report("K4a affinity mode1 (fp64) N=%d" % n, timed(lambda: ctx.gram_affinity(xs, 1.0, 1), max(R // 4, 2)), flops=3.0 * n * n * 625)
+    def sec_k4():
+        # K4a: standardise + affinity, tensor-core Gram
+        for n in (250, 2000, 8192):
+            x = torch.from_numpy(rng.normal(0, 1, (n, 625))).cuda()
+            mean, scale, xs = ctx.standardize(x)
+            report("K4a standardize N=%d" % n, timed(lambda: ctx.standardize(x), R), n * 625 * 8 * 3)
+            report("K4a gram tcgen05 N=%d (3xTF32, K'=1920)" % n, timed(lambda: ctx.gram_tc(xs), R), flops=2.0 * n * n * 1920,
+                   useful_TFLOP_per_s=None)
+            if n <= 2000:
+                report("K4a affinity mode0 (tcgen05+refine) N=%d" % n, timed(lambda: ctx.gram_affinity(xs, 1.0, 0), max(R // 4, 2)), flops=2.0 * n * n * 625)
+                report("K4a affinity mode1 (fp64) N=%d" % n, timed(lambda: ctx.gram_affinity(xs, 1.0, 1), max(R // 4, 2)), flops=3.0 * n * n * 625)
 
-    # K4b: 8 clips x (40 tracks x 40 detections)
-    T = D = 40
-    P = 8
-    a = torch.from_numpy(np.concatenate([random_boxes(rng, T, 1920, 1080, 40, 200, np.float64)[0] for _ in range(P)])).cuda()
-    b = torch.from_numpy(np.concatenate([random_boxes(rng, D, 1920, 1080, 40, 200, np.float64)[0] for _ in range(P)])).cuda()
-    ao = torch.from_numpy((np.arange(P + 1) * T).astype(np.int32)).cuda()
-    bo = torch.from_numpy((np.arange(P + 1) * D).astype(np.int32)).cuda()
-    oo = torch.from_numpy((np.arange(P) * T * D).astype(np.int64)).cuda()
-    report("K4b IoU cost 8 clips x 40x40", timed(lambda: ctx.iou_cost(a, b, None, ao, bo, oo, P, T, D, P * T * D, 2), R), P * (T + D) * 32 + P * T * D * 8)
+    def sec_k4b():
+        # K4b: 8 clips x (40 tracks x 40 detections)
+        T = D = 40
+        P = 8
+        a = torch.from_numpy(np.concatenate([random_boxes(rng, T, 1920, 1080, 40, 200, np.float64)[0] for _ in range(P)])).cuda()
+        b = torch.from_numpy(np.concatenate([random_boxes(rng, D, 1920, 1080, 40, 200, np.float64)[0] for _ in range(P)])).cuda()
+        ao = torch.from_numpy((np.arange(P + 1) * T).astype(np.int32)).cuda()
+        bo = torch.from_numpy((np.arange(P + 1) * D).astype(np.int32)).cuda()
+        oo = torch.from_numpy((np.arange(P) * T * D).astype(np.int64)).cuda()
+        report("K4b IoU cost 8 clips x 40x40", timed(lambda: ctx.iou_cost(a, b, None, ao, bo, oo, P, T, D, P * T * D, 2), R), P * (T + D) * 32 + P * T * D * 8)
 
-    # K5 backbone glue at the YOLOv8m / 1080p (736x1280 input) layer sizes, 32 frames per launch
-    CL = torch.channels_last
-    nb = 32
-    for tag, c, h, w in (("layer0 out 48ch 368x640", 48, 368, 640), ("layer1 out 96ch 184x320", 96, 184, 320),
-                         ("bottleneck 48ch 184x320", 48, 184, 320), ("p3 192ch 92x160", 192, 92, 160)):
-        x = torch.randn(nb, c, h, w, device="cuda").contiguous(memory_format=CL)
-        b = torch.randn(c, device="cuda")
-        r = torch.randn(nb, c, h, w, device="cuda").contiguous(memory_format=CL)
-        nbytes = x.numel() * 4
-        report("K5 bias+SiLU in place x%d %s" % (nb, tag), timed(lambda: ctx.bias_act(x, b, "silu"), R), 2 * nbytes)
-        report("K5 bias+SiLU+residual x%d %s" % (nb, tag), timed(lambda: ctx.bias_act(x, b, "silu", residual=r), R), 3 * nbytes)
-        cat = torch.empty(nb, 2 * c, h, w, device="cuda").contiguous(memory_format=CL)
-        report("K5 bias+SiLU -> dense + concat slice x%d %s" % (nb, tag),
-               timed(lambda: ctx.bias_act(x, b, "silu", out1=x, out2=cat, out2_off=c, c2_begin=0, c2_count=c), R), 3 * nbytes)
-        del x, r, cat
-    p5 = torch.randn(nb, 576, 23, 40, device="cuda").contiguous(memory_format=CL)
-    p4 = torch.randn(nb, 384, 46, 80, device="cuda").contiguous(memory_format=CL)
-    out = ctx.concat_nhwc([p5, p4], [1, 0])
-    report("K5 upsample2x+concat x%d (576@23x40, 384@46x80)" % nb, timed(lambda: ctx.concat_nhwc([p5, p4], [1, 0], out=out), R),
-           p5.numel() * 4 + p4.numel() * 4 + out.numel() * 4)
-    xin = torch.rand(nb, 3, 736, 1280, device="cuda")
-    wst = (np.random.default_rng(0).standard_normal((48, 3, 3, 3)) * 0.2).astype(np.float32)
-    bst = np.zeros((48,), np.float32)
-    ms = timed(lambda: ctx.stem_conv(xin, wst, bst), R)
-    report("K5 stem conv 3->48 s2 + SiLU x%d 736x1280" % nb, ms, xin.numel() * 4 + nb * 48 * 368 * 640 * 4,
-           flops=2 * 27 * 48 * nb * 368 * 640)
+    def sec_k5():
+        # K5 backbone glue at the YOLOv8m / 1080p (736x1280 input) layer sizes, 32 frames per launch
+        CL = torch.channels_last
+        nb = 32
+        shapes = (("layer0 out 48ch 368x640", 48, 368, 640), ("layer1 out 96ch 184x320", 96, 184, 320),
+                  ("bottleneck 48ch 184x320", 48, 184, 320), ("p3 192ch 92x160", 192, 92, 160))
+        for tag, c, h, w in shapes[:1] if args.profile else shapes:
+            x = torch.randn(nb, c, h, w, device="cuda").contiguous(memory_format=CL)
+            b = torch.randn(c, device="cuda")
+            r = torch.randn(nb, c, h, w, device="cuda").contiguous(memory_format=CL)
+            nbytes = x.numel() * 4
+            report("K5 bias+SiLU in place x%d %s" % (nb, tag), timed(lambda: ctx.bias_act(x, b, "silu"), R), 2 * nbytes)
+            report("K5 bias+SiLU+residual x%d %s" % (nb, tag), timed(lambda: ctx.bias_act(x, b, "silu", residual=r), R), 3 * nbytes)
+            cat = torch.empty(nb, 2 * c, h, w, device="cuda").contiguous(memory_format=CL)
+            report("K5 bias+SiLU -> dense + concat slice x%d %s" % (nb, tag),
+                   timed(lambda: ctx.bias_act(x, b, "silu", out1=x, out2=cat, out2_off=c, c2_begin=0, c2_count=c), R), 3 * nbytes)
+            del x, r, cat
+        p5 = torch.randn(nb, 576, 23, 40, device="cuda").contiguous(memory_format=CL)
+        p4 = torch.randn(nb, 384, 46, 80, device="cuda").contiguous(memory_format=CL)
+        out = ctx.concat_nhwc([p5, p4], [1, 0])
+        report("K5 upsample2x+concat x%d (576@23x40, 384@46x80)" % nb, timed(lambda: ctx.concat_nhwc([p5, p4], [1, 0], out=out), R),
+               p5.numel() * 4 + p4.numel() * 4 + out.numel() * 4)
+        xin = torch.rand(nb, 3, 736, 1280, device="cuda")
+        wst = (np.random.default_rng(0).standard_normal((48, 3, 3, 3)) * 0.2).astype(np.float32)
+        bst = np.zeros((48,), np.float32)
+        ms = timed(lambda: ctx.stem_conv(xin, wst, bst), R)
+        report("K5 stem conv 3->48 s2 + SiLU x%d 736x1280" % nb, ms, xin.numel() * 4 + nb * 48 * 368 * 640 * 4,
+               flops=2 * 27 * 48 * nb * 368 * 640)
+
+    if want('k1'):
+        sec_k1()
+    if want('k2'):
+        sec_k2()
+    if want('k3'):
+        sec_k3()
+    if want('k4'):
+        sec_k4()
+    if want('k4b'):
+        sec_k4b()
+    if want('k5'):
+        sec_k5()
 
 
 if __name__ == "__main__":
