@@ -38,6 +38,18 @@ METRIC = "hot_path_frames_per_sec_1080p"
 UNIT = "frames/s"
 
 
+def ncu_traffic(kernel_key: str):
+    """DRAM bytes per launch (dram__bytes_read.sum + dram__bytes_write.sum) of the roofline kernel from the
+    committed `ncu --set full` capture (profiles/ncu_traffic.json, written from tools/ncu_summary.py output)."""
+    p = os.path.join(ROOT, "profiles", "ncu_traffic.json")
+    if not os.path.exists(p):
+        return None
+    try:
+        return json.load(open(p)).get(kernel_key, {}).get("traffic_bytes")
+    except Exception:
+        return None
+
+
 def measured_peaks():
     p = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(p):
@@ -341,7 +353,9 @@ def run_hvb(args, rank, world):
                                    "team classification (K3a/K3b on 12 planted player boxes per frame, MobileNetV3-small fp32, "
                                    "K4a scale_transform, rule)",
                        "frames_per_step_per_gpu": F, "players_per_frame": PLAYERS, "team_boxes": "planted",
-                       "backbones": "torch fp32, conv+bn fused, channels_last, cudnn.benchmark (cudnn TF32 default for YOLO, TF32 off for MobileNetV3)",
+                       "backbones": "convolutions in torch/cuDNN (fp32 storage, conv+bn folded, channels_last, cudnn.benchmark, TF32 for YOLO / "
+                                    "TF32 off for MobileNetV3); everything between the YOLO convolutions (bias, SiLU, residual, concat, "
+                                    "upsample, layer 0) in libhvb K5 kernels",
                        "l2": "inputs larger than L2 (%.0f MB frames + %.0f MB letterboxed per step)" % (frames.nbytes / 1e6, k1_bytes / 1e6),
                        "parallelism": "frame chunks sharded per GPU, no data-path collective; one NCCL feature all-gather at fit"},
             "e2e": {"value": fps_e2e, "unit": UNIT, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h)},
@@ -349,7 +363,8 @@ def run_hvb(args, rank, world):
             "clocks": clocks,
             "roofline": {"kernel": "letterbox_kernel<false> (K1a, 1080p->736x1280, %d frames/launch)" % F, "bound": "hbm",
                          "achieved": achieved, "peak": peak, "peak_source": peak_src, "unit": "GB/s", "frac": achieved / peak,
-                         "traffic": None, "algorithmic_bytes_per_launch": int(k1_bytes), "avg_launch_ms": k1_ms},
+                         "traffic": ncu_traffic("K1a_1080p_x%d" % F), "algorithmic_bytes_per_launch": int(k1_bytes),
+                         "avg_launch_ms": k1_ms},
             "cpu_baseline": cpu,
             "extra": extra,
         }

@@ -29,6 +29,9 @@ struct hvb_ctx {
     size_t scratch3_bytes = 0;
     void* pinned = nullptr;
     size_t pinned_bytes = 0;
+    // K2a split-scan work area: device counters (kept zero between launches) + per-image candidate key lists
+    void* k2_work_dev = nullptr;
+    size_t k2_work_bytes = 0, k2_ctr_bytes = 0;
 };
 
 void hvb_set_error(const char* fmt, ...);

@@ -124,6 +124,7 @@ int hvb_ctx_destroy(hvb_ctx* ctx) {
     if (ctx->scratch_dev) cudaFree(ctx->scratch_dev);
     if (ctx->scratch2_dev) cudaFree(ctx->scratch2_dev);
     if (ctx->scratch3_dev) cudaFree(ctx->scratch3_dev);
+    if (ctx->k2_work_dev) cudaFree(ctx->k2_work_dev);
     if (ctx->pinned) cudaFreeHost(ctx->pinned);
     if (ctx->ev_start) cudaEventDestroy(ctx->ev_start);
     if (ctx->ev_stop) cudaEventDestroy(ctx->ev_stop);

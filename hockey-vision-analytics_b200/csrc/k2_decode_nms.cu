@@ -1,12 +1,17 @@
 // K2a — YOLOv8 Detect head decode + confidence gate + per-image class-aware NMS + scale_boxes,
-// one CTA per image, one launch per batch.  Replaces ultralytics Detect._inference /
+// one launch per batch: grid = (anchor chunks, images).  Replaces ultralytics Detect._inference /
 // ops.non_max_suppression (torchvision.ops.nms) / ops.scale_boxes reached from
 // hockey/main.py:179-186.
 //
-// Pipeline inside a CTA (256 threads):
-//   1. scan the image's anchors: read only the nc class logits per anchor (coalesced across
-//      threads), sigmoid, first-max over classes, conf > thr gate; survivors are appended to a
-//      shared-memory key list  key = score_bits << 32 | (0xFFFFFF - anchor) << 8 | cls
+// Pipeline (256 threads per CTA):
+//   1. every CTA scans ONE 1024-anchor chunk of one image: read only the nc class logits per anchor,
+//      cheap logit pre-gate (x > logit(thr) - margin) and the exact fp32 sigmoid only for the few logits
+//      that pass it, first-max over classes, conf > thr gate; survivors are appended to the image's
+//      key list in global scratch  key = score_bits << 32 | (0xFFFFFF - anchor) << 8 | cls.
+//      The chunk CTAs of an image count themselves off on a device counter; the LAST one to finish
+//      (threadFenceReduction pattern) pulls the list into shared memory and runs steps 2-5, so the
+//      latency-bound scan is spread over all SMs while sort + NMS stay on chip.  The append order is
+//      arbitrary but keys are unique per image, so the sorted order — and the result — is deterministic.
 //   2. bitonic sort of the keys (descending): score order, ties -> lower anchor index first
 //      (== torchvision's stable descending sort of the filtered rows)
 //   3. decode the DFL box of each survivor only (64 strided reads + 4 softmax-expectations)
@@ -165,59 +170,85 @@ __device__ __forceinline__ NmsSmem carve(uint8_t* smem, int cap, int max_det) {
 
 size_t nms_smem_bytes(int cap, int max_det) { return (size_t)cap * 24 + (size_t)max_det * 20; }
 
+constexpr int kChunk = 1024;                         // anchors scanned per CTA
+constexpr int kPerThread = kChunk / kThreads;
+
 __global__ void __launch_bounds__(kThreads)
-decode_nms_kernel(Levels L, int nc, float conf_thres, float iou_thres, int max_det, int agnostic, int cap,
+decode_nms_kernel(Levels L, int nc, float conf_thres, float pre_gate, float iou_thres, int max_det, int agnostic, int cap,
                   const hvb_img_meta* __restrict__ meta, float* __restrict__ out_xyxy, float* __restrict__ out_conf,
-                  int32_t* __restrict__ out_cls, int32_t* __restrict__ out_count, const int32_t* __restrict__ only_images) {
+                  int32_t* __restrict__ out_cls, int32_t* __restrict__ out_count, const int32_t* __restrict__ only_images,
+                  unsigned long long* __restrict__ g_keys /*[images][cap]*/, int32_t* __restrict__ g_ctr /*[images][2]*/) {
     extern __shared__ __align__(16) uint8_t smem[];
     __shared__ int s_count;
     __shared__ int s_nkept;
     __shared__ unsigned s_sup[kWarps];
     NmsSmem S = carve(smem, cap, max_det);
 
-    const int b = only_images ? only_images[blockIdx.x] : blockIdx.x;
-    if (threadIdx.x == 0) s_count = 0;
-    __syncthreads();
+    const int img = blockIdx.y;
+    const int b = only_images ? only_images[img] : img;
+    unsigned long long* keys_g = g_keys + (size_t)img * cap;
+    int32_t* ctr = g_ctr + 2 * img;                   // [0] candidates appended, [1] chunk CTAs finished
 
-    // ---- 1. scan class logits, gate, append
+    // ---- 1. scan this CTA's chunk of class logits, gate, append to the image's global key list.
+    // All loads of the kPerThread anchors are issued before the first append (no sync in between).
     const int A = L.base[3];
-    for (int a0 = 0; a0 < A; a0 += kThreads) {
-        const int a = a0 + threadIdx.x;
-        bool pass = false;
-        float best = 0.f;
-        int bestc = 0;
+    const int a_begin = blockIdx.x * kChunk;
+    float best[kPerThread];
+    int bestc[kPerThread];
+#pragma unroll
+    for (int i = 0; i < kPerThread; i++) {
+        const int a = a_begin + i * kThreads + threadIdx.x;
+        best[i] = -1.f; bestc[i] = 0;
         if (a < A) {
             int lvl, q;
             locate(L, a, lvl, q);
             const float* p = L.ptr[lvl] + (int64_t)b * L.bstride[lvl] + (int64_t)q * L.astride[lvl] + 64 * L.cstride[lvl];
-            best = -1.f;
             for (int c = 0; c < nc; c++) {
-                float s = sigmoidf_exact(__ldg(p + (int64_t)c * L.cstride[lvl]));
-                if (s > best) { best = s; bestc = c; }
-            }
-            pass = best > conf_thres;
-        }
-        // warp-aggregated append
-        unsigned m = __ballot_sync(0xffffffffu, pass);
-        if (m) {
-            const int lane = threadIdx.x & 31;
-            int base = 0;
-            if (lane == 0) base = atomicAdd(&s_count, __popc(m));
-            base = __shfl_sync(0xffffffffu, base, 0);
-            if (pass) {
-                int slot = base + __popc(m & ((1u << lane) - 1u));
-                if (slot < cap)
-                    S.keys[slot] = ((unsigned long long)__float_as_uint(best) << 32) |
-                                   ((unsigned long long)(0xFFFFFFu - (unsigned)a) << 8) | (unsigned)bestc;
+                const float x = __ldg(p + (int64_t)c * L.cstride[lvl]);
+                // a logit at or below the pre-gate has sigmoid <= conf_thres, so it can neither pass nor be the max of a
+                // passing anchor; the exact sigmoid (expf + IEEE division) is evaluated only above it
+                if (x > pre_gate) {
+                    const float sg = sigmoidf_exact(x);
+                    if (sg > best[i]) { best[i] = sg; bestc[i] = c; }
+                }
             }
         }
     }
+#pragma unroll
+    for (int i = 0; i < kPerThread; i++) {
+        const int a = a_begin + i * kThreads + threadIdx.x;
+        const bool pass = a < A && best[i] > conf_thres;
+        const unsigned m = __ballot_sync(0xffffffffu, pass);       // warp-aggregated append
+        if (m) {
+            const int lane = threadIdx.x & 31;
+            int base = 0;
+            if (lane == 0) base = atomicAdd(&ctr[0], __popc(m));
+            base = __shfl_sync(0xffffffffu, base, 0);
+            if (pass) {
+                const int slot = base + __popc(m & ((1u << lane) - 1u));
+                if (slot < cap)
+                    keys_g[slot] = ((unsigned long long)__float_as_uint(best[i]) << 32) |
+                                   ((unsigned long long)(0xFFFFFFu - (unsigned)a) << 8) | (unsigned)bestc[i];
+            }
+        }
+    }
+    // ---- last chunk CTA of the image takes over
+    __threadfence();
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        const int prev = atomicAdd(&ctr[1], 1);
+        s_count = (prev == (int)gridDim.x - 1) ? atomicAdd(&ctr[0], 0) : -1;
+        if (s_count >= 0) { ctr[0] = 0; ctr[1] = 0; }             // ready for the next launch
+    }
     __syncthreads();
     const int total = s_count;
+    if (total < 0) return;
+    __threadfence();
     if (total > cap) {                       // capacity exceeded: report, host retries with the large tier
         if (threadIdx.x == 0) out_count[meta[b].out_slot] = -1;
         return;
     }
+    for (int i = threadIdx.x; i < total; i += kThreads) S.keys[i] = __ldcg(keys_g + i);
     const int n = total;
     int n_pow2 = 1;
     while (n_pow2 < n) n_pow2 <<= 1;
@@ -335,6 +366,35 @@ int fill_levels(Levels& L, const float* const level_dev[3], const int32_t level_
     return HVB_OK;
 }
 
+// Conservative logit-space version of `sigmoid(x) > conf`: everything at or below the returned value has
+// sigmoid(x) <= conf with a margin (1e-3 in logit space) far larger than the fp32 error of the exact sigmoid.
+float logit_pre_gate(float conf) {
+    if (!(conf > 0.0f)) return -INFINITY;
+    if (conf >= 1.0f) return INFINITY;
+    const double lg = log((double)conf / (1.0 - (double)conf));
+    return (float)(lg - 1e-3 - 1e-5 * fabs(lg));
+}
+
+// Global work area of the split scan: [images][2] int32 counters (zero between launches: zeroed when the
+// buffer is (re)allocated, reset by the finalising CTA after use) followed by [images][cap] 64-bit keys.
+int k2_work(hvb_ctx* ctx, int images, int cap, unsigned long long** keys, int32_t** ctr) {
+    const size_t ctr_bytes = (((size_t)images * 2 * sizeof(int32_t)) + 255) & ~(size_t)255;
+    const size_t key_bytes = (size_t)images * cap * sizeof(unsigned long long);
+    if (ctr_bytes > ctx->k2_ctr_bytes || key_bytes > ctx->k2_work_bytes - ctx->k2_ctr_bytes) {
+        // the stream may still be using the old buffer: drain it before replacing (rare: only on growth)
+        HVB_CUDA(cudaStreamSynchronize(ctx->stream));
+        if (ctx->k2_work_dev) HVB_CUDA(cudaFree(ctx->k2_work_dev));
+        ctx->k2_work_dev = nullptr; ctx->k2_work_bytes = 0; ctx->k2_ctr_bytes = 0;
+        const size_t ctr_cap = ctr_bytes * 2, total = ctr_cap + key_bytes * 2;
+        HVB_CUDA(cudaMalloc(&ctx->k2_work_dev, total));
+        HVB_CUDA(cudaMemset(ctx->k2_work_dev, 0, ctr_cap));
+        ctx->k2_work_bytes = total; ctx->k2_ctr_bytes = ctr_cap;
+    }
+    *ctr = reinterpret_cast<int32_t*>(ctx->k2_work_dev);
+    *keys = reinterpret_cast<unsigned long long*>(reinterpret_cast<uint8_t*>(ctx->k2_work_dev) + ctx->k2_ctr_bytes);
+    return HVB_OK;
+}
+
 template <typename K>
 int set_smem(K kernel, size_t bytes) {
     if (bytes > 227 * 1024) {
@@ -368,11 +428,16 @@ int hvb_decode_nms(hvb_ctx* ctx, const float* const level_dev[3], const int32_t 
     HVB_TRY(fill_levels(L, level_dev, level_h, level_w, batch_stride, chan_stride, anchor_stride));
 
     // Tier 1: small shared-memory capacity for every image.
+    HVB_ARG(batch <= 65535, "more than 65535 images in one launch");
     size_t sm1 = nms_smem_bytes(kCapSmall, max_det);
     HVB_TRY(set_smem(decode_nms_kernel, sm1));
-    decode_nms_kernel<<<batch, kThreads, sm1, ctx->stream>>>(L, nc, conf_thres, iou_thres, max_det, agnostic, kCapSmall,
-                                                             meta_dev, out_xyxy_dev, out_conf_dev, out_cls_dev,
-                                                             out_count_dev, nullptr);
+    unsigned long long* keys = nullptr;
+    int32_t* ctr = nullptr;
+    HVB_TRY(k2_work(ctx, batch, kCapSmall, &keys, &ctr));
+    dim3 grid(hvb_div_up(L.base[3], kChunk), batch);
+    decode_nms_kernel<<<grid, kThreads, sm1, ctx->stream>>>(L, nc, conf_thres, logit_pre_gate(conf_thres), iou_thres, max_det,
+                                                            agnostic, kCapSmall, meta_dev, out_xyxy_dev, out_conf_dev,
+                                                            out_cls_dev, out_count_dev, nullptr, keys, ctr);
     HVB_LAUNCHED(ctx);
     return HVB_OK;
 }
@@ -390,11 +455,16 @@ int hvb_decode_nms_large(hvb_ctx* ctx, const float* const level_dev[3], const in
     HVB_ARG(images_dev && meta_dev && out_xyxy_dev && out_conf_dev && out_cls_dev && out_count_dev, "null pointer");
     Levels L;
     HVB_TRY(fill_levels(L, level_dev, level_h, level_w, batch_stride, chan_stride, anchor_stride));
+    HVB_ARG(n_images <= 65535, "more than 65535 images in one launch");
     size_t sm = nms_smem_bytes(kCapLarge, max_det);
     HVB_TRY(set_smem(decode_nms_kernel, sm));
-    decode_nms_kernel<<<n_images, kThreads, sm, ctx->stream>>>(L, nc, conf_thres, iou_thres, max_det, agnostic, kCapLarge,
-                                                               meta_dev, out_xyxy_dev, out_conf_dev, out_cls_dev,
-                                                               out_count_dev, images_dev);
+    unsigned long long* keys = nullptr;
+    int32_t* ctr = nullptr;
+    HVB_TRY(k2_work(ctx, n_images, kCapLarge, &keys, &ctr));
+    dim3 grid(hvb_div_up(L.base[3], kChunk), n_images);
+    decode_nms_kernel<<<grid, kThreads, sm, ctx->stream>>>(L, nc, conf_thres, logit_pre_gate(conf_thres), iou_thres, max_det,
+                                                           agnostic, kCapLarge, meta_dev, out_xyxy_dev, out_conf_dev,
+                                                           out_cls_dev, out_count_dev, images_dev, keys, ctr);
     HVB_LAUNCHED(ctx);
     return HVB_OK;
 }

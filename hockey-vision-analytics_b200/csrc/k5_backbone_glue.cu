@@ -177,44 +177,69 @@ template <int CO>
 __global__ void __launch_bounds__(STEM_PX)
 stem_conv_kernel(const float* __restrict__ in, float* __restrict__ out, int H, int W, int OH, int OW,
                  const __grid_constant__ StemParams<CO> prm) {
-    __shared__ float s_in[3][3][2 * STEM_PX + 2];            // [ci][ky][input column - (2*ox0 - 1)]
-    __shared__ __align__(16) float s_out[STEM_PX * (CO + 1)]; // +1: conflict-free transposed read
+    // Input window of the block, de-interleaved by column parity so that the three taps of thread t are
+    // stride-1 across the warp: window column j (frame column 2*ox0 - 2 + j) lives in s_ev[j/2] or s_od[j/2];
+    // tap kx of output t reads window column 2t + kx + 1  ->  od[t], ev[t+1], od[t+1].
+    __shared__ float s_ev[3][3][STEM_PX + 2];
+    __shared__ float s_od[3][3][STEM_PX + 2];
+    constexpr int LDO = CO + 4;                                   // 16-byte aligned rows, conflict-free 128-bit accesses
+    __shared__ __align__(16) float s_out[STEM_PX * LDO];
     const int n = blockIdx.z, oy = blockIdx.y, ox0 = blockIdx.x * STEM_PX;
-    const int ix0 = 2 * ox0 - 1;
-    const int ncols = min(2 * STEM_PX + 1, 2 * (OW - ox0) + 1);
-    for (int i = threadIdx.x; i < 9 * (2 * STEM_PX + 2); i += STEM_PX) {
-        const int plane = i / (2 * STEM_PX + 2), col = i - plane * (2 * STEM_PX + 2);
+    const int t = threadIdx.x;
+    const int ixw = 2 * ox0 - 2;                                  // frame column of window column 0 (even)
+    const bool pair_ok = (W & 1) == 0 && ((reinterpret_cast<uintptr_t>(in) & 7) == 0);
+#pragma unroll
+    for (int plane = 0; plane < 9; ++plane) {
         const int ci = plane / 3, ky = plane - ci * 3;
-        const int iy = 2 * oy - 1 + ky, ix = ix0 + col;
-        float v = 0.0f;
-        if (col < ncols && iy >= 0 && iy < H && ix >= 0 && ix < W)
-            v = __ldg(in + (((size_t)n * 3 + ci) * H + iy) * W + ix);
-        s_in[ci][ky][col] = v;
+        const int iy = 2 * oy - 1 + ky;
+        const float* row = in + (((size_t)n * 3 + ci) * H + iy) * W;
+        const bool row_ok = iy >= 0 && iy < H;
+        for (int j = t; j < STEM_PX + 2; j += STEM_PX) {          // pair j = window columns 2j, 2j+1
+            const int ix = ixw + 2 * j;
+            float e = 0.0f, o = 0.0f;
+            if (row_ok) {
+                if (pair_ok && ix >= 0 && ix + 1 < W) {
+                    const float2 v = __ldg(reinterpret_cast<const float2*>(row + ix));
+                    e = v.x; o = v.y;
+                } else {
+                    if (ix >= 0 && ix < W) e = __ldg(row + ix);
+                    if (ix + 1 >= 0 && ix + 1 < W) o = __ldg(row + ix + 1);
+                }
+            }
+            s_ev[ci][ky][j] = e; s_od[ci][ky][j] = o;
+        }
     }
     __syncthreads();
-    const int t = threadIdx.x;
     float acc[CO];
 #pragma unroll
     for (int co = 0; co < CO; ++co) acc[co] = prm.b[co];
 #pragma unroll
     for (int ci = 0; ci < 3; ++ci)
 #pragma unroll
-        for (int ky = 0; ky < 3; ++ky)
+        for (int ky = 0; ky < 3; ++ky) {
+            const float x0 = s_od[ci][ky][t], x1 = s_ev[ci][ky][t + 1], x2 = s_od[ci][ky][t + 1];
 #pragma unroll
-            for (int kx = 0; kx < 3; ++kx) {
-                const float x = s_in[ci][ky][2 * t + kx];
-#pragma unroll
-                for (int co = 0; co < CO; ++co) acc[co] = __fmaf_rn(prm.w[((ci * 3 + ky) * 3 + kx) * CO + co], x, acc[co]);
+            for (int co = 0; co < CO; ++co) {
+                acc[co] = __fmaf_rn(prm.w[((ci * 3 + ky) * 3 + 0) * CO + co], x0, acc[co]);
+                acc[co] = __fmaf_rn(prm.w[((ci * 3 + ky) * 3 + 1) * CO + co], x1, acc[co]);
+                acc[co] = __fmaf_rn(prm.w[((ci * 3 + ky) * 3 + 2) * CO + co], x2, acc[co]);
             }
+        }
 #pragma unroll
-    for (int co = 0; co < CO; ++co) s_out[t * (CO + 1) + co] = silu_fast(acc[co]);
+    for (int c4 = 0; c4 < CO / 4; ++c4) {
+        float4 v;
+        v.x = silu_fast(acc[4 * c4]); v.y = silu_fast(acc[4 * c4 + 1]); v.z = silu_fast(acc[4 * c4 + 2]); v.w = silu_fast(acc[4 * c4 + 3]);
+        *reinterpret_cast<float4*>(&s_out[t * LDO + 4 * c4]) = v;
+    }
     __syncthreads();
-    // the block's 128 x CO outputs are one contiguous NHWC run: coalesced stores
+    // the block's 128 x CO outputs are one contiguous NHWC run: coalesced 128-bit stores
     const int npx = min(STEM_PX, OW - ox0);
-    float* o = out + (((size_t)n * OH + oy) * OW + ox0) * CO;
-    for (int i = threadIdx.x; i < npx * CO; i += STEM_PX) {
-        const int px = i / CO, co = i - px * CO;
-        o[i] = s_out[px * (CO + 1) + co];
+    float4* o4 = reinterpret_cast<float4*>(out + (((size_t)n * OH + oy) * OW + ox0) * CO);
+    constexpr int Q = CO / 4;
+#pragma unroll 4
+    for (int i = t; i < npx * Q; i += STEM_PX) {
+        const int px = i / Q, q = i - px * Q;
+        o4[i] = *reinterpret_cast<const float4*>(&s_out[px * LDO + 4 * q]);
     }
 }
 

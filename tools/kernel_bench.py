@@ -63,7 +63,8 @@ def main():
 
     def sec_k1():
         # K1a / K1b
-        for tag, n, h, w, mode, imgsz in (("K1a 1080p->736x1280 x16", 16, 1080, 1920, _ffi.LB_WHOLE, 1280),
+        for tag, n, h, w, mode, imgsz in (("K1a 1080p->736x1280 x32 (bench.py's launch)", 32, 1080, 1920, _ffi.LB_WHOLE, 1280),
+                                          ("K1a 1080p->736x1280 x16", 16, 1080, 1920, _ffi.LB_WHOLE, 1280),
                                           ("K1a 1080p->736x1280 x64", 64, 1080, 1920, _ffi.LB_WHOLE, 1280),
                                           ("K1a 720p->384x640 x64 (2x area path)", 64, 720, 1280, _ffi.LB_WHOLE, 640),
                                           ("K1b 4K sliced exact x4", 4, 2160, 3840, _ffi.LB_SLICE_EXACT, 640),
