@@ -10,13 +10,15 @@
 // the RGB statistics unswapped, like the reference.
 //
 // One CTA per crop.  Coefficients and the uint8 intermediate live in shared memory; tall ROIs are
-// processed in output-row blocks so that the intermediate window always fits.  Two instantiations of
-// the same kernel body share the work: the FAST one (<= 8 taps per sample, i.e. ROI up to 192 x 384 px —
-// every player crop of a 1080p/4K rink frame — 128 intermediate rows, ~35 KB shared memory; four CTAs
-// are resident per SM, so the per-crop chain load -> sync -> filter -> sync -> store of one CTA hides
-// behind the others) and the GENERAL one (<= 48 taps, 87 KB) which only touches the crops the fast
-// one skipped.  ToTensor + Normalize are a 3 x 256-entry table built once per CTA with the exact
-// float32 divisions, so the store loop does one shared-memory lookup per value.
+// processed in output-row blocks so that the intermediate window always fits.  Two kernels share the
+// work: the FAST one (<= 8 taps per sample, i.e. ROI up to 192 x 384 px — every player crop of a
+// 1080p/4K rink frame) first stages the block's source rows into shared memory with aligned 32-bit
+// loads, all of them in flight at once (the ROI rows are unaligned 3-byte pixels; the first/last
+// partial word of a row is assembled from byte loads so nothing outside the ROI is touched), then runs
+// both filter passes out of shared memory; ~50 KB per CTA, four CTAs resident per SM.  The GENERAL one
+// (<= 48 taps, 87 KB, filters straight from global memory) only touches the crops the fast one skipped.
+// ToTensor + Normalize are a 3 x 256-entry table built once per CTA with the exact float32 divisions, so
+// the store loop does one shared-memory lookup per value.
 #include "hvb_common.cuh"
 #include "hvb_roi.cuh"
 
@@ -37,7 +39,8 @@ struct SmemT {
     uint8_t inter[ROWS * kOutW * 3];
     int blk[4];
 };
-constexpr int kFastK = 8, kFastRows = 128;        // ROI up to 192 x 384 px (scale <= 3 per axis)
+constexpr int kFastK = 8, kFastRows = 96;         // ROI up to 192 x 384 px (scale <= 3 per axis)
+constexpr int kStageBytes = 20480;                // staged source rows of one row block (fast kernel)
 constexpr int kGenK = 48, kGenRows = 256;         // ROI up to ~1400 x 2900 px
 
 // Pillow precompute_coeffs + normalize_coeffs_8bpc for output sample `o` (bilinear, support 1).
@@ -92,6 +95,135 @@ __device__ __forceinline__ void write_out(const float (*lut)[256], float* __rest
     }
 }
 
+struct SmemFast {
+    int bh[kOutW][2];
+    int bv[kOutH][2];
+    int kh[kOutW * kFastK];
+    int kv[kOutH * kFastK];
+    float lut[3][256];
+    uint8_t inter[kFastRows * kOutW * 3];
+    uint32_t roi[kStageBytes / 4];      // staged source rows: row r at byte r * pitch_s, ROI byte 0 at + shift_r
+    int blk[4];
+};
+
+__device__ __forceinline__ bool mnv3_fast_case(int rw, int rh, int ksh, int ksv) {
+    // empty ROIs, and ROIs within the tap budget that resize horizontally first (rh <= 100 * rw)
+    return rw <= 0 || rh <= 0 || (ksh <= kFastK && ksv <= kFastK && !(rh > 100 * rw));
+}
+
+__global__ void __launch_bounds__(kThreads, 4)
+mnv3_prep_fast_kernel(const uint8_t* __restrict__ pixels, const hvb_crop_desc* __restrict__ crops, int n, int roi_mode,
+                      float* __restrict__ out, uint8_t* __restrict__ out_u8, uint8_t* __restrict__ out_valid) {
+    extern __shared__ __align__(16) uint8_t smem_raw[];
+    SmemFast& S = *reinterpret_cast<SmemFast*>(smem_raw);
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+
+    bool lut_ready = false;
+    for (int ci = blockIdx.x; ci < n; ci += gridDim.x) {
+        const hvb_crop_desc cd = crops[ci];
+        const hvb_rect rc = hvb_roi_rect(cd.h, cd.w, roi_mode);
+        const int rw = max(rc.right - rc.left, 0), rh = max(rc.bottom - rc.top, 0);
+        const int ksh = (rw > 0) ? pil_ksize(rw, kOutW) : 1, ksv = (rh > 0) ? pil_ksize(rh, kOutH) : 1;
+        if (!mnv3_fast_case(rw, rh, ksh, ksv)) continue;            // the general kernel owns this crop
+        float* o = out + (int64_t)ci * 3 * kOutH * kOutW;
+        uint8_t* o8 = out_u8 ? out_u8 + (int64_t)ci * kOutH * kOutW * 3 : nullptr;
+        if (rw <= 0 || rh <= 0) {
+            // empty ROI: the reference's `except:` path (zero feature row)
+            for (int i = threadIdx.x; i < 3 * kOutH * kOutW; i += kThreads) o[i] = 0.f;
+            if (o8) for (int i = threadIdx.x; i < 3 * kOutH * kOutW; i += kThreads) o8[i] = 0;
+            if (out_valid && threadIdx.x == 0) out_valid[ci] = 0;
+            continue;
+        }
+        if (!lut_ready) {
+            const float mean[3] = {0.485f, 0.456f, 0.406f};
+            const float stdv[3] = {0.229f, 0.224f, 0.225f};
+            for (int i = threadIdx.x; i < 3 * 256; i += kThreads) {
+                const int c = i >> 8, v = i & 255;
+                S.lut[c][v] = __fdiv_rn(__fsub_rn(__fdiv_rn((float)v, 255.0f), mean[c]), stdv[c]);   // ToTensor, Normalize
+            }
+            lut_ready = true;                       // visible after the __syncthreads below
+        }
+        if (out_valid && threadIdx.x == 0) out_valid[ci] = 1;
+        const uint8_t* base = pixels + cd.offset + (int64_t)rc.top * cd.pitch + (int64_t)rc.left * 3;
+        const int row_bytes = rw * 3;
+        const int pitch_s = ((row_bytes + 3 + 3) >> 2) << 2;       // room for a shift of up to 3 bytes, word multiple
+        const int rmax = min(kFastRows, kStageBytes / pitch_s);    // >= 8 = kFastK source rows always fit
+
+        __syncthreads();   // previous crop's readers are done with the tables
+        if (threadIdx.x < kOutW) pil_coeffs(rw, kOutW, threadIdx.x, ksh, S.bh[threadIdx.x], S.kh);
+        else if (threadIdx.x >= 128 && threadIdx.x < 128 + kOutH) pil_coeffs(rh, kOutH, threadIdx.x - 128, ksv, S.bv[threadIdx.x - 128], S.kv);
+        __syncthreads();
+
+        int y0 = 0;
+        while (y0 < kOutH) {
+            // largest block of output rows whose source-row window fits the staging + intermediate buffers
+            if (threadIdx.x == 0) {
+                const int r_lo = S.bv[y0][0];
+                int y1 = y0 + 1;
+                while (y1 < kOutH && S.bv[y1][0] + S.bv[y1][1] - r_lo <= rmax) y1++;
+                S.blk[0] = y1; S.blk[1] = r_lo; S.blk[2] = S.bv[y1 - 1][0] + S.bv[y1 - 1][1];
+            }
+            __syncthreads();
+            const int y1 = S.blk[0], r_lo = S.blk[1], r_hi = S.blk[2];
+            const int nrows = r_hi - r_lo;
+            // ---- stage rows [r_lo, r_hi): warp per row, lane per aligned 32-bit word; all loads independent
+            for (int r = warp; r < nrows; r += kThreads / 32) {
+                const uint8_t* rowp = base + (int64_t)(r_lo + r) * cd.pitch;
+                const int sh = (int)(reinterpret_cast<uintptr_t>(rowp) & 3);
+                const uint8_t* ap = rowp - sh;                      // aligned-down address of the row's first word
+                const int nwords = (sh + row_bytes + 3) >> 2;
+                uint32_t* dst = S.roi + r * (pitch_s >> 2);
+                for (int i = lane; i < nwords; i += 32) {
+                    uint32_t v;
+                    const int b0 = 4 * i - sh;                      // ROI byte index of the word's first byte
+                    if (b0 >= 0 && b0 + 4 <= row_bytes) {
+                        v = __ldg(reinterpret_cast<const uint32_t*>(ap) + i);
+                    } else {                                        // first / last partial word: only bytes of the ROI
+                        v = 0;
+#pragma unroll
+                        for (int k = 0; k < 4; k++)
+                            if (b0 + k >= 0 && b0 + k < row_bytes) v |= (uint32_t)__ldg(rowp + b0 + k) << (8 * k);
+                    }
+                    dst[i] = v;
+                }
+            }
+            __syncthreads();
+            // ---- horizontal pass out of shared memory: rows [r_lo, r_hi) -> inter[row - r_lo][xx][c]
+            const uint8_t* sroi = reinterpret_cast<const uint8_t*>(S.roi);
+            const int sh0 = (int)(reinterpret_cast<uintptr_t>(base + (int64_t)r_lo * cd.pitch) & 3), dsh = cd.pitch & 3;
+            for (int it = threadIdx.x; it < nrows * kOutW; it += kThreads) {
+                const int row = it >> 6, xx = it & (kOutW - 1);
+                const int xmin = S.bh[xx][0], cnt = S.bh[xx][1];
+                const uint8_t* src = sroi + row * pitch_s + ((sh0 + row * dsh) & 3) + xmin * 3;
+                const int* k = S.kh + xx * ksh;
+                int s0 = 1 << (kPrecision - 1), s1 = s0, s2 = s0;
+                for (int x = 0; x < cnt; x++) {
+                    const int kk = k[x];
+                    s0 += src[3 * x] * kk; s1 += src[3 * x + 1] * kk; s2 += src[3 * x + 2] * kk;
+                }
+                uint8_t* d = S.inter + (row * kOutW + xx) * 3;
+                d[0] = (uint8_t)clip8(s0); d[1] = (uint8_t)clip8(s1); d[2] = (uint8_t)clip8(s2);
+            }
+            __syncthreads();
+            // ---- vertical pass: output rows [y0, y1)
+            for (int it = threadIdx.x; it < (y1 - y0) * kOutW; it += kThreads) {
+                const int y = y0 + (it >> 6), x = it & (kOutW - 1);
+                const int ymin = S.bv[y][0], cnt = S.bv[y][1];
+                const int* k = S.kv + y * ksv;
+                const uint8_t* src = S.inter + ((ymin - r_lo) * kOutW + x) * 3;
+                int s0 = 1 << (kPrecision - 1), s1 = s0, s2 = s0;
+                for (int t = 0; t < cnt; t++) {
+                    const int kk = k[t];
+                    s0 += src[t * kOutW * 3] * kk; s1 += src[t * kOutW * 3 + 1] * kk; s2 += src[t * kOutW * 3 + 2] * kk;
+                }
+                write_out(S.lut, o, o8, y, x, clip8(s0), clip8(s1), clip8(s2));
+            }
+            __syncthreads();
+            y0 = y1;
+        }
+    }
+}
+
 // FAST = true: handles the crops that fit the small tables and skips the rest; FAST = false: the complement.
 template <int KMAX, int ROWS, bool FAST>
 __global__ void __launch_bounds__(kThreads)
@@ -112,8 +244,7 @@ mnv3_prep_kernel(const uint8_t* __restrict__ pixels, const hvb_crop_desc* __rest
         const int ksh = (rw > 0) ? pil_ksize(rw, kOutW) : 1, ksv = (rh > 0) ? pil_ksize(rh, kOutH) : 1;
         const bool vfirst = rh > 100 * rw;
         // the fast instantiation owns: empty ROIs, and ROIs within its tap budget that resize horizontally first
-        const bool fast_case = rw <= 0 || rh <= 0 || (ksh <= kFastK && ksv <= kFastK && !vfirst);
-        if (fast_case != FAST) continue;
+        if (mnv3_fast_case(rw, rh, ksh, ksv) != FAST) continue;
         if (!lut_ready) {
             const float mean[3] = {0.485f, 0.456f, 0.406f};
             const float stdv[3] = {0.229f, 0.224f, 0.225f};
@@ -227,11 +358,11 @@ int hvb_mnv3_preprocess(hvb_ctx* ctx, const uint8_t* pixels_dev, const hvb_crop_
     HVB_ARG(roi_mode >= 0 && roi_mode <= 2, "bad roi_mode");
     if (n == 0) return HVB_OK;
     HVB_ARG(pixels_dev && crops_dev && out_dev, "null pointer");
-    typedef SmemT<kFastK, kFastRows> SmemFast;
     typedef SmemT<kGenK, kGenRows> SmemGen;
-    static_assert(sizeof(SmemFast) <= 37 * 1024 && sizeof(SmemGen) < 200 * 1024, "smem budget");
-    auto fast = mnv3_prep_kernel<kFastK, kFastRows, true>;
+    static_assert(sizeof(SmemFast) <= 52 * 1024 && sizeof(SmemGen) < 200 * 1024, "smem budget");
+    auto fast = mnv3_prep_fast_kernel;
     auto gen = mnv3_prep_kernel<kGenK, kGenRows, false>;
+    HVB_CUDA(cudaFuncSetAttribute(fast, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(SmemFast)));
     HVB_CUDA(cudaFuncSetAttribute(gen, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(SmemGen)));
     // fast pass: one CTA per crop up to the four CTAs (64 registers x 256 threads) resident per SM
     const int gfast = n < ctx->sm_count * 4 ? n : ctx->sm_count * 4;

@@ -33,6 +33,8 @@ template <int V> struct Vec;
 template <> struct Vec<4> { typedef float4 T; };
 template <> struct Vec<2> { typedef float2 T; };
 template <> struct Vec<1> { typedef float T; };
+struct __align__(32) float8 { float4 lo, hi; };
+template <> struct Vec<8> { typedef float8 T; };
 
 template <int V> __device__ __forceinline__ void vload(const float* p, float (&r)[V]) {
     typename Vec<V>::T t = *reinterpret_cast<const typename Vec<V>::T*>(p);
@@ -243,6 +245,71 @@ stem_conv_kernel(const float* __restrict__ in, float* __restrict__ out, int H, i
     }
 }
 
+// ------------------------------------------------------------------------------------------------
+// SPPF pooling: ultralytics SPPF.forward computes y1 = m(y0), y2 = m(y1), y3 = m(y2) with m = MaxPool2d(5, 1, 2)
+// and concatenates [y0, y1, y2, y3].  One CTA holds an (image, CH-channel slice) tile of y0 in shared memory and
+// runs the three cascaded pools on chip (each separable: 5-wide row max, then 5-tall column max; out-of-range
+// taps are skipped, which is MaxPool's implicit -inf padding), writing every stage straight into its slice of
+// the NHWC concat buffer: y0 is read from HBM once and nothing but the concat buffer is written.
+template <int CH>
+__global__ void __launch_bounds__(256)
+sppf_pool_concat_kernel(const float* __restrict__ y0, int h, int w, int c, float* __restrict__ cat) {
+    extern __shared__ __align__(16) float sp[];                 // [2][h*w][CH]: current stage, row-max scratch
+    typedef typename Vec<CH>::T VT;
+    const int n = blockIdx.y, c0 = blockIdx.x * CH, hw = h * w;
+    VT* cur = reinterpret_cast<VT*>(sp);
+    VT* tmp = cur + hw;
+    const float* src = y0 + (size_t)n * hw * c + c0;
+    float* dst = cat + (size_t)n * hw * 4 * c + c0;
+    for (int p = threadIdx.x; p < hw; p += 256) {
+        const VT v = *reinterpret_cast<const VT*>(src + (size_t)p * c);
+        cur[p] = v;
+        *reinterpret_cast<VT*>(dst + (size_t)p * 4 * c) = v;     // slice 0: y0 itself
+    }
+    __syncthreads();
+    for (int stage = 1; stage <= 3; ++stage) {
+        for (int p = threadIdx.x; p < hw; p += 256) {             // row max over x-2..x+2
+            const int y = p / w, x = p - y * w;
+            float m[CH];
+            const float* f = reinterpret_cast<const float*>(&cur[p]);
+#pragma unroll
+            for (int k = 0; k < CH; ++k) m[k] = f[k];
+#pragma unroll
+            for (int d = -2; d <= 2; ++d) {
+                if (d == 0 || x + d < 0 || x + d >= w) continue;
+                const float* g = reinterpret_cast<const float*>(&cur[p + d]);
+#pragma unroll
+                for (int k = 0; k < CH; ++k) m[k] = fmaxf(m[k], g[k]);
+            }
+            float* o = reinterpret_cast<float*>(&tmp[p]);
+#pragma unroll
+            for (int k = 0; k < CH; ++k) o[k] = m[k];
+        }
+        __syncthreads();
+        for (int p = threadIdx.x; p < hw; p += 256) {             // column max over y-2..y+2, write stage slice
+            const int y = p / w;
+            float m[CH];
+            const float* f = reinterpret_cast<const float*>(&tmp[p]);
+#pragma unroll
+            for (int k = 0; k < CH; ++k) m[k] = f[k];
+#pragma unroll
+            for (int d = -2; d <= 2; ++d) {
+                if (d == 0 || y + d < 0 || y + d >= h) continue;
+                const float* g = reinterpret_cast<const float*>(&tmp[p + d * w]);
+#pragma unroll
+                for (int k = 0; k < CH; ++k) m[k] = fmaxf(m[k], g[k]);
+            }
+            VT v;
+            float* o = reinterpret_cast<float*>(&v);
+#pragma unroll
+            for (int k = 0; k < CH; ++k) o[k] = m[k];
+            cur[p] = v;                                           // safe: this pass reads tmp only
+            *reinterpret_cast<VT*>(dst + (size_t)p * 4 * c + (size_t)stage * c) = v;
+        }
+        __syncthreads();
+    }
+}
+
 template <int V>
 int launch_bias_act(hvb_ctx* ctx, const EpiArgs& a, int act) {
     const uint32_t per_block = EPI_THREADS * EPI_UNROLL;
@@ -341,6 +408,33 @@ int hvb_concat_nhwc(hvb_ctx* ctx, const float* const src_dev[4], const int32_t s
     if (v == 4) concat_nhwc_kernel<4><<<grid, 256, 0, ctx->stream>>>(a);
     else if (v == 2) concat_nhwc_kernel<2><<<grid, 256, 0, ctx->stream>>>(a);
     else concat_nhwc_kernel<1><<<grid, 256, 0, ctx->stream>>>(a);
+    HVB_LAUNCHED(ctx);
+    return HVB_OK;
+}
+
+int hvb_sppf_pool_concat(hvb_ctx* ctx, const float* y0_dev, int n, int h, int w, int channels, float* out_cat_dev) {
+    HVB_CHECK_CTX(ctx);
+    HVB_ARG(y0_dev && out_cat_dev && n >= 0 && h > 0 && w > 0 && channels > 0, "bad arguments");
+    if (n == 0) return HVB_OK;
+    HVB_ARG(n <= 65535, "more than 65535 images");
+    HVB_ARG(channels % 4 == 0 && aligned_to(y0_dev, 16) && aligned_to(out_cat_dev, 16), "channels must be a multiple of 4 and buffers 16-byte aligned");
+    const size_t per_ch = (size_t)2 * h * w * sizeof(float);
+    if (per_ch * 4 > 200 * 1024) {
+        hvb_set_error("hvb_sppf_pool_concat: a %dx%d map does not fit shared memory; use MaxPool2d + hvb_concat_nhwc", h, w);
+        return HVB_ERR_UNSUPPORTED;
+    }
+    // 8-channel slices (32-byte sectors per pixel) when two tiles of them fit, 4-channel slices otherwise
+    // (ctx->max_smem_optin is not assumed: 200 KB is within every sm_100 part's 227 KB opt-in limit)
+    if (channels % 8 == 0 && per_ch * 8 <= 100 * 1024) {
+        const size_t sm = per_ch * 8;
+        if (sm > 48 * 1024) HVB_CUDA(cudaFuncSetAttribute(sppf_pool_concat_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));
+        // float8 is not a CUDA vector type: Vec<8> below
+        sppf_pool_concat_kernel<8><<<dim3(channels / 8, n), 256, sm, ctx->stream>>>(y0_dev, h, w, channels, out_cat_dev);
+    } else {
+        const size_t sm = per_ch * 4;
+        if (sm > 48 * 1024) HVB_CUDA(cudaFuncSetAttribute(sppf_pool_concat_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));
+        sppf_pool_concat_kernel<4><<<dim3(channels / 4, n), 256, sm, ctx->stream>>>(y0_dev, h, w, channels, out_cat_dev);
+    }
     HVB_LAUNCHED(ctx);
     return HVB_OK;
 }

@@ -104,10 +104,18 @@ class FusedYOLOv8:
         return self._cba(mod.cv2, cat, dest)
 
     def _sppf(self, mod: SPPF, x, dest=None):
-        y = [self._cba(mod.cv1, x)]
-        for _ in range(3):
-            y.append(mod.m(y[-1]))
-        return self._cba(mod.cv2, self._cat(y, [0, 0, 0, 0]), dest)
+        y0 = self._cba(mod.cv1, x)
+        n, c, h, w = y0.shape
+        k = mod.m.kernel_size if isinstance(mod.m.kernel_size, int) else mod.m.kernel_size[0]
+        if k == 5 and c % 4 == 0 and 2 * h * w * 16 <= 200 * 1024:
+            cat = self._buf(n, 4 * c, h, w)             # three cascaded 5x5 pools + concat in one on-chip pass
+            _ffi.check(self._lib.hvb_sppf_pool_concat(self._h, C.c_void_p(y0.data_ptr()), n, h, w, c, C.c_void_p(cat.data_ptr())))
+        else:
+            y = [y0]
+            for _ in range(3):
+                y.append(mod.m(y[-1]))
+            cat = self._cat(y, [0, 0, 0, 0])
+        return self._cba(mod.cv2, cat, dest)
 
     def _cat(self, srcs, shifts):
         n = srcs[0].shape[0]

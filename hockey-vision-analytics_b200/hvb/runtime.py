@@ -326,6 +326,17 @@ class Context:
             check(self.lib.hvb_concat_nhwc(self.handle, srcs, chans, shs, k, n, h, w, ptr(out)))
         return out
 
+    def sppf_pool_concat(self, y0: torch.Tensor, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+        """[y0, m(y0), m(m(y0)), m(m(m(y0)))] along channels, m = MaxPool2d(5, 1, 2); channels-last in and out."""
+        self._nhwc(y0)
+        n, c, h, w = y0.shape
+        with self.lock:
+            self._enter()
+            if out is None:
+                out = torch.empty((n, 4 * c, h, w), dtype=torch.float32, device=self.device, memory_format=torch.channels_last)
+            check(self.lib.hvb_sppf_pool_concat(self.handle, ptr(y0), n, h, w, c, ptr(out)))
+        return out
+
     def stem_conv(self, x_nchw: torch.Tensor, weight_host: np.ndarray, bias_host: Optional[np.ndarray]) -> torch.Tensor:
         """Layer 0 (3->C, 3x3, stride 2, pad 1) + bias + SiLU: NCHW float32 in, channels-last out."""
         n, ci, h, w = x_nchw.shape

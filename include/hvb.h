@@ -295,6 +295,10 @@ HVB_API int hvb_bias_act(hvb_ctx* ctx, const float* x_dev, const float* bias_dev
                  int out2_up2_h, int out2_up2_w);
 HVB_API int hvb_concat_nhwc(hvb_ctx* ctx, const float* const src_dev[4], const int32_t src_channels[4],
                     const int32_t src_shift[4], int n_src, int n, int h, int w, float* out_dev);
+/* SPPF.forward's pooling + concat (ultralytics nn/modules/block.py): out[n,y,x,:] = [y0, m(y0), m(m(y0)), m(m(m(y0)))]
+ * with m = MaxPool2d(5, stride 1, pad 2), computed on chip from one read of y0.  y0: [n,h,w,channels] NHWC,
+ * out: [n,h,w,4*channels].  HVB_ERR_UNSUPPORTED when an h x w map does not fit shared memory (h*w > ~6400). */
+HVB_API int hvb_sppf_pool_concat(hvb_ctx* ctx, const float* y0_dev, int n, int h, int w, int channels, float* out_cat_dev);
 HVB_API int hvb_stem_conv(hvb_ctx* ctx, const float* in_nchw_dev, const float* weight_host, const float* bias_host,
                   int n, int h, int w, int c_out, float* out_nhwc_dev);
 

@@ -122,6 +122,17 @@ def test_concat_upsample(ctx, shifts, chans):
     assert torch.equal(out.cpu(), ref)                            # pure data movement: bit-exact
 
 
+@pytest.mark.parametrize("c,hw", [(288, (23, 40)), (128, (20, 20)), (12, (4, 20)), (8, (1, 3)), (64, (50, 60))])
+def test_sppf_pool_concat(ctx, c, hw):
+    g = torch.Generator().manual_seed(c)
+    y0 = torch.randn(3, c, *hw, generator=g)
+    m = torch.nn.MaxPool2d(5, 1, 2)
+    y1 = m(y0); y2 = m(y1); y3 = m(y2)
+    out = ctx.sppf_pool_concat(nhwc(y0))
+    assert out.is_contiguous(memory_format=CL)
+    assert torch.equal(out.cpu(), torch.cat([y0, y1, y2, y3], 1))       # max is exact: bit-identical
+
+
 @pytest.mark.parametrize("co,hw", [(16, (64, 96)), (48, (96, 160)), (48, (33, 271)), (32, (32, 32)), (64, (64, 130))])
 def test_stem_conv(ctx, no_tf32, co, hw):
     g = torch.Generator().manual_seed(co)
