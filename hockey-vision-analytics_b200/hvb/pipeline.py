@@ -176,8 +176,9 @@ class SlicedPuckPath:
         self.slicer = B200InferenceSlicer(detector=self.detector, slice_wh=(640, 640), overlap_ratio_wh=(0.2, 0.2),
                                           iou_threshold=iou_threshold, tile_imgsz=640, uniform_tiles=uniform_tiles)
 
-    def process_chunk_device(self, frames_dev: torch.Tensor):
-        return self.slicer.run_device(frames_dev)
+    def process_chunk_device(self, frames_dev: torch.Tensor, sync: bool = False):
+        """Device-resident chunk: no host round trip unless sync=True (exact-size outputs + overflow retry)."""
+        return self.slicer.run_device(frames_dev, sync=sync)
 
     def process_chunk(self, frames: np.ndarray):
         return self.slicer.run_batch(frames)

@@ -90,8 +90,13 @@ class B200InferenceSlicer:
         return merged[keep]
 
     # ------------------------------------------------------------------ device path
-    def run_device(self, frames_dev: torch.Tensor):
-        """frames_dev uint8[n,H,W,3] -> (xyxy f64[total,4], conf f32, cls i32, keep u8, seg i32[n+1]) on device."""
+    def run_device(self, frames_dev: torch.Tensor, sync: bool = True):
+        """frames_dev uint8[n,H,W,3] -> (xyxy f64[total,4], conf f32, cls i32, keep u8, seg i32[n+1]) on device.
+
+        sync=True: one small D2H of the per-tile counts sizes the outputs exactly and triggers the large-capacity
+        retry for tiles with more than 1024 candidates.  sync=False: nothing is read back — outputs have the full
+        capacity n_tiles*max_det rows, only rows [0, seg[-1]) are meaningful, and the per-tile counts are returned
+        as a sixth element so the caller can check for overflow (-1) when it reads the results."""
         det = self.detector
         ctx = det.ctx
         n, h, w, _ = frames_dev.shape
@@ -108,28 +113,38 @@ class B200InferenceSlicer:
             *_, state = det._decode(heads, meta_h, meta_d, n_slots, out=out)
             states.append(state)
         xyxy, cf, cl, cnt = out
-        # overflow (> 1024 candidates in a tile) is rare: one small D2H of the counts decides
-        cnt_h = cnt.cpu().numpy()
-        if (cnt_h < 0).any():
-            for state in states:
-                cnt_h = det._retry_overflow(xyxy, cf, cl, cnt, state, cnt_h)
         key = ("slot_off", id(plan))
         if key not in det._meta:
             det._meta[key] = ctx.to_device(plan.slot_offsets())
+        if sync:
+            # overflow (> 1024 candidates in a tile) is rare: one small D2H of the counts decides
+            cnt_h = cnt.cpu().numpy()
+            if (cnt_h < 0).any():
+                for state in states:
+                    cnt_h = det._retry_overflow(xyxy, cf, cl, cnt, state, cnt_h)
+            total = int(np.maximum(cnt_h, 0).sum())
+        else:
+            total = n_slots * det.max_det
         g_xyxy, g_conf, g_cls, g_slot, seg = ctx.gather_tiles(xyxy, cf, cl, cnt, det._meta[key], plan.tiles_per_frame, det.max_det)
-        total = int(np.maximum(cnt_h, 0).sum())
         if self.overlap_filter == OverlapFilter.NONE or total == 0:
             keep = torch.ones((total,), dtype=torch.uint8, device=ctx.device)
         else:
             keep = ctx.merge_nms(g_xyxy, g_conf, None if self.class_agnostic else g_cls, seg, n, total, self.iou_threshold,
                                  self.class_agnostic)
-        return g_xyxy[:total], g_conf[:total], g_cls[:total], keep, seg
+        if sync:
+            return g_xyxy[:total], g_conf[:total], g_cls[:total], keep, seg
+        return g_xyxy, g_conf, g_cls, keep, seg, cnt
 
     def run_batch(self, frames) -> List[Detections]:
         det = self.detector
         frames_dev = det.upload(frames)
-        xyxy, conf, cls, keep, seg = self.run_device(frames_dev)
-        xyxy_h, conf_h, cls_h, keep_h, seg_h = (t.cpu().numpy() for t in (xyxy, conf, cls, keep, seg))
+        xyxy, conf, cls, keep, seg, cnt = self.run_device(frames_dev, sync=False)      # no host round trip mid-pipeline
+        seg_h, cnt_h = seg.cpu().numpy(), cnt.cpu().numpy()
+        if (cnt_h < 0).any():                       # a tile overflowed the 1024-candidate tier: redo with the retry path
+            xyxy, conf, cls, keep, seg = self.run_device(frames_dev, sync=True)
+            seg_h = seg.cpu().numpy()
+        total = int(seg_h[-1])
+        xyxy_h, conf_h, cls_h, keep_h = (t[:total].cpu().numpy() for t in (xyxy, conf, cls, keep))
         if (keep_h == 0xFF).any():
             raise _ffi.HvbError(_ffi.HVB_ERR_CAPACITY, "merged detections of one frame exceed the on-chip NMS capacity")
         out = []

@@ -131,6 +131,13 @@ def test_slicer_device_path_matches_restated_inference_slicer(ctx):
     det = Detector(model, "cuda:0", imgsz=640, conf=0.4)
     slicer = B200InferenceSlicer(detector=det, slice_wh=(640, 640), overlap_ratio_wh=(0.2, 0.2), iou_threshold=0.1)
     got = slicer.run_batch(frames)
+    # the sync-free device path (full-capacity outputs, no host round trip) agrees with the exact-size one
+    fd = torch.from_numpy(frames).cuda()
+    a, b = slicer.run_device(fd, sync=True), slicer.run_device(fd, sync=False)
+    tot = int(a[4][-1])
+    assert int(b[4][-1]) == tot and torch.equal(a[4], b[4]) and int(b[5].min()) >= 0
+    for x, y in zip(a[:4], b[:4]):
+        assert torch.equal(x[:tot], y[:tot])
 
     def callback(tile):
         lb = ur.letterbox(np.ascontiguousarray(tile), 640, auto=True)
