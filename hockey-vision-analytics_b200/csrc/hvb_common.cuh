@@ -32,6 +32,9 @@ struct hvb_ctx {
     // K2a split-scan work area: device counters (kept zero between launches) + per-image candidate key lists
     void* k2_work_dev = nullptr;
     size_t k2_work_bytes = 0, k2_ctr_bytes = 0;
+    // CUDA-graph support: once set, work buffers replaced by growth are kept alive (captured graphs may point at them)
+    bool retain_buffers = false;
+    std::vector<void*> retired;
 };
 
 void hvb_set_error(const char* fmt, ...);
@@ -40,6 +43,7 @@ int hvb_scratch(hvb_ctx* ctx, size_t bytes, void** out);     // device scratch #
 int hvb_scratch2(hvb_ctx* ctx, size_t bytes, void** out);    // device scratch #2 (grow-only)
 int hvb_scratch3(hvb_ctx* ctx, size_t bytes, void** out);    // device scratch #3 (grow-only)
 int hvb_pinned(hvb_ctx* ctx, size_t bytes, void** out);      // pinned host staging (grow-only)
+int hvb_capturing(hvb_ctx* ctx, const char* what);           // HVB_ERR_UNSUPPORTED (with message) if ctx->stream is being captured
 
 #define HVB_CUDA(call)                                                            \
     do {                                                                          \

@@ -21,12 +21,28 @@ int hvb_cuda_fail(cudaError_t e, const char* what, const char* file, int line) {
     return (e == cudaErrorNoDevice || e == cudaErrorInsufficientDriver) ? HVB_ERR_NO_DEVICE : HVB_ERR_CUDA;
 }
 
-static int grow(void** buf, size_t* have, size_t want, bool pinned) {
+int hvb_capturing(hvb_ctx* ctx, const char* what) {
+    cudaStreamCaptureStatus st = cudaStreamCaptureStatusNone;
+    if (cudaStreamIsCapturing(ctx->stream, &st) == cudaSuccess && st != cudaStreamCaptureStatusNone) {
+        hvb_set_error("%s needs to (re)allocate a work buffer while the stream is being captured into a CUDA graph: "
+                      "run the same step once eagerly before capturing", what);
+        return HVB_ERR_UNSUPPORTED;
+    }
+    (void)cudaGetLastError();
+    return HVB_OK;
+}
+
+static int grow(hvb_ctx* ctx, void** buf, size_t* have, size_t want, bool pinned) {
     if (*have >= want && *buf) return HVB_OK;
+    HVB_TRY(hvb_capturing(ctx, "libhvb scratch"));
     size_t n = want + want / 4 + 4096;
     if (*buf) {
-        HVB_CUDA(cudaDeviceSynchronize());
-        if (pinned) HVB_CUDA(cudaFreeHost(*buf)); else HVB_CUDA(cudaFree(*buf));
+        if (ctx->retain_buffers && !pinned) {
+            ctx->retired.push_back(*buf);            // a captured CUDA graph may still point at it
+        } else {
+            HVB_CUDA(cudaDeviceSynchronize());
+            if (pinned) HVB_CUDA(cudaFreeHost(*buf)); else HVB_CUDA(cudaFree(*buf));
+        }
         *buf = nullptr;
         *have = 0;
     }
@@ -36,22 +52,22 @@ static int grow(void** buf, size_t* have, size_t want, bool pinned) {
 }
 
 int hvb_scratch(hvb_ctx* ctx, size_t bytes, void** out) {
-    HVB_TRY(grow(&ctx->scratch_dev, &ctx->scratch_bytes, bytes, false));
+    HVB_TRY(grow(ctx, &ctx->scratch_dev, &ctx->scratch_bytes, bytes, false));
     *out = ctx->scratch_dev;
     return HVB_OK;
 }
 int hvb_scratch2(hvb_ctx* ctx, size_t bytes, void** out) {
-    HVB_TRY(grow(&ctx->scratch2_dev, &ctx->scratch2_bytes, bytes, false));
+    HVB_TRY(grow(ctx, &ctx->scratch2_dev, &ctx->scratch2_bytes, bytes, false));
     *out = ctx->scratch2_dev;
     return HVB_OK;
 }
 int hvb_scratch3(hvb_ctx* ctx, size_t bytes, void** out) {
-    HVB_TRY(grow(&ctx->scratch3_dev, &ctx->scratch3_bytes, bytes, false));
+    HVB_TRY(grow(ctx, &ctx->scratch3_dev, &ctx->scratch3_bytes, bytes, false));
     *out = ctx->scratch3_dev;
     return HVB_OK;
 }
 int hvb_pinned(hvb_ctx* ctx, size_t bytes, void** out) {
-    HVB_TRY(grow(&ctx->pinned, &ctx->pinned_bytes, bytes, true));
+    HVB_TRY(grow(ctx, &ctx->pinned, &ctx->pinned_bytes, bytes, true));
     *out = ctx->pinned;
     return HVB_OK;
 }
@@ -116,6 +132,12 @@ int hvb_ctx_create(int device, hvb_ctx** out_ctx) {
     return HVB_OK;
 }
 
+int hvb_ctx_retain_buffers(hvb_ctx* ctx, int on) {
+    if (!ctx) { hvb_set_error("null context"); return HVB_ERR_ARG; }
+    ctx->retain_buffers = on != 0;
+    return HVB_OK;
+}
+
 int hvb_ctx_destroy(hvb_ctx* ctx) {
     if (!ctx) return HVB_OK;
     cudaSetDevice(ctx->device);
@@ -125,6 +147,7 @@ int hvb_ctx_destroy(hvb_ctx* ctx) {
     if (ctx->scratch2_dev) cudaFree(ctx->scratch2_dev);
     if (ctx->scratch3_dev) cudaFree(ctx->scratch3_dev);
     if (ctx->k2_work_dev) cudaFree(ctx->k2_work_dev);
+    for (void* p : ctx->retired) cudaFree(p);
     if (ctx->pinned) cudaFreeHost(ctx->pinned);
     if (ctx->ev_start) cudaEventDestroy(ctx->ev_start);
     if (ctx->ev_stop) cudaEventDestroy(ctx->ev_stop);

@@ -382,8 +382,12 @@ int k2_work(hvb_ctx* ctx, int images, int cap, unsigned long long** keys, int32_
     const size_t key_bytes = (size_t)images * cap * sizeof(unsigned long long);
     if (ctr_bytes > ctx->k2_ctr_bytes || key_bytes > ctx->k2_work_bytes - ctx->k2_ctr_bytes) {
         // the stream may still be using the old buffer: drain it before replacing (rare: only on growth)
+        HVB_TRY(hvb_capturing(ctx, "hvb_decode_nms"));
         HVB_CUDA(cudaStreamSynchronize(ctx->stream));
-        if (ctx->k2_work_dev) HVB_CUDA(cudaFree(ctx->k2_work_dev));
+        if (ctx->k2_work_dev) {
+            if (ctx->retain_buffers) ctx->retired.push_back(ctx->k2_work_dev);
+            else HVB_CUDA(cudaFree(ctx->k2_work_dev));
+        }
         ctx->k2_work_dev = nullptr; ctx->k2_work_bytes = 0; ctx->k2_ctr_bytes = 0;
         const size_t ctr_cap = ctr_bytes * 2, total = ctr_cap + key_bytes * 2;
         HVB_CUDA(cudaMalloc(&ctx->k2_work_dev, total));

@@ -56,6 +56,7 @@ PROTOTYPES = {
     "hvb_ctx_use_own_stream": [_vp],
     "hvb_ctx_get_stream": [_vp, _pp],
     "hvb_ctx_synchronize": [_vp],
+    "hvb_ctx_retain_buffers": [_vp, _i],
     "hvb_ctx_sm_count": [_vp, C.POINTER(_i)],
     "hvb_malloc": [_vp, _sz, _pp],
     "hvb_free": [_vp, _vp],

@@ -175,10 +175,19 @@ class SlicedPuckPath:
                                  fuse=fuse, channels_last=channels_last, autocast_dtype=autocast_dtype)
         self.slicer = B200InferenceSlicer(detector=self.detector, slice_wh=(640, 640), overlap_ratio_wh=(0.2, 0.2),
                                           iou_threshold=iou_threshold, tile_imgsz=640, uniform_tiles=uniform_tiles)
+        self._graphs = {}
 
-    def process_chunk_device(self, frames_dev: torch.Tensor, sync: bool = False):
-        """Device-resident chunk: no host round trip unless sync=True (exact-size outputs + overflow retry)."""
-        return self.slicer.run_device(frames_dev, sync=sync)
+    def process_chunk_device(self, frames_dev: torch.Tensor, sync: bool = False, graph: bool = False):
+        """Device-resident chunk: no host round trip unless sync=True (exact-size outputs + overflow retry).
+        graph=True replays the whole chunk (K1b, every shape-class forward, K2a, gather, K2b: ~900 launches) as ONE
+        CUDA graph captured on first use for this chunk shape — the sliced path is launch-bound otherwise."""
+        if not graph or sync:
+            return self.slicer.run_device(frames_dev, sync=sync)
+        key = tuple(frames_dev.shape)
+        if key not in self._graphs:
+            from .runtime import GraphedStep
+            self._graphs[key] = GraphedStep(self.detector.ctx, lambda f: self.slicer.run_device(f, sync=False), [frames_dev])
+        return self._graphs[key](frames_dev)
 
     def process_chunk(self, frames: np.ndarray):
         return self.slicer.run_batch(frames)

@@ -61,6 +61,10 @@ class Context:
             self._enter()
             check(self.lib.hvb_ctx_synchronize(self.handle))
 
+    def retain_buffers(self, on: bool = True) -> None:
+        """Keep work buffers alive across growth (call before capturing libhvb launches into a CUDA graph)."""
+        check(self.lib.hvb_ctx_retain_buffers(self.handle, 1 if on else 0))
+
     def launch_count(self, reset: bool = False) -> int:
         n = C.c_uint64()
         check(self.lib.hvb_ctx_launch_count(self.handle, 1 if reset else 0, C.byref(n)))
@@ -492,3 +496,43 @@ class LetterboxPlan:
     def slot_offsets(self) -> np.ndarray:
         """float32[n_slots, 2] tile offsets in slot order (frame-major, slicer tile order)."""
         return np.stack([self.tiles["src_x"], self.tiles["src_y"]], 1).astype(np.float32)
+
+
+class GraphedStep:
+    """A fixed-shape device step captured once into a CUDA graph and replayed.
+
+    The hot path of one chunk is several hundred launches (library convolutions + libhvb kernels); for the small
+    batches of the sliced path the host cannot issue them as fast as the GPU retires them.  `fn(*tensors)` must be
+    free of host synchronisation and must only depend on its tensor arguments' CONTENTS (shapes fixed).  The step is
+    run eagerly first (cuDNN autotuning, libhvb plan / work-buffer allocation), then captured; later calls copy the
+    inputs into the captured input buffers (unless the very same tensors are passed) and replay.  The returned
+    tensors are the graph's static outputs: consume them before the next call."""
+
+    def __init__(self, ctx: Context, fn, example_inputs: Sequence[torch.Tensor], warmup: int = 2):
+        self.ctx, self.fn = ctx, fn
+        self.static_in = list(example_inputs)
+        self._launches = 0
+        ctx.retain_buffers(True)
+        side = torch.cuda.Stream(device=ctx.device)
+        side.wait_stream(torch.cuda.current_stream(ctx.device))
+        with torch.cuda.stream(side):
+            for _ in range(warmup):
+                fn(*self.static_in)
+        torch.cuda.current_stream(ctx.device).wait_stream(side)
+        torch.cuda.synchronize(ctx.device)
+        before = ctx.launch_count()
+        self.graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(self.graph):
+            self.static_out = fn(*self.static_in)
+        self._launches = ctx.launch_count() - before      # libhvb kernels inside one replay
+
+    @property
+    def launches_per_replay(self) -> int:
+        return self._launches
+
+    def __call__(self, *inputs: torch.Tensor):
+        for dst, src in zip(self.static_in, inputs):
+            if dst.data_ptr() != src.data_ptr():
+                dst.copy_(src, non_blocking=True)
+        self.graph.replay()
+        return self.static_out

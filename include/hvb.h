@@ -59,6 +59,12 @@ HVB_API int hvb_ctx_set_stream(hvb_ctx* ctx, void* cuda_stream);    /* cudaStrea
 HVB_API int hvb_ctx_use_own_stream(hvb_ctx* ctx);                   /* back to the context's private non-blocking stream (the initial state) */
 HVB_API int hvb_ctx_get_stream(hvb_ctx* ctx, void** out_stream);
 HVB_API int hvb_ctx_synchronize(hvb_ctx* ctx);
+/* CUDA-graph support.  libhvb launches may be captured into a CUDA graph (bind the capturing stream with
+ * hvb_ctx_set_stream).  Call this with on=1 BEFORE capturing: from then on a work buffer that has to grow is
+ * replaced without freeing the old one, so pointers baked into captured graphs stay valid until hvb_ctx_destroy.
+ * A call that would have to (re)allocate while its stream is being captured fails with HVB_ERR_UNSUPPORTED —
+ * run the step once eagerly first. */
+HVB_API int hvb_ctx_retain_buffers(hvb_ctx* ctx, int on);
 HVB_API int hvb_ctx_sm_count(hvb_ctx* ctx, int* out_sms);
 HVB_API int hvb_malloc(hvb_ctx* ctx, size_t bytes, void** out_dev);
 HVB_API int hvb_free(hvb_ctx* ctx, void* ptr_dev);

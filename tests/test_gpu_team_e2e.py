@@ -203,3 +203,28 @@ def test_pipelined_stream_equals_chunk_api(ctx):
     for a, b in zip(ref, got):
         assert np.array_equal(a["team"], b["team"]) and np.array_equal(a["count"], b["count"])
         assert len(a["team"]) == 12
+
+
+def test_sliced_path_cuda_graph_replay_equals_eager(ctx):
+    """SlicedPuckPath.process_chunk_device(graph=True): the whole chunk (K1b, per-shape-class YOLOv8n forwards with
+    the K5 glue, K2a, gather, K2b) captured once and replayed gives what the eager launches give, also on new frames."""
+    from hvb.pipeline import SlicedPuckPath
+    from hvb.synth import rink_frame
+    rng = np.random.default_rng(11)
+    path = SlicedPuckPath("cuda:0", "n", 1, conf=5e-3, seed=2)            # random-init: low conf so that boxes come out
+    f1 = torch.from_numpy(np.stack([rink_frame(rng, 720, 1280, 8)[0] for _ in range(2)])).cuda()
+    f2 = torch.from_numpy(np.stack([rink_frame(rng, 720, 1280, 8)[0] for _ in range(2)])).cuda()
+    eager1 = [t.clone() for t in path.process_chunk_device(f1)]
+    eager2 = [t.clone() for t in path.process_chunk_device(f2)]
+    before = ctx.launch_count()
+    g1 = [t.clone() for t in path.process_chunk_device(f1, graph=True)]   # captures
+    captured = ctx.launch_count() - before
+    g2 = [t.clone() for t in path.process_chunk_device(f2, graph=True)]   # replays with other frames
+    assert ctx.launch_count() - before == captured                         # the replay issued no eager libhvb launch
+    for e, g in ((eager1, g1), (eager2, g2)):
+        tot = int(e[4][-1])
+        assert tot > 0 and int(g[4][-1]) == tot
+        assert torch.equal(e[4], g[4]) and torch.equal(e[5], g[5])
+        for a, b in zip(e[:4], g[:4]):
+            assert torch.equal(a[:tot], b[:tot])
+    assert not torch.equal(eager1[0][: int(eager1[4][-1])], eager2[0][: int(eager1[4][-1])]) or int(eager1[4][-1]) != int(eager2[4][-1])
