@@ -132,7 +132,7 @@ letterbox_kernel(const uint8_t* __restrict__ frames, int64_t frame_bytes, int32_
             const float inv16 = 1.0f / (float)n16;
             for (int it0 = threadIdx.x; it0 < n_items16; it0 += 3 * kThreads) {
                 uint4 q[3][3];
-                int soff[3];
+                int soff[3], fsw[3];
                 bool live[3];
 #pragma unroll
                 for (int k = 0; k < 3; k++) {
@@ -143,6 +143,7 @@ letterbox_kernel(const uint8_t* __restrict__ frames, int64_t frame_bytes, int32_
                     if (g < 0) { r--; g += n16; }
                     if (g >= n16) { r++; g -= n16; }
                     soff[k] = r * smem_row_words + 16 * g;
+                    fsw[k] = (g >> 1) & 3;             // bank swizzle of the 16-byte chunk inside its 16-word group
                     if (live[k]) {
                         const uint4* p128 = reinterpret_cast<const uint4*>(src + r * pitch + g * 48);
                         q[k][0] = __ldg(p128); q[k][1] = __ldg(p128 + 1); q[k][2] = __ldg(p128 + 2);
@@ -161,7 +162,7 @@ letterbox_kernel(const uint8_t* __restrict__ frames, int64_t frame_bytes, int32_
                         o.y = __byte_perm(a, b, 0x0543) & 0x00ffffffu;
                         o.z = __byte_perm(b, c, 0x0432) & 0x00ffffffu;
                         o.w = c >> 8;
-                        *reinterpret_cast<uint4*>(spix + soff[k] + 4 * t) = o;
+                        *reinterpret_cast<uint4*>(spix + soff[k] + 4 * (t ^ fsw[k])) = o;
                     }
                 }
             }
@@ -185,7 +186,7 @@ letterbox_kernel(const uint8_t* __restrict__ frames, int64_t frame_bytes, int32_
                 if (g < 0) { r--; g += n_groups; }
                 if (g >= n_groups) { r++; g -= n_groups; }
                 poff[k] = r * pitch + g * 12;
-                soff[k] = r * smem_row_words + 4 * g;
+                soff[k] = r * smem_row_words + 4 * (g ^ ((g >> 3) & 3));      // same swizzle as the 16-pixel path
                 g4[k] = 4 * g;
                 fast[k] = live[k] && vec_ok && 4 * g + 4 <= row_px;
                 a[k] = b[k] = c[k] = 0;
@@ -269,8 +270,10 @@ letterbox_kernel(const uint8_t* __restrict__ frames, int64_t frame_bytes, int32_
     o += ja * out_w;
 
     // raw shared-memory byte addresses of the two taps of this column (row offsets are added per row)
-    const uint32_t a0 = (uint32_t)__cvta_generic_to_shared(spix) + 4u * (uint32_t)i0;
-    const uint32_t a1 = (uint32_t)__cvta_generic_to_shared(spix) + 4u * (uint32_t)i1;
+    // staged rows are stored with their 16-byte chunks XOR-swizzled inside each 16-word group (chunk ^= (word >> 5) & 3)
+    // so that the 64-byte-strided 128-bit staging stores of a quarter-warp fall into distinct banks
+    const uint32_t a0 = (uint32_t)__cvta_generic_to_shared(spix) + 4u * ((uint32_t)i0 ^ ((((uint32_t)i0 >> 5) & 3u) << 2));
+    const uint32_t a1 = (uint32_t)__cvta_generic_to_shared(spix) + 4u * ((uint32_t)i1 ^ ((((uint32_t)i1 >> 5) & 3u) << 2));
     float* q0 = U8OUT ? nullptr : tile_f32 + o;             // R plane, then +plane, +2*plane
     float* q1 = U8OUT ? nullptr : q0 + plane;
     float* q2 = U8OUT ? nullptr : q1 + plane;
@@ -303,12 +306,20 @@ letterbox_kernel(const uint8_t* __restrict__ frames, int64_t frame_bytes, int32_
             emit((br >> 2) & 255, gg >> 2, (br >> 18) & 255);
         }
     } else {
+        uint32_t ph[3] = {0u, 0u, 0u};
+        int prev_r1 = -1;
 #pragma unroll 4
         for (int j = ja; j < jb; j++) {
             const YCoef yc = s_y[j];
             uint32_t h0[3], h1[3];
-            lb_hrow(lds32(a0 + yc.r0), lds32(a1 + yc.r0), apk, h0);
+            if (yc.r0 == prev_r1) {                       // warp-uniform: the upper source row is the previous row's lower one
+                h0[0] = ph[0]; h0[1] = ph[1]; h0[2] = ph[2];
+            } else {
+                lb_hrow(lds32(a0 + yc.r0), lds32(a1 + yc.r0), apk, h0);
+            }
             lb_hrow(lds32(a0 + yc.r1), lds32(a1 + yc.r1), apk, h1);
+            ph[0] = h1[0]; ph[1] = h1[1]; ph[2] = h1[2];
+            prev_r1 = yc.r1;
             const uint32_t b0 = (uint32_t)yc.b0, b1 = (uint32_t)yc.b1;     // coefficients << 16
             // OpenCV vertical pass: ((b0*(H0>>4))>>16) + ((b1*(H1>>4))>>16) + 2 >> 2, as two mad.hi per channel
 #if HVB_K1_MADHI
@@ -557,7 +568,7 @@ int hvb_lb_plan_create(hvb_ctx* ctx, int n_frames, int frame_h, int frame_w, int
         }
         p->resize_heavy = 2 * px_resize > px_all;
     }
-    p->smem_row_stride = max_span + 4;                                 // pixel words per staged row (whole 4-pixel groups)
+    p->smem_row_stride = (max_span + 15) & ~15;                        // pixel words per staged row: whole 16-word groups (the bank swizzle permutes chunks inside a group)
     p->smem_bytes = p->smem_row_stride * max_rows * 4;
     if (p->smem_bytes > ctx->max_smem_optin - 1024) {
         delete p;

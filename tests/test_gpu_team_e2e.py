@@ -227,4 +227,3 @@ def test_sliced_path_cuda_graph_replay_equals_eager(ctx):
         assert torch.equal(e[4], g[4]) and torch.equal(e[5], g[5])
         for a, b in zip(e[:4], g[:4]):
             assert torch.equal(a[:tot], b[:tot])
-    assert not torch.equal(eager1[0][: int(eager1[4][-1])], eager2[0][: int(eager1[4][-1])]) or int(eager1[4][-1]) != int(eager2[4][-1])
