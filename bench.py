@@ -222,21 +222,21 @@ def run_hvb(args, rank, world):
             dist.barrier()
         torch.cuda.synchronize()
 
-    def timed(fn, steps, warmup, sampler=None):
+    def timed(fn, steps, warmup, sampler=None, profile=False):
         for _ in range(warmup):
             fn()
         barrier()
         if sampler:
             sampler.start()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        if sampler and args.profile_region:
+        if profile:
             torch.cuda.profiler.start()          # ncu --profile-from-start off: only the timed steps are captured
         e0.record()
         for _ in range(steps):
             fn()
         e1.record()
         barrier()
-        if sampler and args.profile_region:
+        if profile:
             torch.cuda.profiler.stop()
         ms = e0.elapsed_time(e1)
         clocks = sampler.stop() if sampler else None
@@ -254,7 +254,7 @@ def run_hvb(args, rank, world):
 
     ctx.launch_count(reset=True)
     sampler = ClockSampler(local) if rank == 0 else None
-    ms_dev, clocks = timed(step_device, args.steps, args.warmup, sampler)
+    ms_dev, clocks = timed(step_device, args.steps, args.warmup, sampler, profile=args.profile_region and not args.profile_4k)
     launches = ctx.launch_count() // (args.steps + args.warmup) * args.steps
     fps_dev = world * F * args.steps / (ms_dev / 1e3)
 
@@ -311,7 +311,8 @@ def run_hvb(args, rank, world):
         f4 = np.stack([rink_frame(rng, 2160, 3840, PLAYERS, 2.0)[0] for _ in range(F4)])
         f4_dev = torch.from_numpy(f4).to(dev)
         puck = SlicedPuckPath(dev, "n", 1, 0.4)
-        ms4_eager, _ = timed(lambda: puck.process_chunk_device(f4_dev), max(2, args.steps // 2), 2)
+        ms4_eager, _ = timed(lambda: puck.process_chunk_device(f4_dev), max(2, args.steps // 2), 2,
+                             profile=args.profile_region and args.profile_4k)
         # the sliced path is launch-bound (≈900 launches per chunk over 5 tile shape classes): replay it as one CUDA graph
         ms4, _ = timed(lambda: puck.process_chunk_device(f4_dev, graph=True), max(2, args.steps // 2), 2)
         plan4 = puck.detector.plan(F4, 2160, 3840, _ffi.LB_SLICE_EXACT, 640, (640, 640), (128, 128))
@@ -386,6 +387,7 @@ def main():
     ap.add_argument("--ref-frames", type=int, default=2, help="frames per CPU-reference step (bounded sample)")
     ap.add_argument("--no-4k", dest="with_4k", action="store_false")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--profile-4k", action="store_true", help="with --profile-region: bracket the eager 4K sliced steps instead of the 1080p steps")
     ap.add_argument("--profile-region", action="store_true", help="cudaProfilerStart/Stop around the timed device steps (for ncu --profile-from-start off)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "hvb" else args.warmup

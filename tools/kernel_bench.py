@@ -170,6 +170,10 @@ def main():
         out = ctx.concat_nhwc([p5, p4], [1, 0])
         report("K5 upsample2x+concat x%d (576@23x40, 384@46x80)" % nb, timed(lambda: ctx.concat_nhwc([p5, p4], [1, 0], out=out), R),
                p5.numel() * 4 + p4.numel() * 4 + out.numel() * 4)
+        y0 = torch.randn(nb, 288, 23, 40, device="cuda").contiguous(memory_format=CL)
+        cat4 = ctx.sppf_pool_concat(y0)
+        report("K5 SPPF 3x maxpool5 + concat x%d 288ch 23x40" % nb, timed(lambda: ctx.sppf_pool_concat(y0, out=cat4), R),
+               y0.numel() * 4 * 5)
         xin = torch.rand(nb, 3, 736, 1280, device="cuda")
         wst = (np.random.default_rng(0).standard_normal((48, 3, 3, 3)) * 0.2).astype(np.float32)
         bst = np.zeros((48,), np.float32)
