@@ -45,8 +45,8 @@ def build(handle, n, cin, cout, h, w, k, stride, x_ld, y_ld, residual, act=True)
     B = g.tensor(name="B", dim=[1, cout, 1, 1], stride=[cout, 1, cout, cout], data_type=F32)
     y = g.conv_fprop(image=X, weight=W, padding=[pad, pad], stride=[stride, stride], dilation=[1, 1], compute_data_type=F32)
     y = g.bias(input=y, bias=B)
-    if act:
-        y = g.swish(input=y)
+    if act:                                # SiLU as sigmoid * x (the swish() binding of frontend 1.18 has its defaults mixed up)
+        y = g.mul(a=y, b=g.sigmoid(input=y))
     R = None
     if residual:
         R = g.tensor(name="R", dim=[n, cout, oh, ow], stride=nhwc_strides(cout, oh, ow), data_type=F32)
