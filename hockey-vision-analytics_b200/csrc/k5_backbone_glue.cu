@@ -172,7 +172,10 @@ __device__ __forceinline__ float silu_fast(float v) {
 // Input NCHW (what K1 writes), zero padding 1.  Weights arrive as kernel parameters, i.e. in the
 // constant bank: with the loops fully unrolled every FFMA takes its weight as a c[0][..] operand, so
 // the inner loop is 27 shared-memory loads + 27*CO FFMAs per pixel and no weight traffic at all.
-constexpr int STEM_PX = 128;                 // output pixels (one row segment) per block = threads per block
+#ifndef HVB_STEM_PX
+#define HVB_STEM_PX 128
+#endif
+constexpr int STEM_PX = HVB_STEM_PX;         // output pixels (one row segment) per block = threads per block
 template <int CO> struct StemParams { float w[27 * CO]; float b[CO]; };   // w index: ((ci*3+ky)*3+kx)*CO + co
 
 template <int CO>

@@ -180,6 +180,14 @@ def main():
         ms = timed(lambda: ctx.stem_conv(xin, wst, bst), R)
         report("K5 stem conv 3->48 s2 + SiLU x%d 736x1280" % nb, ms, xin.numel() * 4 + nb * 48 * 368 * 640 * 4,
                flops=2 * 27 * 48 * nb * 368 * 640)
+        del xin
+        nt = 112                                                   # 4 x 4K frames: the 640x640 tile class of the sliced path
+        xt = torch.rand(nt, 3, 640, 640, device="cuda")
+        w16 = (np.random.default_rng(1).standard_normal((16, 3, 3, 3)) * 0.2).astype(np.float32)
+        b16 = np.zeros((16,), np.float32)
+        ms = timed(lambda: ctx.stem_conv(xt, w16, b16), R)
+        report("K5 stem conv 3->16 s2 + SiLU x%d tiles 640x640 (YOLOv8n)" % nt, ms, xt.numel() * 4 + nt * 16 * 320 * 320 * 4,
+               flops=2 * 27 * 16 * nt * 320 * 320)
 
     if want('k1'):
         sec_k1()
