@@ -25,9 +25,14 @@ from .slicer import B200InferenceSlicer
 class HotPath:
     def __init__(self, device="cuda:0", yolo_scale: str = "m", nc: int = 2, imgsz: int = 1280, conf: float = 0.4,
                  seed: int = 0, trunk: Optional[torch.nn.Module] = None, affinity_mode: int = 0, fuse: bool = True,
-                 channels_last: bool = True, autocast_dtype: Optional[torch.dtype] = None):
+                 channels_last: bool = True, autocast_dtype: Optional[torch.dtype] = None, overlap_team: bool = True):
         from .models import build_trunk, build_yolov8
         self.ctx = get_context(device)
+        # The team stage (K3a/K3b, MobileNetV3, K4a: ~170 small launches, 2 ms) underfills the GPU; when its boxes are
+        # already known (tracker output / previous chunk) it runs on a high-priority side stream next to the detection
+        # stage (large HBM-bound kernels) instead of after it.
+        self.overlap_team = overlap_team
+        self._side = None
         torch.backends.cudnn.benchmark = True
         self.detector = Detector(build_yolov8(yolo_scale, nc, seed), device, imgsz=imgsz, conf=conf,
                                  class_names={0: "player", 1: "goalie"}, fuse=fuse, channels_last=channels_last,
@@ -59,6 +64,22 @@ class HotPath:
     def process_chunk_device(self, frames_dev: torch.Tensor, team_boxes: Optional[torch.Tensor] = None,
                              team_frame_idx: Optional[torch.Tensor] = None):
         """Everything on the device; returns the tensors a caller would copy back."""
+        if team_boxes is not None and self.overlap_team and team_boxes.shape[0]:
+            dev = frames_dev.device
+            main = torch.cuda.current_stream(dev)
+            if self._side is None:
+                self._side = torch.cuda.Stream(device=dev, priority=-1)
+            side = self._side
+            side.wait_stream(main)                                    # frames / boxes are ready at this point of main
+            with torch.cuda.stream(side):
+                tail = self.team_device(frames_dev, team_boxes, team_frame_idx)
+            for t in (frames_dev, team_boxes, team_frame_idx):
+                if t is not None:
+                    t.record_stream(side)
+            xyxy, conf, cls, cnt, _ = self.detect_device(frames_dev)
+            main.wait_stream(side)                                    # team stage finished long before detection does
+            tail.record_stream(main)
+            return dict(xyxy=xyxy, conf=conf, cls=cls, count=cnt, team_tail=tail, team_frame_idx=team_frame_idx)
         xyxy, conf, cls, cnt, _ = self.detect_device(frames_dev)
         if team_boxes is None:
             # boxes of detected players (class 0), compacted with torch indexing (tiny)
