@@ -27,6 +27,9 @@ def __getattr__(name):
     if name == "TeamClassifier":
         from .team import TeamClassifier
         return TeamClassifier
+    if name in ("VideoProcessor", "Config", "FrameResult"):
+        from . import video
+        return getattr(video, name)
     if name == "ByteTrack":
         from .tracker import ByteTrack
         return ByteTrack

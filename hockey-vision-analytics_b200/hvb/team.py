@@ -126,6 +126,28 @@ class TeamClassifier:
             predictions.append(team)
         return np.array(predictions)
 
+    def predict_from_frame(self, frames_dev, xyxy, frame_idx=None, tracker_ids: Optional[np.ndarray] = None,
+                           host_frames: Optional[np.ndarray] = None) -> np.ndarray:
+        """predict() for crops that are boxes into device-resident frames (no host crops): same routing and the same
+        failure cascade.  `host_frames` (the same frames on the host) is only needed if the cascade lands on the simple
+        rule, which packs host crops."""
+        if xyxy.shape[0] == 0:
+            return np.array([])
+        if self.use_hybrid:
+            try:
+                return self.hybrid_classifier.predict_from_frame(frames_dev, xyxy, frame_idx, tracker_ids)
+            except Exception as e:                          # noqa: BLE001
+                print(f"Hybrid prediction failed: {e}")
+                print("Falling back to simple classifier")
+                self.use_hybrid = False
+        if host_frames is None:
+            host_frames = frames_dev.cpu().numpy()
+        from .detections import crop_image
+        fi = frame_idx.cpu().numpy() if frame_idx is not None else np.zeros(xyxy.shape[0], np.int64)
+        boxes = xyxy.cpu().numpy() if hasattr(xyxy, "cpu") else np.asarray(xyxy)
+        frames = host_frames if host_frames.ndim == 4 else host_frames[None]
+        return self.predict([crop_image(frames[int(f)], b) for f, b in zip(fi, boxes)], tracker_ids)
+
     def get_segmentation_masks(self, tracker_ids: List[int]):
         return None
 
