@@ -315,6 +315,27 @@ def run_hvb(args, rank, world):
                              profile=args.profile_region and args.profile_4k)
         # the sliced path is launch-bound (≈900 launches per chunk over 5 tile shape classes): replay it as one CUDA graph
         ms4, _ = timed(lambda: puck.process_chunk_device(f4_dev, graph=True), max(2, args.steps // 2), 2)
+        # end to end through the public sliced API: pinned 4K frames in, per-frame Detections out
+        pinned4 = torch.from_numpy(f4).pin_memory()
+        k4 = max(2, args.steps // 2)
+
+        def run_e2e4(k):
+            return sum(len(r) for r in puck.process_stream(pinned4 for _ in range(k)))
+
+        run_e2e4(2)
+        barrier()
+        ea, eb = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        ea.record()
+        run_e2e4(k4)
+        eb.record()
+        barrier()
+        ms4_e2e = ea.elapsed_time(eb)
+        if world > 1:
+            t = torch.tensor([ms4_e2e], device=dev)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            ms4_e2e = float(t.item())
+        extra["c4_4k_sliced_e2e_frames_per_sec"] = world * F4 * k4 / (ms4_e2e / 1e3)
+        extra["c4_e2e_h2d_bytes_per_step"] = int(f4.nbytes)
         plan4 = puck.detector.plan(F4, 2160, 3840, _ffi.LB_SLICE_EXACT, 640, (640, 640), (128, 128))
         o4 = plan4.run(f4_dev)
         torch.cuda.synchronize()

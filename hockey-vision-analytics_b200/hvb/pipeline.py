@@ -212,3 +212,72 @@ class SlicedPuckPath:
 
     def process_chunk(self, frames: np.ndarray):
         return self.slicer.run_batch(frames)
+
+    def process_stream(self, chunks, graph: bool = True):
+        """Pipelined host API of the sliced path: `chunks` yields pinned uint8[n,H,W,3] host tensors (or numpy arrays);
+        yields per chunk a list of Detections (one per frame), one step behind.  The H2D copy of chunk i (side stream,
+        two device buffers) overlaps the kernels of chunk i-1 (one CUDA-graph replay) and the host's read of chunk i-1's
+        results (asynchronous D2H into pinned buffers + an event)."""
+        det = self.detector
+        dev = det.ctx.device
+        copy_stream = torch.cuda.Stream(device=dev)
+        main = torch.cuda.current_stream(dev)
+        bufs, free_ev = [None, None], [None, None]
+        pinned_out = [dict(), dict(), dict()]
+        names = ("xyxy", "conf", "cls", "keep", "seg", "count")
+
+        def stage(i, frames):
+            src = frames if isinstance(frames, torch.Tensor) else torch.from_numpy(np.ascontiguousarray(frames)).pin_memory()
+            slot = i & 1
+            if bufs[slot] is None or bufs[slot].shape != src.shape:
+                bufs[slot] = torch.empty(src.shape, dtype=torch.uint8, device=dev)
+            with torch.cuda.stream(copy_stream):
+                if free_ev[slot] is not None:
+                    copy_stream.wait_event(free_ev[slot])
+                bufs[slot].copy_(src, non_blocking=True)
+                ready = torch.cuda.Event()
+                ready.record(copy_stream)
+            return slot, ready, src
+
+        def launch(i, staged):
+            slot, ready, keep_alive = staged
+            main.wait_event(ready)
+            out = self.process_chunk_device(bufs[slot], graph=graph)
+            ev = torch.cuda.Event()
+            ev.record(main)
+            free_ev[slot] = ev
+            host = pinned_out[i % 3]
+            for k, t in zip(names, out):
+                if k not in host or host[k].shape != t.shape or host[k].dtype != t.dtype:
+                    host[k] = torch.empty(t.shape, dtype=t.dtype).pin_memory()
+                host[k].copy_(t, non_blocking=True)
+            done = torch.cuda.Event()
+            done.record(main)
+            return host, done, bufs[slot], keep_alive
+
+        def collect(item):
+            host, done, frames_dev, _keep = item
+            done.synchronize()
+            seg, cnt = host["seg"].numpy(), host["count"].numpy()
+            if (cnt < 0).any():                                # > 1024 candidates in a tile: redo this chunk with the retry tier
+                return self.slicer.run_batch(frames_dev)
+            total = int(seg[-1])
+            xyxy, conf, cls, keep = (host[k].numpy()[:total] for k in ("xyxy", "conf", "cls", "keep"))
+            if (keep == 0xFF).any():
+                raise _ffi.HvbError(_ffi.HVB_ERR_CAPACITY, "merged detections of one frame exceed the on-chip NMS capacity")
+            res = []
+            for f in range(len(seg) - 1):
+                lo, hi = int(seg[f]), int(seg[f + 1])
+                k = keep[lo:hi].astype(bool)
+                d = det._to_detections(xyxy[lo:hi][k], conf[lo:hi][k], cls[lo:hi][k])
+                d.xyxy = xyxy[lo:hi][k].copy()
+                res.append(d)
+            return res
+
+        inflight = []
+        for i, frames in enumerate(chunks):
+            inflight.append(launch(i, stage(i, frames)))
+            if len(inflight) > 1:
+                yield collect(inflight.pop(0))
+        while inflight:
+            yield collect(inflight.pop(0))

@@ -227,3 +227,21 @@ def test_sliced_path_cuda_graph_replay_equals_eager(ctx):
         assert torch.equal(e[4], g[4]) and torch.equal(e[5], g[5])
         for a, b in zip(e[:4], g[:4]):
             assert torch.equal(a[:tot], b[:tot])
+
+
+def test_sliced_stream_equals_run_batch(ctx):
+    """SlicedPuckPath.process_stream (pinned H2D on a side stream, graph replay, async D2H) == run_batch per chunk."""
+    from hvb.pipeline import SlicedPuckPath
+    from hvb.synth import rink_frame
+    rng = np.random.default_rng(13)
+    path = SlicedPuckPath("cuda:0", "n", 1, conf=5e-3, seed=2)
+    chunks = [np.stack([rink_frame(rng, 720, 1280, 8)[0] for _ in range(2)]) for _ in range(3)]
+    want = [path.process_chunk(c) for c in chunks]
+    for graph in (False, True):
+        got = list(path.process_stream(iter(chunks), graph=graph))
+        assert len(got) == len(want) == 3
+        for g, w in zip(got, want):
+            assert len(g) == len(w) == 2
+            for a, b in zip(g, w):
+                assert len(a) == len(b) and np.array_equal(a.xyxy, b.xyxy) and np.array_equal(a.confidence, b.confidence)
+                assert np.array_equal(a.class_id, b.class_id)
