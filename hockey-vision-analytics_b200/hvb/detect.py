@@ -15,7 +15,7 @@ import torch
 
 from . import _ffi
 from .detections import Detections
-from .runtime import Context, LetterboxPlan, get_context
+from .runtime import Context, LetterboxPlan, get_context, nvtx
 
 PLAYER_CLASS_ID = 0
 GOALKEEPER_CLASS_ID = 1
@@ -116,10 +116,13 @@ class Detector:
         """frames_dev uint8[n,H,W,3] on the GPU -> device tensors (xyxy[n,max_det,4], conf, cls, count)."""
         n, h, w, _ = frames_dev.shape
         plan = self.plan(n, h, w, _ffi.LB_WHOLE)
-        x = plan.class_views(plan.run(frames_dev))[0]
-        heads = self.forward_heads(x)
+        with nvtx("hvb:K1a letterbox"):
+            x = plan.class_views(plan.run(frames_dev))[0]
+        with nvtx("hvb:yolo forward (cuDNN convs + K5)"):
+            heads = self.forward_heads(x)
         meta_h, meta_d = self._meta_dev(plan, 0)
-        return self._decode(heads, meta_h, meta_d, n)
+        with nvtx("hvb:K2a decode+nms"):
+            return self._decode(heads, meta_h, meta_d, n)
 
     def _decode(self, heads, meta_h, meta_d, n_slots, out=None):
         # meta stays resident on the device; the host copy is only used by the overflow retry

@@ -24,7 +24,7 @@ import numpy as np
 import torch
 
 from . import _ffi
-from .runtime import Context, get_context
+from .runtime import Context, get_context, nvtx
 from .synth import pack_crops
 
 N_DEEP = 576
@@ -100,12 +100,15 @@ class HybridTeamClassifier:
         ctx = self.ctx
         feats = ctx.empty((n, N_DEEP + N_COLOR), torch.float64)
         raw = None
-        res = ctx.color_features(pixels, crops_dev, n, _ffi.ROI_HYBRID, want_raw=want_raw,
-                                 out_feat=feats[:, N_DEEP:], feat_stride=N_DEEP + N_COLOR)
+        with nvtx("hvb:K3a colour features"):
+            res = ctx.color_features(pixels, crops_dev, n, _ffi.ROI_HYBRID, want_raw=want_raw,
+                                     out_feat=feats[:, N_DEEP:], feat_stride=N_DEEP + N_COLOR)
         if want_raw:
             _, raw = res
-        x, valid = ctx.mnv3_preprocess(pixels, crops_dev, n, _ffi.ROI_HYBRID)
-        deep = self._trunk_forward(x)
+        with nvtx("hvb:K3b crop preprocessing"):
+            x, valid = ctx.mnv3_preprocess(pixels, crops_dev, n, _ffi.ROI_HYBRID)
+        with nvtx("hvb:mobilenetv3 trunk"):
+            deep = self._trunk_forward(x)
         deep = deep * (valid == 1).to(deep.dtype).unsqueeze(1)       # failed preprocessing -> zeros(576)
         feats[:, :N_DEEP] = deep.to(torch.float64)
         return feats, raw, valid
