@@ -302,6 +302,21 @@ def run_hvb(args, rank, world):
     peak, peak_src = measured_peaks()
     achieved = k1_bytes / (k1_ms / 1e3) / 1e9
 
+    # ---- roofline of the DOMINANT libhvb kernel of the step: the K5 conv epilogue (bias_act_kernel, ~28 % of the step,
+    # 82 launches).  Every launch of three more steps is bracketed by CUDA events on its launching stream.
+    runner = path.detector.runner
+    k5 = None
+    if runner is not None:
+        runner.epi_log = []
+        for _ in range(3):
+            path.detect_device(frames_dev)
+        torch.cuda.synchronize()
+        log, runner.epi_log = runner.epi_log, None
+        k5_bytes = sum(b for b, _, _ in log)
+        k5_ms = sum(a.elapsed_time(b) for _, a, b in log)
+        k5 = {"launches_per_step": len(log) // 3, "bytes_per_step": k5_bytes // 3, "ms_per_step": k5_ms / 3,
+              "achieved": k5_bytes / (k5_ms / 1e3) / 1e9}
+
     # ---- secondary workload: 4K sliced puck path (C4), reported in `extra`
     extra = {"fit_ms": fit_ms}
     if args.with_4k:
@@ -370,6 +385,21 @@ def run_hvb(args, rank, world):
                          "CPU forward (torch, %d threads), restated decode + real torchvision NMS, reference colour + "
                          "MobileNetV3 features, predict" % (nf, F, cores)}
 
+    k1_roof = {"kernel": "letterbox_kernel<false> (K1a, 1080p->736x1280, %d frames/launch)" % F, "bound": "hbm",
+               "achieved": achieved, "peak": peak, "peak_source": peak_src, "unit": "GB/s", "frac": achieved / peak,
+               "traffic": ncu_traffic("K1a_1080p_x%d" % F), "algorithmic_bytes_per_launch": int(k1_bytes), "avg_launch_ms": k1_ms}
+    if k5 is not None:
+        n5 = k5["launches_per_step"]
+        t5 = ncu_traffic("K5_bias_act_step_x%d" % F)          # summed over the launches of one step
+        roofline = {"kernel": "bias_act_kernel (K5 conv epilogue: bias + SiLU + residual -> dense / concat-slice destinations), "
+                              "%d launches per step of %d frames" % (n5, F),
+                    "bound": "hbm", "achieved": k5["achieved"], "peak": peak, "peak_source": peak_src, "unit": "GB/s",
+                    "frac": k5["achieved"] / peak, "traffic": (t5 / n5) if t5 else None,
+                    "algorithmic_bytes_per_launch": k5["bytes_per_step"] / n5, "avg_launch_ms": k5["ms_per_step"] / n5,
+                    "share_of_step": k5["ms_per_step"] / (ms_dev / args.steps)}
+        extra["roofline_k1a"] = k1_roof
+    else:
+        roofline = k1_roof
     if rank == 0:
         line = {
             "metric": METRIC, "value": fps_dev, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
@@ -387,10 +417,7 @@ def run_hvb(args, rank, world):
             "e2e": {"value": fps_e2e, "unit": UNIT, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h)},
             "gpu_launches": int(launches),
             "clocks": clocks,
-            "roofline": {"kernel": "letterbox_kernel<false> (K1a, 1080p->736x1280, %d frames/launch)" % F, "bound": "hbm",
-                         "achieved": achieved, "peak": peak, "peak_source": peak_src, "unit": "GB/s", "frac": achieved / peak,
-                         "traffic": ncu_traffic("K1a_1080p_x%d" % F), "algorithmic_bytes_per_launch": int(k1_bytes),
-                         "avg_launch_ms": k1_ms},
+            "roofline": roofline,
             "cpu_baseline": cpu,
             "extra": extra,
         }

@@ -61,6 +61,9 @@ class FusedYOLOv8:
         self.stem_b = m.b0.conv.bias.detach().float().cpu().contiguous().numpy()
         self.use_stem = stem_kernel and self.stem_w.shape[0] in (16, 32, 48, 64)
         self._lib, self._h = ctx.lib, ctx.handle
+        # measurement hook (bench.py): when set to a list, every epilogue launch is bracketed by CUDA events on the
+        # launching stream and logged as (algorithmic bytes, start event, stop event)
+        self.epi_log = None
 
     # ------------------------------------------------------------------ primitives (ctx lock is held by forward)
     # A "dest" says where the LAST epilogue of a block writes: dict(out1=, off1=, out2=, off2=, up2=).  out1 None = in
@@ -73,8 +76,17 @@ class FusedYOLOv8:
             c2n = c
         p = lambda t: C.c_void_p(t.data_ptr()) if t is not None else C.c_void_p(0)
         uh, uw = (x.shape[2], x.shape[3]) if (up2 and out2 is not None) else (0, 0)
+        log = self.epi_log
+        if log is not None:
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
         _ffi.check(self._lib.hvb_bias_act(self._h, p(x), p(bias), p(res), npix, c, act, p(out1), out1.shape[1], off1,
                                           p(out2), out2.shape[1] if out2 is not None else 0, off2, c2b, c2n, uh, uw))
+        if log is not None:
+            e1.record()
+            # algorithmic bytes: read x (+ residual), write every destination element once
+            nbytes = 4 * npix * (c * (2 + (res is not None)) + (c2n * (4 if uh else 1) if out2 is not None else 0))
+            log.append((nbytes, e0, e1))
         return out1
 
     def _buf(self, n, c, h, w):
