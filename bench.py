@@ -319,6 +319,19 @@ def run_hvb(args, rank, world):
 
     # ---- secondary workload: 4K sliced puck path (C4), reported in `extra`
     extra = {"fit_ms": fit_ms}
+    # frame-at-a-time use of the drop-in (what process_frame does per frame: host frame in, Detections out)
+    if rank == 0:
+        one = frames[0]
+        for tag, flag in (("eager", False), ("cuda_graph", True)):
+            path.detector.cuda_graph = flag
+            for _ in range(3):
+                path.detector.detect_players(one)
+            torch.cuda.synchronize()
+            t0 = time.perf_counter()
+            for _ in range(20):
+                path.detector.detect_players(one)
+            extra["frame_at_a_time_detect_fps_" + tag] = 20 / (time.perf_counter() - t0)
+        path.detector.cuda_graph = False
     if args.with_4k:
         from hvb.synth import rink_frame
         rng = np.random.default_rng(7 + rank)

@@ -39,7 +39,7 @@ class Detector:
     def __init__(self, model: torch.nn.Module, device="cuda:0", imgsz: int = 1280, conf: float = 0.4, iou: float = 0.7,
                  max_det: int = 300, agnostic_nms: bool = False, class_names: Optional[Dict[int, str]] = None,
                  autocast_dtype: Optional[torch.dtype] = None, channels_last: bool = False, fuse: bool = False,
-                 glue: Optional[bool] = None):
+                 glue: Optional[bool] = None, cuda_graph: Optional[bool] = False):
         self.ctx: Context = get_context(device)
         self.device = self.ctx.device
         if fuse:
@@ -63,6 +63,11 @@ class Detector:
         self.imgsz, self.conf, self.iou, self.max_det, self.agnostic = imgsz, conf, iou, max_det, agnostic_nms
         self.autocast_dtype = autocast_dtype
         self.class_names = class_names or {i: str(i) for i in range(self.nc)}
+        # cuda_graph=True: the whole device side of a detect call (K1a, ~270 backbone launches, K2a) is captured once per
+        # input shape and replayed — for frame-at-a-time use (process_frame) the eager path is launch-bound.
+        # None = automatic: on when the forward is the K5 runner (known to be capturable: no host synchronisation inside).
+        self.cuda_graph = (self.runner is not None) if cuda_graph is None else bool(cuda_graph)
+        self._graphs: Dict[Tuple, object] = {}
         self._plans: Dict[Tuple, LetterboxPlan] = {}
         self._meta: Dict[Tuple, torch.Tensor] = {}
 
@@ -112,10 +117,22 @@ class Detector:
         return self._meta[key]
 
     # -------------------------------------------------------------- whole-frame path
-    def detect_device(self, frames_dev: torch.Tensor):
+    def detect_device(self, frames_dev: torch.Tensor, graph: Optional[bool] = None):
         """frames_dev uint8[n,H,W,3] on the GPU -> device tensors (xyxy[n,max_det,4], conf, cls, count)."""
         n, h, w, _ = frames_dev.shape
         plan = self.plan(n, h, w, _ffi.LB_WHOLE)
+        if self.cuda_graph if graph is None else graph:
+            key = (n, h, w)
+            if key not in self._graphs:
+                from .runtime import GraphedStep
+
+                def step(f):
+                    xyxy, cf, cl, cnt, (heads, _, _) = self.detect_device(f, graph=False)
+                    return (xyxy, cf, cl, cnt) + tuple(heads)
+                self._graphs[key] = GraphedStep(self.ctx, step, [frames_dev])
+            out = self._graphs[key](frames_dev)          # static outputs: valid until the next call with this shape
+            meta_h, meta_d = self._meta_dev(plan, 0)
+            return out[0], out[1], out[2], out[3], (list(out[4:]), meta_h, meta_d)
         with nvtx("hvb:K1a letterbox"):
             x = plan.class_views(plan.run(frames_dev))[0]
         with nvtx("hvb:yolo forward (cuDNN convs + K5)"):

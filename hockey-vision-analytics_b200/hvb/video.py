@@ -63,7 +63,7 @@ class VideoProcessor:
                  team_selector: Optional[Callable] = None, detector_kwargs: Optional[dict] = None):
         self.config = config or Config()
         self.device = device
-        kw = dict(fuse=True, channels_last=True)
+        kw = dict(fuse=True, channels_last=True, cuda_graph=None)       # frame-at-a-time calls are launch-bound: replay a graph when the forward is capturable
         kw.update(detector_kwargs or {})
         self.detector = Detector(player_model, device, imgsz=self.config.detection_imgsz, conf=self.config.detection_confidence,
                                  class_names={PLAYER_CLASS_ID: "player", GOALKEEPER_CLASS_ID: "goalie"}, **kw)

@@ -187,3 +187,20 @@ def test_detector_uses_the_glue_by_default_and_agrees_with_plain_torch(ctx, no_t
     ia, ib = np.argsort(-da.confidence)[:k], np.argsort(-db.confidence)[:k]
     np.testing.assert_allclose(da.confidence[ia], db.confidence[ib], rtol=0, atol=1e-5)
     np.testing.assert_allclose(da.xyxy[ia], db.xyxy[ib], rtol=0, atol=1e-2)
+
+
+def test_detector_cuda_graph_replay_equals_eager(ctx):
+    """Detector(cuda_graph=True): K1a + the K5-driven forward + K2a captured once per frame shape and replayed."""
+    from hvb import Detector
+    from hvb.models import build_yolov8
+    from hvb.synth import rink_frame
+    rng = np.random.default_rng(8)
+    f1, f2 = rink_frame(rng, 720, 1280, 8)[0], rink_frame(rng, 720, 1280, 8)[0]
+    model = build_yolov8("n", 2, 1)
+    eager = Detector(model, "cuda:0", imgsz=640, conf=2e-3, fuse=True, channels_last=True, cuda_graph=False)
+    graph = Detector(model, "cuda:0", imgsz=640, conf=2e-3, fuse=True, channels_last=True, cuda_graph=None)
+    assert graph.cuda_graph and not eager.cuda_graph
+    for f in (f1, f2, f1):
+        a, b = eager(f), graph(f)
+        assert len(a) == len(b) > 0
+        assert np.array_equal(a.xyxy, b.xyxy) and np.array_equal(a.confidence, b.confidence) and np.array_equal(a.class_id, b.class_id)
