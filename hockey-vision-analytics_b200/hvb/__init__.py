@@ -30,7 +30,7 @@ def __getattr__(name):
     if name in ("VideoProcessor", "Config", "FrameResult"):
         from . import video
         return getattr(video, name)
-    if name == "ByteTrack":
-        from .tracker import ByteTrack
-        return ByteTrack
+    if name in ("ByteTrack", "MultiClipByteTrack"):
+        from . import tracker
+        return getattr(tracker, name)
     raise AttributeError(name)

@@ -163,6 +163,21 @@ class ByteTrack:
 
     # ------------------------------------------------------------------ one frame
     def _step(self, xyxy: np.ndarray, scores: np.ndarray) -> List[int]:
+        return self._drive(self._step_gen(xyxy, scores))
+
+    def _drive(self, gen):
+        """Run a cost-requesting generator to completion with this tracker's own cost function."""
+        try:
+            req = next(gen)
+            while True:
+                req = gen.send(self._cost(*req))
+        except StopIteration as stop:
+            return stop.value
+
+    def _step_gen(self, xyxy: np.ndarray, scores: np.ndarray):
+        """BYTETracker.update_with_tensors as a generator: every IoU cost matrix it needs is requested with
+        ``cost = yield (a_boxes, b_boxes, scores_or_None)`` so that a driver can batch the requests of many clips into
+        one K4b launch (MultiClipByteTrack); the single-clip path answers them one by one (_drive)."""
         self.frame_id += 1
         activated, refind, lost, removed = [], [], [], []
         hi = scores > self.track_activation_threshold
@@ -179,7 +194,7 @@ class ByteTrack:
         self._predict(pool)
 
         # round 1: all confirmed + lost tracks vs high-score detections, IoU fused with the score
-        m, u_trk, u_det = _assign(self._cost(self._tlbr(pool), det_box, det_s.astype(np.float64)), self.minimum_matching_threshold)
+        m, u_trk, u_det = _assign((yield (self._tlbr(pool), det_box, det_s.astype(np.float64))), self.minimum_matching_threshold)
         for it, idt in m:
             t = pool[it]
             was_tracked = self._state[t] == _TRACKED
@@ -193,7 +208,7 @@ class ByteTrack:
         lo_box = lo_tlwh.copy()
         lo_box[:, 2:] += lo_box[:, :2]
         rest = [pool[i] for i in u_trk if self._state[pool[i]] == _TRACKED]
-        m2, u_rest, _ = _assign(self._cost(self._tlbr(rest), lo_box), 0.5)
+        m2, u_rest, _ = _assign((yield (self._tlbr(rest), lo_box, None)), 0.5)
         for it, idt in m2:
             t = rest[it]
             self._hit(t, lo_tlwh[idt], lo_s[idt], reactivate=False)
@@ -206,7 +221,7 @@ class ByteTrack:
 
         # round 3: unconfirmed tracks vs the remaining high-score detections
         rem = list(u_det)
-        m3, u_unc, u_rem = _assign(self._cost(self._tlbr(unconfirmed), det_box[rem], det_s[rem].astype(np.float64)), 0.7)
+        m3, u_unc, u_rem = _assign((yield (self._tlbr(unconfirmed), det_box[rem], det_s[rem].astype(np.float64))), 0.7)
         for it, idt in m3:
             t = unconfirmed[it]
             self._hit(t, det_tlwh[rem[idt]], det_s[rem[idt]], reactivate=False)
@@ -239,7 +254,7 @@ class ByteTrack:
         self.removed = removed
         # duplicates between tracked and lost (IoU distance < 0.15): keep the longer-lived one
         if self.tracked and self.lost:
-            d = self._cost(self._tlbr(self.tracked), self._tlbr(self.lost))
+            d = yield (self._tlbr(self.tracked), self._tlbr(self.lost), None)
             da, db = set(), set()
             for ia, ib in zip(*np.where(d < 0.15)):
                 ta, tb = self.tracked[ia], self.lost[ib]
@@ -256,11 +271,14 @@ class ByteTrack:
         return self._step(t[:, :4], t[:, 4])
 
     def update_with_detections(self, detections: Detections) -> Detections:
+        return self._drive(self._update_gen(detections))
+
+    def _update_gen(self, detections: Detections):
         xyxy = np.asarray(detections.xyxy, np.float32).reshape(-1, 4)
         conf = np.asarray(detections.confidence, np.float32).reshape(-1) if len(xyxy) else np.zeros(0, np.float32)
-        out = self._step(xyxy, conf)
+        out = yield from self._step_gen(xyxy, conf)
         if len(out) > 0 and len(xyxy) > 0:
-            m, _, _ = _assign(self._cost(xyxy, self._tlbr(out)), 0.5)
+            m, _, _ = _assign((yield (xyxy, self._tlbr(out), None)), 0.5)
             ids = np.full(len(xyxy), -1, dtype=int)
             for i_det, i_trk in m:
                 ids[i_det] = int(self._ext[out[i_trk]])
@@ -269,3 +287,83 @@ class ByteTrack:
         empty = Detections.empty()
         empty.tracker_id = np.array([], dtype=int)
         return empty
+
+
+class MultiClipByteTrack:
+    """N independent ByteTrack instances (one per clip) stepped in lockstep, one frame of every clip per call.
+
+    Tracking is sequential per clip, but the clips are independent: the IoU cost matrices that the N
+    trackers need in the same association round (first / second / unconfirmed association, duplicate removal,
+    track -> detection id mapping) are computed by ONE batched K4b launch (``hvb_iou_cost`` takes per-problem offsets)
+    and one device -> host copy, instead of one launch + copy per clip and round: 5 launches per frame for any number
+    of clips.  Results are those of N separate ``ByteTrack`` objects (tests/test_tracker.py)."""
+
+    def __init__(self, n_clips: int, device="cuda:0", batched_cost: Optional[Callable] = None, **kwargs):
+        self.trackers = [ByteTrack(device=device, **kwargs) for _ in range(n_clips)]
+        self._device = device
+        self._batched_cost = batched_cost        # list of (a, b, scores|None) -> list of cost matrices; default = K4b
+
+    def reset(self):
+        for t in self.trackers:
+            t.reset()
+
+    def _costs(self, reqs: List[tuple]) -> List[np.ndarray]:
+        if self._batched_cost is not None:
+            return self._batched_cost(reqs)
+        out: List[Optional[np.ndarray]] = [None] * len(reqs)
+        live = []
+        for i, (a, b, _s) in enumerate(reqs):
+            if len(a) == 0 or len(b) == 0:
+                out[i] = np.zeros((len(a), len(b)))
+            else:
+                live.append(i)
+        if not live:
+            return out
+        import torch
+        from .runtime import get_context
+        ctx = get_context(self._device)
+        # every request of one round has the same dtype pattern (the float32-area quirk of numpy's box_iou_batch)
+        a0, b0, s0 = reqs[live[0]]
+        flags = (1 if np.asarray(a0).dtype == np.float32 else 0) | (2 if np.asarray(b0).dtype == np.float32 else 0)
+        A = np.concatenate([np.asarray(reqs[i][0], np.float64).reshape(-1, 4) for i in live])
+        B = np.concatenate([np.asarray(reqs[i][1], np.float64).reshape(-1, 4) for i in live])
+        na = np.array([len(reqs[i][0]) for i in live]); nb = np.array([len(reqs[i][1]) for i in live])
+        a_off = np.concatenate([[0], np.cumsum(na)]).astype(np.int32)
+        b_off = np.concatenate([[0], np.cumsum(nb)]).astype(np.int32)
+        sizes = na * nb
+        out_off = np.concatenate([[0], np.cumsum(sizes)[:-1]]).astype(np.int64)
+        S = np.concatenate([np.asarray(reqs[i][2], np.float64) for i in live]) if s0 is not None else None
+        dev = ctx.device
+        cost = ctx.iou_cost(torch.from_numpy(A).to(dev), torch.from_numpy(B).to(dev),
+                            torch.from_numpy(S).to(dev) if S is not None else None,
+                            torch.from_numpy(a_off).to(dev), torch.from_numpy(b_off).to(dev), torch.from_numpy(out_off).to(dev),
+                            len(live), int(na.max()), int(nb.max()), int(sizes.sum()), flags).cpu().numpy()
+        for k, i in enumerate(live):
+            out[i] = cost[out_off[k]: out_off[k] + sizes[k]].reshape(na[k], nb[k])
+        return out
+
+    def update_with_detections(self, detections: Sequence[Detections]) -> List[Detections]:
+        """One frame of every clip: detections[i] belongs to clip i.  Returns the tracked detections per clip."""
+        assert len(detections) == len(self.trackers)
+        gens = [t._update_gen(d) for t, d in zip(self.trackers, detections)]
+        results: List[Optional[Detections]] = [None] * len(gens)
+        pending = {}
+        for i, g in enumerate(gens):
+            try:
+                pending[i] = next(g)
+            except StopIteration as stop:
+                results[i] = stop.value
+        while pending:
+            order = sorted(pending)
+            # clips whose request has a different dtype/score pattern than the first one wait for the next batch
+            sig = lambda r: (np.asarray(r[0]).dtype == np.float32, np.asarray(r[1]).dtype == np.float32, r[2] is not None)
+            first = sig(pending[order[0]])
+            batch = [i for i in order if sig(pending[i]) == first]
+            costs = self._costs([pending[i] for i in batch])
+            for i, c in zip(batch, costs):
+                try:
+                    pending[i] = gens[i].send(c)
+                except StopIteration as stop:
+                    results[i] = stop.value
+                    del pending[i]
+        return results

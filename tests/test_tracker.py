@@ -80,3 +80,40 @@ def test_tracker_with_k4b_kernel(ctx, kw):
     launches = ctx.launch_count(reset=True)
     run_pair(None, 5, **kw)
     assert ctx.launch_count() > 100          # every cost matrix came from the K4b kernel
+
+
+def _numpy_batched(reqs):
+    return [numpy_cost(a, b, sc) if len(a) and len(b) else np.zeros((len(a), len(b))) for a, b, sc in reqs]
+
+
+def _run_multi(batched_cost, n_clips=4, n_frames=40):
+    from hvb.tracker import MultiClipByteTrack
+    clips = [synthetic_detections(20 + c, n_frames) for c in range(n_clips)]
+    multi = MultiClipByteTrack(n_clips, batched_cost=batched_cost, **MAIN)
+    singles = [RefByteTrack(**MAIN) for _ in range(n_clips)]
+    seen = 0
+    for f in range(n_frames):
+        dets = [Detections(xyxy=clips[c][f][0].copy(), confidence=clips[c][f][1].copy(), class_id=np.zeros(len(clips[c][f][1]), int))
+                for c in range(n_clips)]
+        if f == 7:
+            dets[1] = Detections.empty()                           # one clip has an empty frame: the others must not care
+        outs = multi.update_with_detections(dets)
+        for c in range(n_clips):
+            xyxy, conf = (clips[c][f] if not (f == 7 and c == 1) else (np.zeros((0, 4), np.float32), np.zeros(0, np.float32)))
+            keep, ids = singles[c].update_with_detections(xyxy.copy(), conf.copy())
+            assert np.array_equal(outs[c].tracker_id, ids), (f, c)
+            assert np.array_equal(outs[c].xyxy, xyxy[keep])
+            seen = max(seen, ids.max() if len(ids) else 0)
+    assert seen >= 8
+
+
+def test_multi_clip_lockstep_equals_independent_trackers():
+    _run_multi(_numpy_batched)
+
+
+@pytest.mark.gpu
+def test_multi_clip_lockstep_with_batched_k4b(ctx):
+    ctx.launch_count(reset=True)
+    _run_multi(None, n_clips=8, n_frames=30)
+    per_frame = ctx.launch_count() / 30
+    assert 1 <= per_frame <= 5.01, per_frame             # at most five batched K4b launches per frame for all 8 clips

@@ -48,7 +48,7 @@ def report(name, ms, nbytes=None, flops=None, **kw):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--reps", type=int, default=20)
-    ap.add_argument("--only", default="", help="comma-separated sections: k1,k2,k3,k4,k4b,k5")
+    ap.add_argument("--only", default="", help="comma-separated sections: k1,k2,k3,k4,k4b,track,k5")
     ap.add_argument("--profile", action="store_true", help="one launch per kernel configuration, no timing (for ncu)")
     args = ap.parse_args()
     if args.profile:
@@ -148,6 +148,42 @@ def main():
         oo = torch.from_numpy((np.arange(P) * T * D).astype(np.int64)).cuda()
         report("K4b IoU cost 8 clips x 40x40", timed(lambda: ctx.iou_cost(a, b, None, ao, bo, oo, P, T, D, P * T * D, 2), R), P * (T + D) * 32 + P * T * D * 8)
 
+    def sec_track():
+        # ByteTrack association for 8 clips x ~40 detections per frame: independent trackers (one K4b launch + copy per
+        # clip and round) vs MultiClipByteTrack (one batched launch per round for all clips)
+        import time
+        from hvb.detections import Detections
+        from hvb.tracker import ByteTrack, MultiClipByteTrack
+        kw = dict(track_activation_threshold=0.25, lost_track_buffer=30, minimum_matching_threshold=0.8, frame_rate=30,
+                  minimum_consecutive_frames=2)
+        n_clips, n_frames, n_obj = 8, 60, 40
+        r = np.random.default_rng(9)
+        clips = []
+        for c in range(n_clips):
+            cx, cy = r.uniform(200, 1700, n_obj), r.uniform(200, 900, n_obj)
+            w, h = r.uniform(40, 110, n_obj), r.uniform(100, 250, n_obj)
+            fr = []
+            for f in range(n_frames):
+                cx += r.uniform(-6, 6, n_obj); cy += r.uniform(-6, 6, n_obj)
+                b = np.stack([cx - w / 2, cy - h / 2, cx + w / 2, cy + h / 2], 1).astype(np.float32)
+                fr.append((b, r.uniform(0.45, 0.95, n_obj).astype(np.float32)))
+            clips.append(fr)
+        mk = lambda c, f: Detections(xyxy=clips[c][f][0].copy(), confidence=clips[c][f][1].copy(), class_id=np.zeros(n_obj, int))
+        singles = [ByteTrack(**kw) for _ in range(n_clips)]
+        t0 = time.perf_counter()
+        for f in range(n_frames):
+            for c in range(n_clips):
+                singles[c].update_with_detections(mk(c, f))
+        t_single = (time.perf_counter() - t0) / n_frames
+        multi = MultiClipByteTrack(n_clips, **kw)
+        t0 = time.perf_counter()
+        for f in range(n_frames):
+            multi.update_with_detections([mk(c, f) for c in range(n_clips)])
+        t_multi = (time.perf_counter() - t0) / n_frames
+        print(json.dumps({"kernel": "ByteTrack 8 clips x 40 detections, host logic + K4b costs", "ms_per_frame_independent": round(1e3 * t_single, 3),
+                          "ms_per_frame_lockstep_batched_k4b": round(1e3 * t_multi, 3),
+                          "clip_frames_per_s_lockstep": round(n_clips / t_multi, 1)}), flush=True)
+
     def sec_k5():
         # K5 backbone glue at the YOLOv8m / 1080p (736x1280 input) layer sizes, 32 frames per launch
         CL = torch.channels_last
@@ -199,6 +235,8 @@ def main():
         sec_k4()
     if want('k4b'):
         sec_k4b()
+    if want('track'):
+        sec_track()
     if want('k5'):
         sec_k5()
 
