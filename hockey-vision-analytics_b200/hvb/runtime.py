@@ -290,7 +290,7 @@ class Context:
         return out
 
     # ------------------------------------------------------------------ K5 (backbone glue; NHWC float32)
-    ACT = {"none": 0, "silu": 1, "relu": 2, "hardswish": 3}
+    ACT = {"none": 0, "silu": 1, "relu": 2, "hardswish": 3, "silu_fast": 4}
 
     @staticmethod
     def _nhwc(t: torch.Tensor) -> Tuple[int, int]:

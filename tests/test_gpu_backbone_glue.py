@@ -29,10 +29,10 @@ def no_tf32():
     torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32 = prev
 
 
-ACTS = {"none": lambda x: x, "silu": F.silu, "relu": F.relu, "hardswish": F.hardswish}
+ACTS = {"none": lambda x: x, "silu": F.silu, "relu": F.relu, "hardswish": F.hardswish, "silu_fast": F.silu}
 
 
-@pytest.mark.parametrize("c,act", [(48, "silu"), (24, "silu"), (66, "none"), (2, "none"), (7, "relu"), (96, "hardswish")])
+@pytest.mark.parametrize("c,act", [(48, "silu"), (24, "silu"), (66, "none"), (2, "none"), (7, "relu"), (96, "hardswish"), (48, "silu_fast")])
 @pytest.mark.parametrize("with_res", [False, True])
 def test_bias_act_in_place(ctx, c, act, with_res):
     g = torch.Generator().manual_seed(c)
@@ -204,3 +204,14 @@ def test_detector_cuda_graph_replay_equals_eager(ctx):
         a, b = eager(f), graph(f)
         assert len(a) == len(b) > 0
         assert np.array_equal(a.xyxy, b.xyxy) and np.array_equal(a.confidence, b.confidence) and np.array_equal(a.class_id, b.class_id)
+
+
+def test_fast_silu_error_bound(ctx):
+    """act=4 (ex2.approx + rcp.approx): <= 1e-6 relative to the float64 SiLU over the whole useful range."""
+    x = torch.linspace(-30, 30, 1 << 20).view(1, 4, 512, 512).contiguous(memory_format=CL)
+    ref = (x.double() * torch.sigmoid(x.double()))
+    for act, bound in (("silu_fast", 1e-6), ("silu", 5e-7)):
+        got = ctx.bias_act(x.clone(memory_format=torch.preserve_format).cuda(), None, act).cpu().double()
+        rel = ((got - ref).abs() / ref.abs().clamp_min(1e-30))[x.abs() > 1e-3]
+        print(act, "max relative error", float(rel.max()))
+        assert float(rel.max()) <= bound, (act, float(rel.max()))
