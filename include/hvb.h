@@ -284,7 +284,7 @@ HVB_API int hvb_iou_cost(hvb_ctx* ctx, const double* a_dev, const double* b_dev,
  * MobileNetV3 forward at common/team_hybrid.py:73-81.  Tensors are float32 NHWC ("channels_last").
  *
  * hvb_bias_act:  y[p,c] = act(x[p,c] + bias[c]) (+ residual[p,c]);  act: 0 none, 1 SiLU (expf + IEEE division,
- *   the formula of torch's kernel), 2 ReLU, 3 hardswish, 4 SiLU with ex2.approx / rcp.approx (<= 5e-7 relative error; the
+ *   the formula of torch's kernel), 2 ReLU, 3 hardswish, 4 SiLU with ex2.approx / rcp.approx (<= 1e-6 relative error; the
  *   exact formula makes the in-place pass ALU-bound: 5.5 vs 7.0 TB/s).
  *   x_dev is the dense [npix, channels] raw convolution output; y goes to out1 (all channels, row pitch
  *   out1_ld floats, starting at channel out1_off of each row; may alias x_dev) and/or to out2 (only
