@@ -28,15 +28,28 @@ def main():
     a = ap.parse_args()
     rows = list(csv.reader(open(a.csv)))
     hdr = next(i for i, r in enumerate(rows) if r and r[0] == "ID")
-    data = [r for r in rows[hdr + 1:] if len(r) > 5]
+    h = rows[hdr]
+    mi, vi, ui = h.index("Metric Name"), h.index("Metric Value"), h.index("Metric Unit")
+    scale = {"ns": 1e-3, "nsecond": 1e-3, "us": 1.0, "usecond": 1.0, "ms": 1e3, "msecond": 1e3,
+             "byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}
+    launches = collections.OrderedDict()                      # ID -> [name, us, dram bytes]
+    for r in rows[hdr + 1:]:
+        if len(r) <= vi:
+            continue
+        rec = launches.setdefault(r[0], [short(r[4]), 0.0, 0.0])
+        v = float(r[vi].replace(",", "")) * scale.get(r[ui], 1.0)
+        if r[mi] == "gpu__time_duration.sum":
+            rec[1] = v
+        elif r[mi].startswith("dram__bytes"):
+            rec[2] += v
+    data = list(launches.values())
     agg = collections.OrderedDict()
     total = 0.0
-    for r in data:
-        k = short(r[4])
-        us = float(r[-1]) / 1e3
+    for k, us, nbytes in data:
         total += us
-        n, t = agg.get(k, (0, 0.0))
-        agg[k] = (n + 1, t + us)
+        n, t, b = agg.get(k, (0, 0.0, 0.0))
+        agg[k] = (n + 1, t + us, b + nbytes)
+    have_bytes = any(b for _, _, b in agg.values())
     ours = {k: v for k, v in agg.items() if any(h in k for h in HVB)}
     lib = {k: v for k, v in agg.items() if k not in ours}
     print("# %s\n" % a.title)
@@ -46,18 +59,20 @@ def main():
         print(a.note + "\n")
     print("Times are cold-cache and serialised by ncu: compare SHARES, not absolutes.  %d launches, %.2f ms summed.\n" % (len(data), total / 1e3))
     print("## libhvb kernels (hand-written, sm_100a)\n")
-    print("| kernel | launches | total us | share of step |\n|---|---|---|---|")
+    print("| kernel | launches | total us | share of step |%s\n|---|---|---|---|%s" % (" DRAM MB (read+write) | DRAM GB/s |" if have_bytes else "", "---|---|" if have_bytes else ""))
     so = 0.0
-    for k, (n, t) in sorted(ours.items(), key=lambda kv: -kv[1][1]):
-        print("| `%s` | %d | %.1f | %.2f %% |" % (k, n, t, 100 * t / total))
+    for k, (n, t, b) in sorted(ours.items(), key=lambda kv: -kv[1][1]):
+        extra = " %.1f | %.0f |" % (b / 1e6, b / t / 1e3) if have_bytes else ""
+        print("| `%s` | %d | %.1f | %.2f %% |%s" % (k, n, t, 100 * t / total, extra))
         so += t
-    print("| **all libhvb** | %d | %.1f | **%.1f %%** |\n" % (sum(n for n, _ in ours.values()), so, 100 * so / total))
+    print("| **all libhvb** | %d | %.1f | **%.1f %%** |\n" % (sum(v[0] for v in ours.values()), so, 100 * so / total))
     print("## Library kernels (PyTorch / cuDNN / CUTLASS convolutions and the few remaining torch ops)\n")
-    print("| kernel | launches | total us | share |\n|---|---|---|---|")
-    for k, (n, t) in sorted(lib.items(), key=lambda kv: -kv[1][1])[:25]:
-        print("| `%s` | %d | %.1f | %.1f %% |" % (k, n, t, 100 * t / total))
-    sl = sum(t for _, t in lib.values())
-    print("| **all library** | %d | %.1f | **%.1f %%** |" % (sum(n for n, _ in lib.values()), sl, 100 * sl / total))
+    print("| kernel | launches | total us | share |%s\n|---|---|---|---|%s" % (" DRAM MB | DRAM GB/s |" if have_bytes else "", "---|---|" if have_bytes else ""))
+    for k, (n, t, b) in sorted(lib.items(), key=lambda kv: -kv[1][1])[:25]:
+        extra = " %.1f | %.0f |" % (b / 1e6, b / t / 1e3) if have_bytes else ""
+        print("| `%s` | %d | %.1f | %.1f %% |%s" % (k, n, t, 100 * t / total, extra))
+    sl = sum(v[1] for v in lib.values())
+    print("| **all library** | %d | %.1f | **%.1f %%** |" % (sum(v[0] for v in lib.values()), sl, 100 * sl / total))
 
 
 if __name__ == "__main__":
