@@ -196,27 +196,38 @@ stem_conv_kernel(const float* __restrict__ in, float* __restrict__ out, int H, i
     const int t = threadIdx.x;
     const int ixw = 2 * ox0 - 2;                                  // frame column of window column 0 (even)
     const bool pair_ok = (W & 1) == 0 && ((reinterpret_cast<uintptr_t>(in) & 7) == 0);
+    // Staging: thread t loads window pair t (columns 2t, 2t+1) of the nine (channel, row) planes; threads 0 and 1 also
+    // load pairs STEM_PX and STEM_PX+1.  Column validity and the three row offsets are computed once per thread.
+    const size_t hw = (size_t)H * W;
+    const float* img = in + (size_t)n * 3 * hw;
+    const int iy0 = 2 * oy - 1;
+    auto stage = [&](int j) {
+        const int ix = ixw + 2 * j;
+        const bool c0 = ix >= 0 && ix < W, c1 = ix + 1 >= 0 && ix + 1 < W;
+        const bool both = pair_ok && c0 && c1;
 #pragma unroll
-    for (int plane = 0; plane < 9; ++plane) {
-        const int ci = plane / 3, ky = plane - ci * 3;
-        const int iy = 2 * oy - 1 + ky;
-        const float* row = in + (((size_t)n * 3 + ci) * H + iy) * W;
-        const bool row_ok = iy >= 0 && iy < H;
-        for (int j = t; j < STEM_PX + 2; j += STEM_PX) {          // pair j = window columns 2j, 2j+1
-            const int ix = ixw + 2 * j;
-            float e = 0.0f, o = 0.0f;
-            if (row_ok) {
-                if (pair_ok && ix >= 0 && ix + 1 < W) {
-                    const float2 v = __ldg(reinterpret_cast<const float2*>(row + ix));
-                    e = v.x; o = v.y;
-                } else {
-                    if (ix >= 0 && ix < W) e = __ldg(row + ix);
-                    if (ix + 1 >= 0 && ix + 1 < W) o = __ldg(row + ix + 1);
+        for (int ky = 0; ky < 3; ++ky) {
+            const int iy = iy0 + ky;
+            const bool row_ok = iy >= 0 && iy < H;
+            const float* p = img + (size_t)(row_ok ? iy : 0) * W + ix;
+#pragma unroll
+            for (int ci = 0; ci < 3; ++ci) {
+                float e = 0.0f, o = 0.0f;
+                if (row_ok) {
+                    if (both) {
+                        const float2 v = __ldg(reinterpret_cast<const float2*>(p + ci * hw));
+                        e = v.x; o = v.y;
+                    } else {
+                        if (c0) e = __ldg(p + ci * hw);
+                        if (c1) o = __ldg(p + ci * hw + 1);
+                    }
                 }
+                s_ev[ci][ky][j] = e; s_od[ci][ky][j] = o;
             }
-            s_ev[ci][ky][j] = e; s_od[ci][ky][j] = o;
         }
-    }
+    };
+    stage(t);
+    if (t < 2) stage(STEM_PX + t);
     __syncthreads();
     float acc[CO];
 #pragma unroll
