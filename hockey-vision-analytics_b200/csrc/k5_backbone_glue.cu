@@ -181,84 +181,105 @@ concat_nhwc_kernel(const CatArgs a) {
 constexpr int STEM_PX = HVB_STEM_PX;         // output pixels (one row segment) per block = threads per block
 template <int CO> struct StemParams { float w[27 * CO]; float b[CO]; };   // w index: ((ci*3+ky)*3+kx)*CO + co
 
+constexpr int STEM_ROWS = 4;                 // output rows per block: amortises the block start-up and lets row r+1's loads fly under row r's FMAs
+
 template <int CO>
 __global__ void __launch_bounds__(STEM_PX)
 stem_conv_kernel(const float* __restrict__ in, float* __restrict__ out, int H, int W, int OH, int OW,
                  const __grid_constant__ StemParams<CO> prm) {
-    // Input window of the block, de-interleaved by column parity so that the three taps of thread t are
+    // Input window of one output row, de-interleaved by column parity so that the three taps of thread t are
     // stride-1 across the warp: window column j (frame column 2*ox0 - 2 + j) lives in s_ev[j/2] or s_od[j/2];
     // tap kx of output t reads window column 2t + kx + 1  ->  od[t], ev[t+1], od[t+1].
     __shared__ float s_ev[3][3][STEM_PX + 2];
     __shared__ float s_od[3][3][STEM_PX + 2];
     constexpr int LDO = CO + 4;                                   // 16-byte aligned rows, conflict-free 128-bit accesses
     __shared__ __align__(16) float s_out[STEM_PX * LDO];
-    const int n = blockIdx.z, oy = blockIdx.y, ox0 = blockIdx.x * STEM_PX;
+    const int n = blockIdx.z, oy0 = blockIdx.y * STEM_ROWS, ox0 = blockIdx.x * STEM_PX;
     const int t = threadIdx.x;
     const int ixw = 2 * ox0 - 2;                                  // frame column of window column 0 (even)
     const bool pair_ok = (W & 1) == 0 && ((reinterpret_cast<uintptr_t>(in) & 7) == 0);
-    // Staging: thread t loads window pair t (columns 2t, 2t+1) of the nine (channel, row) planes; threads 0 and 1 also
-    // load pairs STEM_PX and STEM_PX+1.  Column validity and the three row offsets are computed once per thread.
     const size_t hw = (size_t)H * W;
     const float* img = in + (size_t)n * 3 * hw;
-    const int iy0 = 2 * oy - 1;
-    auto stage = [&](int j) {
-        const int ix = ixw + 2 * j;
-        const bool c0 = ix >= 0 && ix < W, c1 = ix + 1 >= 0 && ix + 1 < W;
-        const bool both = pair_ok && c0 && c1;
+    // Thread t owns window pair t (columns 2t, 2t+1) of the nine (row, channel) planes; threads 0 and 1 also own pairs
+    // STEM_PX and STEM_PX+1.  Column validity is per thread, row validity per output row.
+    const int ixa = ixw + 2 * t, ixb = ixw + 2 * (STEM_PX + t);
+    const bool a0 = ixa >= 0 && ixa < W, a1 = ixa + 1 >= 0 && ixa + 1 < W;
+    const bool b0 = t < 2 && ixb >= 0 && ixb < W, b1 = t < 2 && ixb + 1 >= 0 && ixb + 1 < W;
+
+    auto fetch = [&](int oy, int ix, bool c0, bool c1, float2 (&v)[9]) {
 #pragma unroll
         for (int ky = 0; ky < 3; ++ky) {
-            const int iy = iy0 + ky;
+            const int iy = 2 * oy - 1 + ky;
             const bool row_ok = iy >= 0 && iy < H;
             const float* p = img + (size_t)(row_ok ? iy : 0) * W + ix;
 #pragma unroll
             for (int ci = 0; ci < 3; ++ci) {
-                float e = 0.0f, o = 0.0f;
+                float2 r = make_float2(0.0f, 0.0f);
                 if (row_ok) {
-                    if (both) {
-                        const float2 v = __ldg(reinterpret_cast<const float2*>(p + ci * hw));
-                        e = v.x; o = v.y;
+                    if (pair_ok && c0 && c1) {
+                        r = __ldg(reinterpret_cast<const float2*>(p + ci * hw));
                     } else {
-                        if (c0) e = __ldg(p + ci * hw);
-                        if (c1) o = __ldg(p + ci * hw + 1);
+                        if (c0) r.x = __ldg(p + ci * hw);
+                        if (c1) r.y = __ldg(p + ci * hw + 1);
                     }
                 }
-                s_ev[ci][ky][j] = e; s_od[ci][ky][j] = o;
+                v[ky * 3 + ci] = r;
             }
         }
     };
-    stage(t);
-    if (t < 2) stage(STEM_PX + t);
-    __syncthreads();
-    float acc[CO];
+    auto put = [&](int j, const float2 (&v)[9]) {
 #pragma unroll
-    for (int co = 0; co < CO; ++co) acc[co] = prm.b[co];
+        for (int ky = 0; ky < 3; ++ky)
 #pragma unroll
-    for (int ci = 0; ci < 3; ++ci)
-#pragma unroll
-        for (int ky = 0; ky < 3; ++ky) {
-            const float x0 = s_od[ci][ky][t], x1 = s_ev[ci][ky][t + 1], x2 = s_od[ci][ky][t + 1];
-#pragma unroll
-            for (int co = 0; co < CO; ++co) {
-                acc[co] = __fmaf_rn(prm.w[((ci * 3 + ky) * 3 + 0) * CO + co], x0, acc[co]);
-                acc[co] = __fmaf_rn(prm.w[((ci * 3 + ky) * 3 + 1) * CO + co], x1, acc[co]);
-                acc[co] = __fmaf_rn(prm.w[((ci * 3 + ky) * 3 + 2) * CO + co], x2, acc[co]);
-            }
+            for (int ci = 0; ci < 3; ++ci) { s_ev[ci][ky][j] = v[ky * 3 + ci].x; s_od[ci][ky][j] = v[ky * 3 + ci].y; }
+    };
+
+    float2 cur[9], ext[9];
+    fetch(oy0, ixa, a0, a1, cur);
+    if (t < 2) fetch(oy0, ixb, b0, b1, ext);
+    const int rows = min(STEM_ROWS, OH - oy0);
+    for (int r = 0; r < rows; ++r) {
+        const int oy = oy0 + r;
+        put(t, cur);
+        if (t < 2) put(STEM_PX + t, ext);
+        if (r + 1 < rows) {                                       // next row's loads are in flight during this row's FMAs
+            fetch(oy + 1, ixa, a0, a1, cur);
+            if (t < 2) fetch(oy + 1, ixb, b0, b1, ext);
         }
+        __syncthreads();
+        float acc[CO];
 #pragma unroll
-    for (int c4 = 0; c4 < CO / 4; ++c4) {
-        float4 v;
-        v.x = silu_fast(acc[4 * c4]); v.y = silu_fast(acc[4 * c4 + 1]); v.z = silu_fast(acc[4 * c4 + 2]); v.w = silu_fast(acc[4 * c4 + 3]);
-        *reinterpret_cast<float4*>(&s_out[t * LDO + 4 * c4]) = v;
-    }
-    __syncthreads();
-    // the block's 128 x CO outputs are one contiguous NHWC run: coalesced 128-bit stores
-    const int npx = min(STEM_PX, OW - ox0);
-    float4* o4 = reinterpret_cast<float4*>(out + (((size_t)n * OH + oy) * OW + ox0) * CO);
-    constexpr int Q = CO / 4;
+        for (int co = 0; co < CO; ++co) acc[co] = prm.b[co];
+#pragma unroll
+        for (int ci = 0; ci < 3; ++ci)
+#pragma unroll
+            for (int ky = 0; ky < 3; ++ky) {
+                const float x0 = s_od[ci][ky][t], x1 = s_ev[ci][ky][t + 1], x2 = s_od[ci][ky][t + 1];
+#pragma unroll
+                for (int co = 0; co < CO; ++co) {
+                    acc[co] = __fmaf_rn(prm.w[((ci * 3 + ky) * 3 + 0) * CO + co], x0, acc[co]);
+                    acc[co] = __fmaf_rn(prm.w[((ci * 3 + ky) * 3 + 1) * CO + co], x1, acc[co]);
+                    acc[co] = __fmaf_rn(prm.w[((ci * 3 + ky) * 3 + 2) * CO + co], x2, acc[co]);
+                }
+            }
+#pragma unroll
+        for (int c4 = 0; c4 < CO / 4; ++c4) {
+            float4 v;
+            v.x = silu_fast(acc[4 * c4]); v.y = silu_fast(acc[4 * c4 + 1]); v.z = silu_fast(acc[4 * c4 + 2]); v.w = silu_fast(acc[4 * c4 + 3]);
+            *reinterpret_cast<float4*>(&s_out[t * LDO + 4 * c4]) = v;
+        }
+        __syncthreads();                                          // s_out complete; every thread is done reading s_ev / s_od
+        // the row segment's 128 x CO outputs are one contiguous NHWC run: coalesced 128-bit stores
+        const int npx = min(STEM_PX, OW - ox0);
+        float4* o4 = reinterpret_cast<float4*>(out + (((size_t)n * OH + oy) * OW + ox0) * CO);
+        constexpr int Q = CO / 4;
 #pragma unroll 4
-    for (int i = t; i < npx * Q; i += STEM_PX) {
-        const int px = i / Q, q = i - px * Q;
-        o4[i] = *reinterpret_cast<const float4*>(&s_out[px * LDO + 4 * q]);
+        for (int i = t; i < npx * Q; i += STEM_PX) {
+            const int px = i / Q, q = i - px * Q;
+            o4[i] = *reinterpret_cast<const float4*>(&s_out[px * LDO + 4 * q]);
+        }
+        // next iteration: put() only touches s_ev / s_od (free since the barrier above); s_out is rewritten after the
+        // next iteration's first barrier, which every thread reaches only after finishing the stores above
     }
 }
 
@@ -351,7 +372,7 @@ int launch_stem(hvb_ctx* ctx, const float* in, const float* w_host, const float*
         for (int k = 0; k < 27; ++k) prm.w[k * CO + co] = w_host[co * 27 + k];
     for (int co = 0; co < CO; ++co) prm.b[co] = b_host ? b_host[co] : 0.0f;
     const int oh = (h - 1) / 2 + 1, ow = (w - 1) / 2 + 1;           // floor((h + 2 - 3) / 2) + 1
-    dim3 grid((ow + STEM_PX - 1) / STEM_PX, oh, n);
+    dim3 grid((ow + STEM_PX - 1) / STEM_PX, (oh + STEM_ROWS - 1) / STEM_ROWS, n);
     stem_conv_kernel<CO><<<grid, STEM_PX, 0, ctx->stream>>>(in, out, h, w, oh, ow, prm);
     HVB_LAUNCHED(ctx);
     return HVB_OK;
@@ -462,7 +483,7 @@ int hvb_stem_conv(hvb_ctx* ctx, const float* in_nchw_dev, const float* weight_ho
     HVB_CHECK_CTX(ctx);
     HVB_ARG(in_nchw_dev && weight_host && out_nhwc_dev && n >= 0 && h > 0 && w > 0, "bad arguments");
     if (n == 0) return HVB_OK;
-    HVB_ARG(n <= 65535 && (h + 1) / 2 <= 65535, "grid extent");
+    HVB_ARG(n <= 65535 && (h + 1) / 2 <= 65535 * 4, "grid extent");
     switch (c_out) {
         case 16: return launch_stem<16>(ctx, in_nchw_dev, weight_host, bias_host, n, h, w, out_nhwc_dev);
         case 32: return launch_stem<32>(ctx, in_nchw_dev, weight_host, bias_host, n, h, w, out_nhwc_dev);
