@@ -11,7 +11,9 @@
 //                         upsampled by 2^s — nn.Upsample(2,'nearest') + Concat of the yolov8.yaml neck
 //   stem_conv_kernel      layer 0: 3x3 stride-2 convolution of the NCHW letterbox output (K1) straight
 //                         to NHWC with bias + SiLU — exact fp32 FMA, weights as kernel parameters
-//                         (constant bank operands), one block = 128 output pixels of one row
+//                         (constant bank operands), one block = 128 output pixels x 8 rows, the next
+//                         row's input prefetched into registers while the current row's FMAs run
+//   sppf_pool_concat_kernel  SPPF's three cascaded 5x5 max-pools + concat on an on-chip tile
 //
 // All three are HBM-bound streaming kernels: 128-bit accesses, 4 independent vectors in flight per
 // thread, grid sized to the data.  Layout everywhere: NHWC ("channels_last") float32.
@@ -181,7 +183,10 @@ concat_nhwc_kernel(const CatArgs a) {
 constexpr int STEM_PX = HVB_STEM_PX;         // output pixels (one row segment) per block = threads per block
 template <int CO> struct StemParams { float w[27 * CO]; float b[CO]; };   // w index: ((ci*3+ky)*3+kx)*CO + co
 
-constexpr int STEM_ROWS = 4;                 // output rows per block: amortises the block start-up and lets row r+1's loads fly under row r's FMAs
+#ifndef HVB_STEM_ROWS
+#define HVB_STEM_ROWS 8
+#endif
+constexpr int STEM_ROWS = HVB_STEM_ROWS;                 // output rows per block: amortises the block start-up and lets row r+1's loads fly under row r's FMAs
 
 template <int CO>
 __global__ void __launch_bounds__(STEM_PX)
