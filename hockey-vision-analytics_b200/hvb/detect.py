@@ -39,7 +39,7 @@ class Detector:
     def __init__(self, model: torch.nn.Module, device="cuda:0", imgsz: int = 1280, conf: float = 0.4, iou: float = 0.7,
                  max_det: int = 300, agnostic_nms: bool = False, class_names: Optional[Dict[int, str]] = None,
                  autocast_dtype: Optional[torch.dtype] = None, channels_last: bool = False, fuse: bool = False,
-                 glue: Optional[bool] = None, cuda_graph: Optional[bool] = False):
+                 glue: Optional[bool] = None, cuda_graph: Optional[bool] = False, exact_silu: bool = False):
         self.ctx: Context = get_context(device)
         self.device = self.ctx.device
         if fuse:
@@ -59,7 +59,8 @@ class Detector:
         self.runner = None
         if glue:
             from .models.fused import FusedYOLOv8
-            self.runner = FusedYOLOv8(self.model, self.ctx)
+            # exact_silu=True: expf + IEEE division (torch's formula) instead of the approximate-unit SiLU (<= 1e-6 relative)
+            self.runner = FusedYOLOv8(self.model, self.ctx, exact_silu=exact_silu)
         self.imgsz, self.conf, self.iou, self.max_det, self.agnostic = imgsz, conf, iou, max_det, agnostic_nms
         self.autocast_dtype = autocast_dtype
         self.class_names = class_names or {i: str(i) for i in range(self.nc)}
