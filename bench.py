@@ -393,7 +393,16 @@ def run_hvb(args, rank, world):
         t0 = time.perf_counter()
         ref.step(frames[:nf], boxes[fidx < nf], fidx[fidx < nf])
         dt = time.perf_counter() - t0
-        cpu = {"value": nf / dt, "unit": UNIT, "cores": cores, "kind": "port",
+        # per-core normalisation: the same path on ONE host thread, one frame
+        import cv2
+        cv_threads = cv2.getNumThreads()
+        torch.set_num_threads(1); cv2.setNumThreads(1)
+        t0 = time.perf_counter()
+        ref.step(frames[:1], boxes[fidx == 0], fidx[fidx == 0])
+        dt1 = time.perf_counter() - t0
+        torch.set_num_threads(cores); cv2.setNumThreads(cv_threads)
+        cpu = {"value": nf / dt, "unit": UNIT, "cores": cores, "kind": "port", "torch_threads": cores, "cv2_threads": cv_threads,
+               "value_1_thread": 1.0 / dt1,
                "sample": "%d of the %d synthetic 1080p frames of one step, same stages on the host: cv2 letterbox, YOLOv8m "
                          "CPU forward (torch, %d threads), restated decode + real torchvision NMS, reference colour + "
                          "MobileNetV3 features, predict" % (nf, F, cores)}
