@@ -10,7 +10,9 @@
 // i.e. ONE kind::tf32 GEMM with K' = 3*Dp, accumulated in fp32 in TMEM.  k4_affinity.cu then
 // recomputes in float64 the few pairs whose affinity does not underflow.
 //
-// Kernel shape (one CTA per 128x128 output tile, cta_group::1):
+// Kernel shape (one CTA per 128x128 output tile ON OR ABOVE THE DIAGONAL — G is symmetric, the mirrored tile is
+// written by the same epilogue, which halves the tensor work: N=2000 is 136 tiles = one wave of the 148 SMs;
+// cta_group::1):
 //   warp 0   TMA producer: cp.async.bulk.tensor.2d loads of a 128x32-float A tile and B tile per
 //            stage (128-byte swizzle), completion on an mbarrier (expect_tx)
 //   warp 1   MMA issuer: one thread issues 4 tcgen05.mma.kind::tf32 (M128,N128,K8) per stage,
@@ -99,8 +101,12 @@ gram_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap, float* __restrict_
     uint8_t* smem_b = smem + kStages * kTileBytes;
     SharedCtl* ctl = (SharedCtl*)(smem + 2 * kStages * kTileBytes);
 
+    // G is symmetric: only tiles on or above the diagonal are computed, each one is also stored transposed
+    // (the whole CTA leaves before touching any barrier or TMEM, so this is safe)
+    if (blockIdx.x < blockIdx.y) return;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int bm = blockIdx.y * kBM, bn = blockIdx.x * kBN;
+    const bool mirror = bm != bn;
     const int kb_per_seg = dp / kBK, num_kb = 3 * kb_per_seg;
 
     if (threadIdx.x == 0) {
@@ -180,6 +186,12 @@ gram_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap, float* __restrict_
 #pragma unroll
                     for (int j = 0; j < 32; j++)
                         if (bn + c + j < n) o[j] = __uint_as_float(v[j]);
+                }
+                if (mirror) {                            // G[col][row]: lanes hold consecutive rows -> coalesced 128-byte stores
+                    float* t = G + (int64_t)(bn + c) * n + row;
+#pragma unroll
+                    for (int j = 0; j < 32; j++)
+                        if (bn + c + j < n) t[(int64_t)j * n] = __uint_as_float(v[j]);
                 }
             }
         }
