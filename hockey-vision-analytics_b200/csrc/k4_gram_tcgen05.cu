@@ -27,7 +27,10 @@
 namespace {
 
 constexpr int kBM = 128, kBN = 128, kBK = 32;        // tile; kBK floats = 128 bytes = one swizzle atom
-constexpr int kStages = 3;
+#ifndef HVB_GRAM_STAGES
+#define HVB_GRAM_STAGES 3
+#endif
+constexpr int kStages = HVB_GRAM_STAGES;
 constexpr int kTileBytes = kBM * kBK * 4;             // 16 KB per operand tile
 constexpr int kThreads = 256;
 constexpr uint32_t kTmemCols = 128;
