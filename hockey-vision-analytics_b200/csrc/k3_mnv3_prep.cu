@@ -40,7 +40,7 @@ struct SmemT {
     int blk[4];
 };
 constexpr int kFastK = 8, kFastRows = 96;         // ROI up to 192 x 384 px (scale <= 3 per axis)
-constexpr int kStageBytes = 16384;                // staged source rows of one row block (fast kernel)
+constexpr int kStageBytes = 20480;                // staged source rows of one row block (fast kernel)
 constexpr int kGenK = 48, kGenRows = 256;         // ROI up to ~1400 x 2900 px
 
 // Pillow precompute_coeffs + normalize_coeffs_8bpc for output sample `o` (bilinear, support 1).
@@ -101,7 +101,7 @@ struct SmemFast {
     int kh[kOutW * kFastK];
     int kv[kOutH * kFastK];
     float lut[3][256];
-    uint32_t inter[kFastRows * kOutW];  // horizontally resized rows as pixel words c0 | c1 << 8 | c2 << 16
+    uint8_t inter[kFastRows * kOutW * 3];
     uint32_t roi[kStageBytes / 4];      // staged source rows: row r at byte r * pitch_s, ROI byte 0 at + shift_r
     int blk[4];
 };
@@ -191,40 +191,32 @@ mnv3_prep_fast_kernel(const uint8_t* __restrict__ pixels, const hvb_crop_desc* _
             // ---- horizontal pass out of shared memory: rows [r_lo, r_hi) -> inter[row - r_lo][xx][c]
             const uint8_t* sroi = reinterpret_cast<const uint8_t*>(S.roi);
             const int sh0 = (int)(reinterpret_cast<uintptr_t>(base + (int64_t)r_lo * cd.pitch) & 3), dsh = cd.pitch & 3;
-            {
-                // thread <-> one output column xx (kThreads is a multiple of kOutW): bounds and coefficients live in
-                // registers for the whole block of rows; one packed 32-bit store per intermediate pixel
-                const int xx = threadIdx.x & (kOutW - 1);
-                const int xmin3 = S.bh[xx][0] * 3, cnt = S.bh[xx][1];
-                int kx[kFastK];
-#pragma unroll
-                for (int x = 0; x < kFastK; x++) kx[x] = x < cnt ? S.kh[xx * ksh + x] : 0;
-                for (int row = threadIdx.x >> 6; row < nrows; row += kThreads / kOutW) {
-                    const uint8_t* src = sroi + row * pitch_s + ((sh0 + row * dsh) & 3) + xmin3;
-                    int s0 = 1 << (kPrecision - 1), s1 = s0, s2 = s0;
-#pragma unroll
-                    for (int x = 0; x < kFastK; x++) {
-                        if (x < cnt) { s0 += src[3 * x] * kx[x]; s1 += src[3 * x + 1] * kx[x]; s2 += src[3 * x + 2] * kx[x]; }
-                    }
-                    S.inter[row * kOutW + xx] = (uint32_t)clip8(s0) | ((uint32_t)clip8(s1) << 8) | ((uint32_t)clip8(s2) << 16);
+            for (int it = threadIdx.x; it < nrows * kOutW; it += kThreads) {
+                const int row = it >> 6, xx = it & (kOutW - 1);
+                const int xmin = S.bh[xx][0], cnt = S.bh[xx][1];
+                const uint8_t* src = sroi + row * pitch_s + ((sh0 + row * dsh) & 3) + xmin * 3;
+                const int* k = S.kh + xx * ksh;
+                int s0 = 1 << (kPrecision - 1), s1 = s0, s2 = s0;
+                for (int x = 0; x < cnt; x++) {
+                    const int kk = k[x];
+                    s0 += src[3 * x] * kk; s1 += src[3 * x + 1] * kk; s2 += src[3 * x + 2] * kk;
                 }
+                uint8_t* d = S.inter + (row * kOutW + xx) * 3;
+                d[0] = (uint8_t)clip8(s0); d[1] = (uint8_t)clip8(s1); d[2] = (uint8_t)clip8(s2);
             }
             __syncthreads();
             // ---- vertical pass: output rows [y0, y1)
-            {
-                const int x = threadIdx.x & (kOutW - 1);
-                for (int y = y0 + (threadIdx.x >> 6); y < y1; y += kThreads / kOutW) {
-                    const int ymin = S.bv[y][0], cnt = S.bv[y][1];         // warp-uniform: broadcast loads
-                    const int* k = S.kv + y * ksv;
-                    const uint32_t* src = S.inter + (ymin - r_lo) * kOutW + x;
-                    int s0 = 1 << (kPrecision - 1), s1 = s0, s2 = s0;
-                    for (int t = 0; t < cnt; t++) {
-                        const int kk = k[t];
-                        const uint32_t p = src[t * kOutW];
-                        s0 += (int)(p & 255u) * kk; s1 += (int)((p >> 8) & 255u) * kk; s2 += (int)(p >> 16) * kk;
-                    }
-                    write_out(S.lut, o, o8, y, x, clip8(s0), clip8(s1), clip8(s2));
+            for (int it = threadIdx.x; it < (y1 - y0) * kOutW; it += kThreads) {
+                const int y = y0 + (it >> 6), x = it & (kOutW - 1);
+                const int ymin = S.bv[y][0], cnt = S.bv[y][1];
+                const int* k = S.kv + y * ksv;
+                const uint8_t* src = S.inter + ((ymin - r_lo) * kOutW + x) * 3;
+                int s0 = 1 << (kPrecision - 1), s1 = s0, s2 = s0;
+                for (int t = 0; t < cnt; t++) {
+                    const int kk = k[t];
+                    s0 += src[t * kOutW * 3] * kk; s1 += src[t * kOutW * 3 + 1] * kk; s2 += src[t * kOutW * 3 + 2] * kk;
                 }
+                write_out(S.lut, o, o8, y, x, clip8(s0), clip8(s1), clip8(s2));
             }
             __syncthreads();
             y0 = y1;
