@@ -27,6 +27,8 @@
 namespace {
 
 constexpr int kBM = 128, kBN = 128, kBK = 32;        // tile; kBK floats = 128 bytes = one swizzle atom
+// 3 stages = 96 KB of operand tiles: two CTAs co-reside per SM, so one CTA's epilogue overlaps the other's main loop.
+// Measured at N=8192: 297 us with 3 stages, 389 us with 4 or 6 (one CTA per SM).
 #ifndef HVB_GRAM_STAGES
 #define HVB_GRAM_STAGES 3
 #endif
