@@ -28,6 +28,9 @@ class HotPath:
                  channels_last: bool = True, autocast_dtype: Optional[torch.dtype] = None, overlap_team: bool = True):
         from .models import build_trunk, build_yolov8
         self.ctx = get_context(device)
+        import os
+        if os.environ.get("HVB_CUDNN_BENCHMARK_LIMIT") is not None:      # 0 = let cuDNN's autotuner try every algorithm
+            torch.backends.cudnn.benchmark_limit = int(os.environ["HVB_CUDNN_BENCHMARK_LIMIT"])
         # The team stage (K3a/K3b, MobileNetV3, K4a: ~170 small launches, 2 ms) underfills the GPU; when its boxes are
         # already known (tracker output / previous chunk) it runs on a high-priority side stream next to the detection
         # stage (large HBM-bound kernels) instead of after it.
