@@ -332,6 +332,18 @@ def run_hvb(args, rank, world):
                 path.detector.detect_players(one)
             extra["frame_at_a_time_detect_fps_" + tag] = 20 / (time.perf_counter() - t0)
         path.detector.cuda_graph = False
+        # the whole-loop drop-in on a clip (hvb.VideoProcessor.process_video_chunked: detection per chunk, ByteTrack per
+        # frame on the host, team features per chunk).  Random-init YOLO detects nothing above conf 0.4, so this times the
+        # driver + detection path; the tracker / team stages see empty inputs.
+        from hvb.video import Config, VideoProcessor
+        from hvb.models import build_yolov8
+        vp = VideoProcessor(build_yolov8("m", 2, 0), dev, Config(), team_classifier=path.classifier_router())
+        clip = [frames[i % F] for i in range(2 * F)]
+        list(vp.process_video_chunked(clip[:F], chunk=F, initialize=False))
+        t0 = time.perf_counter()
+        n_out = len(list(vp.process_video_chunked(clip, chunk=F, initialize=False)))
+        extra["clip_chunked_drop_in_fps"] = n_out / (time.perf_counter() - t0)
+        del vp
     if args.with_4k:
         from hvb.synth import rink_frame
         rng = np.random.default_rng(7 + rank)

@@ -69,6 +69,7 @@ class Detector:
         # None = automatic: on when the forward is the K5 runner (known to be capturable: no host synchronisation inside).
         self.cuda_graph = (self.runner is not None) if cuda_graph is None else bool(cuda_graph)
         self._graphs: Dict[Tuple, object] = {}
+        self._staging: Dict[Tuple, dict] = {}
         self._plans: Dict[Tuple, LetterboxPlan] = {}
         self._meta: Dict[Tuple, torch.Tensor] = {}
 
@@ -81,13 +82,37 @@ class Detector:
         return self._plans[key]
 
     def upload(self, frames) -> torch.Tensor:
-        """Host uint8[n,H,W,3] -> device (through a pinned staging tensor); device tensors pass through."""
-        frames = _as_frames(frames)
+        """Host frames -> device uint8[n,H,W,3]; device tensors pass through.  `frames` is one frame, an array
+        [n,H,W,3] or a sequence of equally sized frames (numpy views are fine).  They are copied frame by frame into a
+        PERSISTENT pinned staging buffer (one per shape, two alternating so that the previous asynchronous H2D copy is
+        never overwritten) — pinning a fresh 200 MB buffer per chunk costs more than the whole GPU step."""
         if isinstance(frames, torch.Tensor):
-            return frames.to(self.device).contiguous()
-        frames = np.ascontiguousarray(frames)
-        pinned = torch.from_numpy(frames).pin_memory() if torch.cuda.is_available() else torch.from_numpy(frames)
-        return pinned.to(self.device, non_blocking=True)
+            return _as_frames(frames).to(self.device).contiguous()
+        if isinstance(frames, np.ndarray):
+            frames = _as_frames(frames)
+        n = len(frames)
+        h, w = frames[0].shape[:2]
+        key = (n, h, w)
+        slot = self._staging.get(key)
+        if slot is None:
+            slot = self._staging[key] = {"bufs": [torch.empty((n, h, w, 3), dtype=torch.uint8).pin_memory() for _ in range(2)],
+                                         "events": [None, None], "next": 0}
+        i = slot["next"]
+        slot["next"] = i ^ 1
+        if slot["events"][i] is not None:
+            slot["events"][i].synchronize()                 # the H2D copy that last used this buffer has finished
+        buf = slot["bufs"][i]
+        view = buf.numpy()
+        if isinstance(frames, np.ndarray):
+            np.copyto(view, frames)
+        else:
+            for k, f in enumerate(frames):
+                np.copyto(view[k], f)
+        dev = buf.to(self.device, non_blocking=True)
+        ev = torch.cuda.Event()
+        ev.record()
+        slot["events"][i] = ev
+        return dev
 
     def forward_heads(self, x: torch.Tensor) -> List[torch.Tensor]:
         """Backbone forward (PyTorch).  Returns the 3 raw head tensors as contiguous float32 NCHW."""

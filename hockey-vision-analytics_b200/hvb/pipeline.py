@@ -43,6 +43,14 @@ class HotPath:
         self.classifier = HybridTeamClassifier(device=device, trunk=trunk if trunk is not None else build_trunk(seed, calibrate=True),
                                                affinity_mode=affinity_mode)
 
+    def classifier_router(self):
+        """A TeamClassifier (the reference's router class) that routes to this path's fitted hybrid classifier."""
+        from .team import TeamClassifier
+        tc = TeamClassifier.__new__(TeamClassifier)
+        TeamClassifier.__init__(tc, device=str(self.ctx.device), use_hybrid=False)
+        tc.use_hybrid, tc.hybrid_classifier = True, self.classifier
+        return tc
+
     # ------------------------------------------------------------------ one-off fit (per clip)
     def fit_from_frames(self, frames_dev: torch.Tensor, boxes: torch.Tensor, frame_idx: torch.Tensor):
         feats, raw, _ = self.classifier.features_from_frame(frames_dev, boxes, frame_idx)

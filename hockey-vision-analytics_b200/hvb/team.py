@@ -145,7 +145,7 @@ class TeamClassifier:
         from .detections import crop_image
         fi = frame_idx.cpu().numpy() if frame_idx is not None else np.zeros(xyxy.shape[0], np.int64)
         boxes = xyxy.cpu().numpy() if hasattr(xyxy, "cpu") else np.asarray(xyxy)
-        frames = host_frames if host_frames.ndim == 4 else host_frames[None]
+        frames = host_frames if isinstance(host_frames, (list, tuple)) or host_frames.ndim == 4 else host_frames[None]
         return self.predict([crop_image(frames[int(f)], b) for f, b in zip(fi, boxes)], tracker_ids)
 
     def get_segmentation_masks(self, tracker_ids: List[int]):

@@ -138,7 +138,7 @@ class VideoProcessor:
             self.initialize_team_classifier(frames)
         det, conf = self.detector, self.config.detection_confidence
         for lo in range(0, len(frames), chunk):
-            block = np.ascontiguousarray(np.stack(frames[lo:lo + chunk]))
+            block = frames[lo:lo + chunk]                               # a list of frames: staged without an extra copy
             frames_dev = det.upload(block)
             xyxy, cf, cl, cnt, state = det.detect_device(frames_dev)
             cnt_h = cnt.cpu().numpy()
@@ -160,7 +160,7 @@ class VideoProcessor:
             if boxes:                                                   # one feature pass for every tracked player of the chunk
                 team_ids = self.team_classifier.predict_from_frame(
                     frames_dev, torch.from_numpy(np.concatenate(boxes)), torch.from_numpy(np.concatenate(fidx)).to(det.device),
-                    tracker_ids=np.concatenate(tids), host_frames=block)
+                    tracker_ids=np.concatenate(tids), host_frames=block)          # host frames only for the fallback cascade
             pos = 0
             for players, goalies in per_frame:
                 n = len(players)
