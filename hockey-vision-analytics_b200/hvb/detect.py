@@ -102,12 +102,11 @@ class Detector:
         if slot["events"][i] is not None:
             slot["events"][i].synchronize()                 # the H2D copy that last used this buffer has finished
         buf = slot["bufs"][i]
-        view = buf.numpy()
-        if isinstance(frames, np.ndarray):
-            np.copyto(view, frames)
+        if isinstance(frames, np.ndarray):                  # torch's CPU copy is vectorised and multi-threaded for large tensors
+            buf.copy_(torch.from_numpy(frames))
         else:
             for k, f in enumerate(frames):
-                np.copyto(view[k], f)
+                buf[k].copy_(torch.from_numpy(f))
         dev = buf.to(self.device, non_blocking=True)
         ev = torch.cuda.Event()
         ev.record()
