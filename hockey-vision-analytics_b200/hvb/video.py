@@ -133,18 +133,62 @@ class VideoProcessor:
             yield self.process_frame(frame)
 
     def process_video_chunked(self, frames: Sequence[np.ndarray], chunk: int = 32, initialize: bool = True) -> Iterator[FrameResult]:
-        """Same results as process_video, GPU work batched per chunk of frames (see the module docstring)."""
+        """Same results as process_video, GPU work batched per chunk of frames (see the module docstring).
+
+        Three things run concurrently: a staging thread copies chunk i+1 into a pinned buffer and starts its H2D copy on
+        a side stream; the GPU detects chunk i (its results leave through an asynchronous D2H copy + an event); the main
+        thread runs ByteTrack and the team stage of chunk i-1.  Results are yielded in frame order."""
+        import queue
+        import threading
         if initialize:
             self.initialize_team_classifier(frames)
         det, conf = self.detector, self.config.detection_confidence
-        for lo in range(0, len(frames), chunk):
-            block = frames[lo:lo + chunk]                               # a list of frames: staged without an extra copy
-            frames_dev = det.upload(block)
-            xyxy, cf, cl, cnt, state = det.detect_device(frames_dev)
-            cnt_h = cnt.cpu().numpy()
-            if (cnt_h < 0).any():
-                cnt_h = det._retry_overflow(xyxy, cf, cl, cnt, state, cnt_h)
-            xyxy_h, cf_h, cl_h = xyxy.cpu().numpy(), cf.cpu().numpy(), cl.cpu().numpy()
+        dev = det.device
+        main = torch.cuda.current_stream(dev)
+        copy_stream = torch.cuda.Stream(device=dev)
+        starts = list(range(0, len(frames), chunk))
+        q: "queue.Queue" = queue.Queue(maxsize=2)
+
+        def stager():
+            try:
+                with torch.cuda.device(dev):
+                    for lo in starts:
+                        block = frames[lo:lo + chunk]                   # a list of frames: staged without an extra copy
+                        with torch.cuda.stream(copy_stream):
+                            fd = det.upload(block)
+                            ev = torch.cuda.Event()
+                            ev.record(copy_stream)
+                        q.put((block, fd, ev))
+                q.put(None)
+            except BaseException as e:                                  # noqa: BLE001 - surfaced in the consumer
+                q.put(e)
+
+        threading.Thread(target=stager, daemon=True).start()
+        pinned = [dict(), dict()]
+
+        def launch(ci, item):
+            block, frames_dev, ready = item
+            main.wait_event(ready)
+            frames_dev.record_stream(main)
+            xyxy, cf, cl, cnt, _state = det.detect_device(frames_dev)
+            host = pinned[ci & 1]
+            for k, t in (("xyxy", xyxy), ("conf", cf), ("cls", cl), ("count", cnt)):
+                if k not in host or host[k].shape != t.shape:
+                    host[k] = torch.empty(t.shape, dtype=t.dtype).pin_memory()
+                host[k].copy_(t, non_blocking=True)                    # stream-ordered before the next graph replay
+            done = torch.cuda.Event()
+            done.record(main)
+            return block, frames_dev, host, done
+
+        def finish(p):
+            block, frames_dev, host, done = p
+            done.synchronize()
+            cnt_h = host["count"].numpy().copy()
+            xyxy_h, cf_h, cl_h = host["xyxy"].numpy(), host["conf"].numpy(), host["cls"].numpy()
+            if (cnt_h < 0).any():                                       # > 1024 candidates in a frame: redo eagerly with the retry tier
+                xyxy, cf, cl, cnt, state = det.detect_device(frames_dev, graph=False)
+                cnt_h = det._retry_overflow(xyxy, cf, cl, cnt, state, cnt.cpu().numpy())
+                xyxy_h, cf_h, cl_h = xyxy.cpu().numpy(), cf.cpu().numpy(), cl.cpu().numpy()
             per_frame, boxes, fidx, tids = [], [], [], []
             for i, k in enumerate(cnt_h):                             # ByteTrack: strictly sequential per frame
                 d = det._to_detections(xyxy_h[i, :k], cf_h[i, :k], cl_h[i, :k])
@@ -159,13 +203,27 @@ class VideoProcessor:
             team_ids = np.array([])
             if boxes:                                                   # one feature pass for every tracked player of the chunk
                 team_ids = self.team_classifier.predict_from_frame(
-                    frames_dev, torch.from_numpy(np.concatenate(boxes)), torch.from_numpy(np.concatenate(fidx)).to(det.device),
+                    frames_dev, torch.from_numpy(np.concatenate(boxes)), torch.from_numpy(np.concatenate(fidx)).to(dev),
                     tracker_ids=np.concatenate(tids), host_frames=block)          # host frames only for the fallback cascade
-            pos = 0
+            out, pos = [], 0
             for players, goalies in per_frame:
                 n = len(players)
-                yield self._finish(players, goalies, team_ids[pos:pos + n] if n else np.array([]))
+                out.append(self._finish(players, goalies, team_ids[pos:pos + n] if n else np.array([])))
                 pos += n
+            return out
+
+        pending, ci = None, 0
+        while True:
+            item = q.get()
+            if isinstance(item, BaseException):
+                raise item
+            nxt = launch(ci, item) if item is not None else None        # chunk ci is queued on the GPU ...
+            ci += 1
+            if pending is not None:
+                yield from finish(pending)                              # ... while the host finishes chunk ci-1
+            pending = nxt
+            if item is None:
+                break
 
     # ------------------------------------------------------------------ main.py:324-358
     @staticmethod
