@@ -338,7 +338,7 @@ def run_hvb(args, rank, world):
         from hvb.video import Config, VideoProcessor
         from hvb.models import build_yolov8
         vp = VideoProcessor(build_yolov8("m", 2, 0), dev, Config(), team_classifier=path.classifier_router())
-        clip = [frames[i % F] for i in range(2 * F)]
+        clip = [frames[i % F] for i in range(6 * F)]
         list(vp.process_video_chunked(clip[:F], chunk=F, initialize=False))
         t0 = time.perf_counter()
         n_out = len(list(vp.process_video_chunked(clip, chunk=F, initialize=False)))
