@@ -131,6 +131,8 @@ class CpuReferencePath:
         self.trunk = build_trunk(0, calibrate=True)
         self.ref = tr.HybridReference(self.trunk)
         self.fitted = False
+        self.stage_s = {"letterbox+preprocess": 0.0, "yolo_forward": 0.0, "decode+nms+scale": 0.0, "crops+team_predict": 0.0}
+        self.stage_frames = 0
 
     def fit(self, frames, boxes, fidx):
         from oracle.supervision_restated import crop_image
@@ -143,15 +145,28 @@ class CpuReferencePath:
         from oracle.supervision_restated import crop_image
         torch = self.torch
         out = []
+        st = self.stage_s
         for i, frame in enumerate(frames):
+            t0 = time.perf_counter()
             lb = ur.letterbox(frame, 1280, auto=True)
             x = torch.from_numpy(ur.preprocess([lb]))
+            t1 = time.perf_counter()
             with torch.no_grad():
                 heads = self.yolo(x)
+            t2 = time.perf_counter()
             det = ur.predict_from_head(heads, 2, tuple(x.shape[2:]), [frame.shape[:2]], 0.4)[0]
+            t3 = time.perf_counter()
             crops = [crop_image(frame, b) for b in boxes[fidx == i]]
             out.append((det, self.ref.predict(crops)))
+            t4 = time.perf_counter()
+            st["letterbox+preprocess"] += t1 - t0; st["yolo_forward"] += t2 - t1
+            st["decode+nms+scale"] += t3 - t2; st["crops+team_predict"] += t4 - t3
+            self.stage_frames += 1
         return out
+
+    def stage_ms_per_frame(self):
+        n = max(self.stage_frames, 1)
+        return {k: round(1e3 * v / n, 3) for k, v in self.stage_s.items()}
 
 
 def run_reference(args, rank, world):
@@ -176,7 +191,7 @@ def run_reference(args, rank, world):
         "vs_baseline": None, "dtype": "u8/f32", "data": "synthetic",
         "config": {"workload": "C2+C3 1080p player detection + team classification, CPU reference path",
                    "frames_per_step": int(len(frames)), "players_per_frame": PLAYERS, "team_boxes": "planted"},
-        "cpu_baseline": {"value": fps, "unit": UNIT, "cores": cores, "kind": "port",
+        "cpu_baseline": {"value": fps, "unit": UNIT, "cores": cores, "kind": "port", "stage_ms_per_frame": path.stage_ms_per_frame(),
                          "sample": "%d synthetic 1080p frames per step: cv2 letterbox + YOLOv8m CPU forward + restated "
                                    "decode/torchvision NMS + reference colour/MobileNetV3 features + predict" % len(frames)},
         "e2e": {"value": fps, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
@@ -402,9 +417,11 @@ def run_hvb(args, rank, world):
         nf = args.ref_frames
         ref.fit(frames[:nf], boxes[fidx < nf], fidx[fidx < nf])
         ref.step(frames[:1], boxes[fidx == 0], fidx[fidx == 0])
+        ref.stage_s = {k: 0.0 for k in ref.stage_s}; ref.stage_frames = 0
         t0 = time.perf_counter()
         ref.step(frames[:nf], boxes[fidx < nf], fidx[fidx < nf])
         dt = time.perf_counter() - t0
+        stage_ms = ref.stage_ms_per_frame()
         # per-core normalisation: the same path on ONE host thread, one frame
         import cv2
         cv_threads = cv2.getNumThreads()
@@ -414,7 +431,7 @@ def run_hvb(args, rank, world):
         dt1 = time.perf_counter() - t0
         torch.set_num_threads(cores); cv2.setNumThreads(cv_threads)
         cpu = {"value": nf / dt, "unit": UNIT, "cores": cores, "kind": "port", "torch_threads": cores, "cv2_threads": cv_threads,
-               "value_1_thread": 1.0 / dt1,
+               "value_1_thread": 1.0 / dt1, "stage_ms_per_frame": stage_ms,
                "sample": "%d of the %d synthetic 1080p frames of one step, same stages on the host: cv2 letterbox, YOLOv8m "
                          "CPU forward (torch, %d threads), restated decode + real torchvision NMS, reference colour + "
                          "MobileNetV3 features, predict" % (nf, F, cores)}
