@@ -181,6 +181,25 @@ class ByteTrack:
                     self._ext[i] = self._next_external
                     self._next_external += 1
 
+    def _hit_many(self, tr: np.ndarray, scores: np.ndarray, was_tracked: np.ndarray):
+        """STrack.update / re_activate bookkeeping for the tracks matched in one association round (already corrected by
+        _correct_many), vectorised; external ids are still handed out in match order."""
+        if len(tr) == 0:
+            return
+        self._state[tr] = _TRACKED
+        self._frame[tr] = self.frame_id
+        self._score[tr] = scores
+        self._len[tr[~was_tracked]] = 0
+        up = tr[was_tracked]
+        self._len[up] += 1
+        newly = up[self._len[up] == self.minimum_consecutive_frames]
+        if len(newly):
+            self._activated[newly] = True
+            for t in newly:
+                if self._ext[t] == -1:
+                    self._ext[t] = self._next_external
+                    self._next_external += 1
+
     # ------------------------------------------------------------------ one frame
     def _step(self, xyxy: np.ndarray, scores: np.ndarray) -> List[int]:
         return self._drive(self._step_gen(xyxy, scores))
@@ -208,19 +227,22 @@ class ByteTrack:
         det_box = det_tlwh.copy()
         det_box[:, 2:] += det_box[:, :2]                    # float32 tlbr exactly as STrack.tlbr gives it
 
-        unconfirmed = [t for t in self.tracked if not self._activated[t]]
-        confirmed = [t for t in self.tracked if self._activated[t]]
-        pool = confirmed + [t for t in self.lost if t not in set(confirmed)]
+        act = self._activated
+        unconfirmed = [t for t in self.tracked if not act[t]]
+        confirmed = [t for t in self.tracked if act[t]]
+        cset = set(confirmed)
+        pool = confirmed + [t for t in self.lost if t not in cset]
         self._predict(pool)
 
         # round 1: all confirmed + lost tracks vs high-score detections, IoU fused with the score
         m, u_trk, u_det = _assign((yield (self._tlbr(pool), det_box, det_s.astype(np.float64))), self.minimum_matching_threshold)
-        self._correct_many([pool[it] for it, _ in m], self._xyah(det_tlwh[[idt for _, idt in m]]))
-        for it, idt in m:
-            t = pool[it]
-            was_tracked = self._state[t] == _TRACKED
-            self._hit(t, det_tlwh[idt], det_s[idt], reactivate=not was_tracked, corrected=True)
-            (activated if was_tracked else refind).append(t)
+        tr1 = np.asarray([pool[it] for it, _ in m], dtype=np.int64)
+        di1 = np.asarray([idt for _, idt in m], dtype=np.int64)
+        self._correct_many(tr1.tolist(), self._xyah(det_tlwh[di1]))
+        was1 = self._state[tr1] == _TRACKED
+        self._hit_many(tr1, det_s[di1], was1)
+        activated.extend(tr1[was1].tolist())
+        refind.extend(tr1[~was1].tolist())
 
         # round 2: still-tracked leftovers vs low-score detections
         lo_xyxy, lo_s = xyxy[lo].astype(np.float32), scores[lo]
@@ -230,11 +252,11 @@ class ByteTrack:
         lo_box[:, 2:] += lo_box[:, :2]
         rest = [pool[i] for i in u_trk if self._state[pool[i]] == _TRACKED]
         m2, u_rest, _ = _assign((yield (self._tlbr(rest), lo_box, None)), 0.5)
-        self._correct_many([rest[it] for it, _ in m2], self._xyah(lo_tlwh[[idt for _, idt in m2]]))
-        for it, idt in m2:
-            t = rest[it]
-            self._hit(t, lo_tlwh[idt], lo_s[idt], reactivate=False, corrected=True)
-            activated.append(t)
+        tr2 = np.asarray([rest[it] for it, _ in m2], dtype=np.int64)
+        di2 = np.asarray([idt for _, idt in m2], dtype=np.int64)
+        self._correct_many(tr2.tolist(), self._xyah(lo_tlwh[di2]))
+        self._hit_many(tr2, lo_s[di2], np.ones(len(tr2), bool))
+        activated.extend(tr2.tolist())
         for it in u_rest:
             t = rest[it]
             if self._state[t] != _LOST:
@@ -244,11 +266,11 @@ class ByteTrack:
         # round 3: unconfirmed tracks vs the remaining high-score detections
         rem = list(u_det)
         m3, u_unc, u_rem = _assign((yield (self._tlbr(unconfirmed), det_box[rem], det_s[rem].astype(np.float64))), 0.7)
-        self._correct_many([unconfirmed[it] for it, _ in m3], self._xyah(det_tlwh[[rem[idt] for _, idt in m3]]))
-        for it, idt in m3:
-            t = unconfirmed[it]
-            self._hit(t, det_tlwh[rem[idt]], det_s[rem[idt]], reactivate=False, corrected=True)
-            activated.append(t)
+        tr3 = np.asarray([unconfirmed[it] for it, _ in m3], dtype=np.int64)
+        di3 = np.asarray([rem[idt] for _, idt in m3], dtype=np.int64)
+        self._correct_many(tr3.tolist(), self._xyah(det_tlwh[di3]))
+        self._hit_many(tr3, det_s[di3], np.ones(len(tr3), bool))
+        activated.extend(tr3.tolist())
         for it in u_unc:
             self._state[unconfirmed[it]] = _REMOVED
             removed.append(unconfirmed[it])
