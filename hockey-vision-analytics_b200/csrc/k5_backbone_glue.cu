@@ -289,148 +289,6 @@ stem_conv_kernel(const float* __restrict__ in, float* __restrict__ out, int H, i
 }
 
 // ------------------------------------------------------------------------------------------------
-// Stem on the (legacy) tensor path, for inputs that are exactly k/255 with k an integer in [0,255] — what K1 writes.
-// The pixel value k is recovered exactly (rint(x*255)) and is an exact TF32 operand; the 1/255 moves into the weights,
-// which are split into two TF32 terms (hi + lo, the lo*k products keep the result within 2^-22 of fp32 arithmetic).
-// One warp = 32 output pixels = two m16n8k8 tiles per 8 output channels; K = 27 taps padded to 32; the B fragments
-// (weights) live in registers for the whole block, the A fragments come from the staged input window.  ~600 instead
-// of ~2600 instructions per 32 pixels at C0=48, which makes layer 0 HBM-bound instead of issue-bound.
-__device__ __forceinline__ uint32_t to_tf32(float x) {
-    uint32_t r;
-    asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(x));
-    return r;
-}
-__device__ __forceinline__ void mma_tf32(float (&d)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
-    asm volatile("mma.sync.aligned.m16n8k8.row.col.f32.tf32.tf32.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
-                 : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3])
-                 : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
-}
-
-template <int CO>
-__global__ void __launch_bounds__(STEM_PX)
-stem_conv_mma_kernel(const float* __restrict__ in, float* __restrict__ out, int H, int W, int OH, int OW,
-                     const __grid_constant__ StemParams<CO> prm) {
-    constexpr int NT = CO / 8;
-    __shared__ float s_ev[3][3][STEM_PX + 2];
-    __shared__ float s_od[3][3][STEM_PX + 2];
-    __shared__ float s_w[32 * CO];                                // w/255, tap-major, taps 27..31 zero
-    const int n = blockIdx.z, oy0 = blockIdx.y * STEM_ROWS, ox0 = blockIdx.x * STEM_PX;
-    const int t = threadIdx.x, lane = t & 31, warp = t >> 5, g = lane >> 2, tig = lane & 3;
-    const int ixw = 2 * ox0 - 2;
-    const bool pair_ok = (W & 1) == 0 && ((reinterpret_cast<uintptr_t>(in) & 7) == 0);
-    const size_t hw = (size_t)H * W;
-    const float* img = in + (size_t)n * 3 * hw;
-    const int ixa = ixw + 2 * t, ixb = ixw + 2 * (STEM_PX + t);
-    const bool a0 = ixa >= 0 && ixa < W, a1 = ixa + 1 >= 0 && ixa + 1 < W;
-    const bool b0 = t < 2 && ixb >= 0 && ixb < W, b1 = t < 2 && ixb + 1 >= 0 && ixb + 1 < W;
-
-    auto fetch = [&](int oy, int ix, bool c0, bool c1, float2 (&v)[9]) {
-#pragma unroll
-        for (int ky = 0; ky < 3; ++ky) {
-            const int iy = 2 * oy - 1 + ky;
-            const bool row_ok = iy >= 0 && iy < H;
-            const float* p = img + (size_t)(row_ok ? iy : 0) * W + ix;
-#pragma unroll
-            for (int ci = 0; ci < 3; ++ci) {
-                float2 r = make_float2(0.0f, 0.0f);
-                if (row_ok) {
-                    if (pair_ok && c0 && c1) {
-                        r = __ldg(reinterpret_cast<const float2*>(p + ci * hw));
-                    } else {
-                        if (c0) r.x = __ldg(p + ci * hw);
-                        if (c1) r.y = __ldg(p + ci * hw + 1);
-                    }
-                }
-                // the pixel value as an exact small integer (an exact TF32 operand)
-                v[ky * 3 + ci] = make_float2(rintf(__fmul_rn(r.x, 255.0f)), rintf(__fmul_rn(r.y, 255.0f)));
-            }
-        }
-    };
-    auto put = [&](int j, const float2 (&v)[9]) {
-#pragma unroll
-        for (int ky = 0; ky < 3; ++ky)
-#pragma unroll
-            for (int ci = 0; ci < 3; ++ci) { s_ev[ci][ky][j] = v[ky * 3 + ci].x; s_od[ci][ky][j] = v[ky * 3 + ci].y; }
-    };
-
-    float2 cur[9], ext[9];
-    fetch(oy0, ixa, a0, a1, cur);
-    if (t < 2) fetch(oy0, ixb, b0, b1, ext);
-    // weights / 255 into shared memory (tap-major), then this thread's B fragments into registers, split hi + lo
-    for (int i = t; i < 32 * CO; i += STEM_PX) s_w[i] = i < 27 * CO ? __fdiv_rn(prm.w[i], 255.0f) : 0.0f;
-    __syncthreads();
-    uint32_t bh[4][NT][2], bl[4][NT][2];
-#pragma unroll
-    for (int ks = 0; ks < 4; ++ks)
-#pragma unroll
-        for (int nt = 0; nt < NT; ++nt)
-#pragma unroll
-            for (int h2 = 0; h2 < 2; ++h2) {
-                const float wv = s_w[(8 * ks + tig + 4 * h2) * CO + 8 * nt + g];
-                const uint32_t hi = to_tf32(wv);
-                bh[ks][nt][h2] = hi;
-                bl[ks][nt][h2] = to_tf32(__fsub_rn(wv, __uint_as_float(hi)));
-            }
-    // shared-memory word offsets (relative to pixel 0) of this thread's two taps per k-step: tap kk -> (ci, ky, kx);
-    // kx = 0 -> s_od[ci][ky][p], kx = 1 -> s_ev[ci][ky][p + 1], kx = 2 -> s_od[ci][ky][p + 1]; kk >= 27 -> a zero word
-    const float* sbase[8];
-    bool svalid[8];
-#pragma unroll
-    for (int i = 0; i < 8; ++i) {
-        const int kk = 8 * (i >> 1) + tig + 4 * (i & 1);
-        svalid[i] = kk < 27;
-        const int kc = svalid[i] ? kk : 0;
-        const int ci = kc / 9, ky = (kc / 3) % 3, kx = kc % 3;
-        sbase[i] = (kx == 1 ? &s_ev[ci][ky][1] : kx == 0 ? &s_od[ci][ky][0] : &s_od[ci][ky][1]);
-    }
-    float bias2[NT][2];
-#pragma unroll
-    for (int nt = 0; nt < NT; ++nt) { bias2[nt][0] = prm.b[8 * nt + 2 * tig]; bias2[nt][1] = prm.b[8 * nt + 2 * tig + 1]; }
-
-    const int rows = min(STEM_ROWS, OH - oy0);
-    for (int r = 0; r < rows; ++r) {
-        const int oy = oy0 + r;
-        __syncthreads();                                          // every warp is done reading the previous row's window
-        put(t, cur);
-        if (t < 2) put(STEM_PX + t, ext);
-        if (r + 1 < rows) {
-            fetch(oy + 1, ixa, a0, a1, cur);
-            if (t < 2) fetch(oy + 1, ixb, b0, b1, ext);
-        }
-        __syncthreads();
-#pragma unroll
-        for (int mt = 0; mt < 2; ++mt) {
-            const int p0 = 32 * warp + 16 * mt;                   // first pixel of this m-tile inside the block
-            float acc[NT][4];
-#pragma unroll
-            for (int nt = 0; nt < NT; ++nt) { acc[nt][0] = acc[nt][2] = bias2[nt][0]; acc[nt][1] = acc[nt][3] = bias2[nt][1]; }
-#pragma unroll
-            for (int ks = 0; ks < 4; ++ks) {
-                uint32_t a[4];
-                a[0] = svalid[2 * ks] ? __float_as_uint(sbase[2 * ks][p0 + g]) : 0u;
-                a[1] = svalid[2 * ks] ? __float_as_uint(sbase[2 * ks][p0 + g + 8]) : 0u;
-                a[2] = svalid[2 * ks + 1] ? __float_as_uint(sbase[2 * ks + 1][p0 + g]) : 0u;
-                a[3] = svalid[2 * ks + 1] ? __float_as_uint(sbase[2 * ks + 1][p0 + g + 8]) : 0u;
-#pragma unroll
-                for (int nt = 0; nt < NT; ++nt) {
-                    mma_tf32(acc[nt], a, bh[ks][nt][0], bh[ks][nt][1]);
-                    mma_tf32(acc[nt], a, bl[ks][nt][0], bl[ks][nt][1]);
-                }
-            }
-            // C fragment: rows g / g+8 (pixels), columns 2*tig, 2*tig+1 of the n-tile -> 8-byte stores, 32 B per pixel and n-tile
-            const int px0 = ox0 + p0 + g, px1 = px0 + 8;
-            float* o0 = out + (((size_t)n * OH + oy) * OW + px0) * CO + 2 * tig;
-            float* o1 = o0 + (size_t)8 * CO;
-#pragma unroll
-            for (int nt = 0; nt < NT; ++nt) {
-                if (px0 < OW) *reinterpret_cast<float2*>(o0 + 8 * nt) = make_float2(silu_fast(acc[nt][0]), silu_fast(acc[nt][1]));
-                if (px1 < OW) *reinterpret_cast<float2*>(o1 + 8 * nt) = make_float2(silu_fast(acc[nt][2]), silu_fast(acc[nt][3]));
-            }
-        }
-    }
-}
-
-// ------------------------------------------------------------------------------------------------
 // SPPF pooling: ultralytics SPPF.forward computes y1 = m(y0), y2 = m(y1), y3 = m(y2) with m = MaxPool2d(5, 1, 2)
 // and concatenates [y0, y1, y2, y3].  One CTA holds an (image, CH-channel slice) tile of y0 in shared memory and
 // runs the three cascaded pools on chip (each separable: 5-wide row max, then 5-tall column max; out-of-range
@@ -512,8 +370,7 @@ int launch_bias_act(hvb_ctx* ctx, const EpiArgs& a, int act) {
 }
 
 template <int CO>
-int launch_stem(hvb_ctx* ctx, const float* in, const float* w_host, const float* b_host, int n, int h, int w, float* out,
-                bool u8norm = false) {
+int launch_stem(hvb_ctx* ctx, const float* in, const float* w_host, const float* b_host, int n, int h, int w, float* out) {
     StemParams<CO> prm;
     // PyTorch weight layout [CO][3][3][3] (co, ci, ky, kx) -> tap-major so one tap's CO weights are adjacent
     for (int co = 0; co < CO; ++co)
@@ -521,8 +378,7 @@ int launch_stem(hvb_ctx* ctx, const float* in, const float* w_host, const float*
     for (int co = 0; co < CO; ++co) prm.b[co] = b_host ? b_host[co] : 0.0f;
     const int oh = (h - 1) / 2 + 1, ow = (w - 1) / 2 + 1;           // floor((h + 2 - 3) / 2) + 1
     dim3 grid((ow + STEM_PX - 1) / STEM_PX, (oh + STEM_ROWS - 1) / STEM_ROWS, n);
-    if (u8norm) stem_conv_mma_kernel<CO><<<grid, STEM_PX, 0, ctx->stream>>>(in, out, h, w, oh, ow, prm);
-    else stem_conv_kernel<CO><<<grid, STEM_PX, 0, ctx->stream>>>(in, out, h, w, oh, ow, prm);
+    stem_conv_kernel<CO><<<grid, STEM_PX, 0, ctx->stream>>>(in, out, h, w, oh, ow, prm);
     HVB_LAUNCHED(ctx);
     return HVB_OK;
 }
@@ -639,20 +495,6 @@ int hvb_stem_conv(hvb_ctx* ctx, const float* in_nchw_dev, const float* weight_ho
         case 48: return launch_stem<48>(ctx, in_nchw_dev, weight_host, bias_host, n, h, w, out_nhwc_dev);
         case 64: return launch_stem<64>(ctx, in_nchw_dev, weight_host, bias_host, n, h, w, out_nhwc_dev);
         default: hvb_set_error("hvb_stem_conv: c_out must be 16/32/48/64 (YOLOv8 n/s/m/l), got %d", c_out); return HVB_ERR_UNSUPPORTED;
-    }
-}
-
-int hvb_stem_conv_u8norm(hvb_ctx* ctx, const float* in_nchw_dev, const float* weight_host, const float* bias_host, int n, int h,
-                         int w, int c_out, float* out_nhwc_dev) {
-    HVB_CHECK_CTX(ctx);
-    HVB_ARG(in_nchw_dev && weight_host && out_nhwc_dev && n >= 0 && h > 0 && w > 0, "bad arguments");
-    if (n == 0) return HVB_OK;
-    HVB_ARG(n <= 65535 && (h + 1) / 2 <= 65535 * 4, "grid extent");
-    switch (c_out) {
-        case 16: return launch_stem<16>(ctx, in_nchw_dev, weight_host, bias_host, n, h, w, out_nhwc_dev, true);
-        case 32: return launch_stem<32>(ctx, in_nchw_dev, weight_host, bias_host, n, h, w, out_nhwc_dev, true);
-        case 48: return launch_stem<48>(ctx, in_nchw_dev, weight_host, bias_host, n, h, w, out_nhwc_dev, true);
-        default: hvb_set_error("hvb_stem_conv_u8norm: c_out must be 16/32/48 (YOLOv8 n/s/m), got %d", c_out); return HVB_ERR_UNSUPPORTED;
     }
 }
 

@@ -97,7 +97,6 @@ PROTOTYPES = {
     "hvb_bias_act": [_vp, _vp, _vp, _vp, _i64, _i, _i, _vp, _i64, _i64, _vp, _i64, _i64, _i, _i, _i, _i],
     "hvb_concat_nhwc": [_vp, _vp, _vp, _vp, _i, _i, _i, _i, _vp],
     "hvb_sppf_pool_concat": [_vp, _vp, _i, _i, _i, _i, _vp],
-    "hvb_stem_conv_u8norm": [_vp, _vp, _vp, _vp, _i, _i, _i, _i, _vp],
     "hvb_stem_conv": [_vp, _vp, _vp, _vp, _i, _i, _i, _i, _vp],
     "hvb_color_features_host": [_vp, _vp, _sz, _vp, _i, _i, _vp, _vp],
     "hvb_mnv3_preprocess_host": [_vp, _vp, _sz, _vp, _i, _i, _vp, _vp],

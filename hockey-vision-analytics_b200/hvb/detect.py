@@ -60,7 +60,7 @@ class Detector:
         if glue:
             from .models.fused import FusedYOLOv8
             # exact_silu=True: expf + IEEE division (torch's formula) instead of the approximate-unit SiLU (<= 1e-6 relative)
-            self.runner = FusedYOLOv8(self.model, self.ctx, exact_silu=exact_silu, input_u8norm=False)
+            self.runner = FusedYOLOv8(self.model, self.ctx, exact_silu=exact_silu)
         self.imgsz, self.conf, self.iou, self.max_det, self.agnostic = imgsz, conf, iou, max_det, agnostic_nms
         self.autocast_dtype = autocast_dtype
         self.class_names = class_names or {i: str(i) for i in range(self.nc)}

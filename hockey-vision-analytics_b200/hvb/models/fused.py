@@ -46,7 +46,7 @@ class _Conv:
 
 
 class FusedYOLOv8:
-    def __init__(self, model: YOLOv8, ctx, stem_kernel: bool = True, exact_silu: bool = False, input_u8norm: bool = False):
+    def __init__(self, model: YOLOv8, ctx, stem_kernel: bool = True, exact_silu: bool = False):
         import copy
         m = copy.deepcopy(model).eval()
         if any(isinstance(x.bn, torch.nn.BatchNorm2d) for x in m.modules() if isinstance(x, ConvBnAct)):
@@ -60,8 +60,6 @@ class FusedYOLOv8:
         self.stem_w = m.b0.conv.weight.detach().float().cpu().contiguous().numpy()
         self.stem_b = m.b0.conv.bias.detach().float().cpu().contiguous().numpy()
         self.use_stem = stem_kernel and self.stem_w.shape[0] in (16, 32, 48, 64)
-        # input_u8norm: the caller guarantees inputs of the form k/255 (K1's letterbox output) -> tensor-core stem
-        self.stem_u8norm = input_u8norm and self.stem_w.shape[0] in (16, 32, 48)
         self._lib, self._h = ctx.lib, ctx.handle
         # SiLU flavour of the epilogue: the approximate-unit version (<= 1e-6 relative error) keeps the pass HBM-bound
         self._silu = _SILU_EXACT if exact_silu else _SILU_FAST
@@ -178,8 +176,7 @@ class FusedYOLOv8:
             cat21 = self._buf(n, c19 + c5, h // 32, w // 32)         # [h19(h18), p5]
             if self.use_stem and x.is_contiguous():
                 y = self._buf(n, self.stem_w.shape[0], h // 2, w // 2)
-                stem = self._lib.hvb_stem_conv_u8norm if self.stem_u8norm else self._lib.hvb_stem_conv
-                _ffi.check(stem(self._h, C.c_void_p(x.data_ptr()), C.c_void_p(self.stem_w.ctypes.data),
+                _ffi.check(self._lib.hvb_stem_conv(self._h, C.c_void_p(x.data_ptr()), C.c_void_p(self.stem_w.ctypes.data),
                                                    C.c_void_p(self.stem_b.ctypes.data), n, h, w, self.stem_w.shape[0],
                                                    C.c_void_p(y.data_ptr())))
             else:

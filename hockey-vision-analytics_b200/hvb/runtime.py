@@ -355,10 +355,8 @@ class Context:
             check(self.lib.hvb_sppf_pool_concat(self.handle, ptr(y0), n, h, w, c, ptr(out)))
         return out
 
-    def stem_conv(self, x_nchw: torch.Tensor, weight_host: np.ndarray, bias_host: Optional[np.ndarray],
-                  u8norm: bool = False) -> torch.Tensor:
-        """Layer 0 (3->C, 3x3, stride 2, pad 1) + bias + SiLU: NCHW float32 in, channels-last out.  u8norm=True: the
-        input is exactly k/255 (K1's output) -> the tensor-core variant (hvb_stem_conv_u8norm)."""
+    def stem_conv(self, x_nchw: torch.Tensor, weight_host: np.ndarray, bias_host: Optional[np.ndarray]) -> torch.Tensor:
+        """Layer 0 (3->C, 3x3, stride 2, pad 1) + bias + SiLU: NCHW float32 in, channels-last out."""
         n, ci, h, w = x_nchw.shape
         if ci != 3 or x_nchw.dtype != torch.float32 or not x_nchw.is_contiguous():
             raise ValueError("stem_conv expects a dense float32 [N,3,H,W] tensor")
@@ -368,8 +366,7 @@ class Context:
             self._enter()
             out = torch.empty((n, co, (h - 1) // 2 + 1, (w - 1) // 2 + 1), dtype=torch.float32, device=self.device,
                               memory_format=torch.channels_last)
-            fn = self.lib.hvb_stem_conv_u8norm if u8norm else self.lib.hvb_stem_conv
-            check(fn(self.handle, ptr(x_nchw), ptr(weight_host), ptr(bias_host), n, h, w, co, ptr(out)))
+            check(self.lib.hvb_stem_conv(self.handle, ptr(x_nchw), ptr(weight_host), ptr(bias_host), n, h, w, co, ptr(out)))
         return out
 
     # ------------------------------------------------------------------ host-buffer entry points

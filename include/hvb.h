@@ -307,11 +307,6 @@ HVB_API int hvb_concat_nhwc(hvb_ctx* ctx, const float* const src_dev[4], const i
  * with m = MaxPool2d(5, stride 1, pad 2), computed on chip from one read of y0.  y0: [n,h,w,channels] NHWC,
  * out: [n,h,w,4*channels].  HVB_ERR_UNSUPPORTED when an h x w map does not fit shared memory (h*w > ~6400). */
 HVB_API int hvb_sppf_pool_concat(hvb_ctx* ctx, const float* y0_dev, int n, int h, int w, int channels, float* out_cat_dev);
-/* Same layer for inputs that are exactly k/255, k an integer in [0,255] (what hvb_lb_plan_run writes): k is recovered
- * exactly and used as a TF32 tensor-core operand, the 1/255 moves into hi+lo split weights — fp32-accurate (2^-22),
- * ~4x fewer instructions.  Any other input gives wrong results: use hvb_stem_conv.  c_out in {16,32,48}. */
-HVB_API int hvb_stem_conv_u8norm(hvb_ctx* ctx, const float* in_nchw_dev, const float* weight_host, const float* bias_host,
-                         int n, int h, int w, int c_out, float* out_nhwc_dev);
 HVB_API int hvb_stem_conv(hvb_ctx* ctx, const float* in_nchw_dev, const float* weight_host, const float* bias_host,
                   int n, int h, int w, int c_out, float* out_nhwc_dev);
 

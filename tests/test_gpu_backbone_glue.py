@@ -145,22 +145,6 @@ def test_stem_conv(ctx, no_tf32, co, hw):
     assert (out.cpu() - ref).abs().max() <= 2e-6 * ref.abs().max()
 
 
-@pytest.mark.parametrize("co,hw", [(16, (64, 96)), (48, (96, 160)), (48, (33, 271)), (32, (32, 32)), (16, (640, 640)), (48, (736, 1280))])
-def test_stem_conv_u8norm_tensor_path(ctx, co, hw):
-    """Inputs of the form k/255 (what K1 writes): k is recovered exactly, weights/255 are split hi+lo into TF32 —
-    the result stays within 2e-6 of the float64 convolution, like the FFMA kernel."""
-    g = torch.Generator().manual_seed(co + hw[0])
-    x = (torch.randint(0, 256, (2, 3, *hw), generator=g).float() / 255.0)
-    w = torch.randn(co, 3, 3, 3, generator=g) * 0.3
-    b = torch.randn(co, generator=g)
-    ref = F.silu(F.conv2d(x.double(), w.double(), b.double(), 2, 1)).float()
-    out = ctx.stem_conv(x.cuda(), w.numpy(), b.numpy(), u8norm=True)
-    assert out.shape == ref.shape and out.is_contiguous(memory_format=CL)
-    assert (out.cpu() - ref).abs().max() <= 2e-6 * ref.abs().max()
-    plain = ctx.stem_conv(x.cuda(), w.numpy(), b.numpy())
-    assert (out - plain).abs().max().item() <= 2e-6 * ref.abs().max().item()
-
-
 @pytest.mark.parametrize("scale,nc,hw", [("n", 1, (128, 640)), ("m", 2, (96, 160)), ("n", 1, (640, 640))])
 def test_fused_forward_matches_module(ctx, no_tf32, scale, nc, hw):
     from hvb.models import build_yolov8

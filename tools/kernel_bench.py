@@ -216,11 +216,6 @@ def main():
         ms = timed(lambda: ctx.stem_conv(xin, wst, bst), R)
         report("K5 stem conv 3->48 s2 + SiLU x%d 736x1280" % nb, ms, xin.numel() * 4 + nb * 48 * 368 * 640 * 4,
                flops=2 * 27 * 48 * nb * 368 * 640)
-        xq = (torch.randint(0, 256, (nb, 3, 736, 1280), device="cuda").float() / 255.0)
-        ms = timed(lambda: ctx.stem_conv(xq, wst, bst, u8norm=True), R)
-        report("K5 stem conv (tensor path, k/255 input) 3->48 x%d 736x1280" % nb, ms, xq.numel() * 4 + nb * 48 * 368 * 640 * 4,
-               flops=2 * 27 * 48 * nb * 368 * 640)
-        del xq
         del xin
         nt = 112                                                   # 4 x 4K frames: the 640x640 tile class of the sliced path
         xt = torch.rand(nt, 3, 640, 640, device="cuda")
@@ -228,10 +223,6 @@ def main():
         b16 = np.zeros((16,), np.float32)
         ms = timed(lambda: ctx.stem_conv(xt, w16, b16), R)
         report("K5 stem conv 3->16 s2 + SiLU x%d tiles 640x640 (YOLOv8n)" % nt, ms, xt.numel() * 4 + nt * 16 * 320 * 320 * 4,
-               flops=2 * 27 * 16 * nt * 320 * 320)
-        xtq = (torch.randint(0, 256, (nt, 3, 640, 640), device="cuda").float() / 255.0)
-        ms = timed(lambda: ctx.stem_conv(xtq, w16, b16, u8norm=True), R)
-        report("K5 stem conv (tensor path, k/255 input) 3->16 x%d tiles 640x640" % nt, ms, xtq.numel() * 4 + nt * 16 * 320 * 320 * 4,
                flops=2 * 27 * 16 * nt * 320 * 320)
 
     if want('k1'):
