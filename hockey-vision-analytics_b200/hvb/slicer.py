@@ -50,7 +50,8 @@ class B200InferenceSlicer:
                  slice_wh: Tuple[int, int] = (320, 320), overlap_ratio_wh: Optional[Tuple[float, float]] = (0.2, 0.2),
                  overlap_wh: Optional[Tuple[int, int]] = None, overlap_filter: str = OverlapFilter.NON_MAX_SUPPRESSION,
                  iou_threshold: float = 0.5, thread_workers: int = 1, *, detector: Optional[Detector] = None,
-                 tile_imgsz: int = 640, uniform_tiles: bool = False, class_agnostic: bool = False):
+                 tile_imgsz: int = 640, uniform_tiles: bool = False, class_agnostic: bool = False,
+                 concurrent_classes: Optional[bool] = None):
         if callback is None and detector is None:
             raise ValueError("either `callback` (compat path) or `detector` (device path) is required")
         if overlap_filter == OverlapFilter.NON_MAX_MERGE:
@@ -60,6 +61,11 @@ class B200InferenceSlicer:
         self.overlap_filter, self.iou_threshold = overlap_filter, iou_threshold
         self.thread_workers = thread_workers          # accepted for signature parity; tiles run in slicer order
         self.tile_imgsz, self.uniform_tiles, self.class_agnostic = tile_imgsz, uniform_tiles, class_agnostic
+        import os
+        if concurrent_classes is None:
+            concurrent_classes = os.environ.get("HVB_SLICER_CONCURRENT", "0") == "1"
+        self.concurrent_classes = concurrent_classes
+        self._side_streams = None
 
     def _overlap(self) -> Tuple[int, int]:
         if self.overlap_wh is not None:
@@ -107,11 +113,39 @@ class B200InferenceSlicer:
         out = (ctx.empty((n_slots, det.max_det, 4), torch.float32), ctx.empty((n_slots, det.max_det), torch.float32),
                ctx.empty((n_slots, det.max_det), torch.int32), torch.zeros((n_slots,), dtype=torch.int32, device=ctx.device))
         states = []
-        for c, x in enumerate(views):
-            heads = det.forward_heads(x)
-            meta_h, meta_d = det._meta_dev(plan, c)
-            *_, state = det._decode(heads, meta_h, meta_d, n_slots, out=out)
-            states.append(state)
+        if self.concurrent_classes and len(views) > 1:
+            # The small shape classes (a handful of clipped edge tiles) underfill the GPU: their forwards run on side
+            # streams next to the big 640x640 class; the K2a launches stay on the main stream (one shared work area).
+            dev = frames_dev.device
+            main = torch.cuda.current_stream(dev)
+            if self._side_streams is None:
+                self._side_streams = [torch.cuda.Stream(device=dev) for _ in range(2)]
+            order = sorted(range(len(views)), key=lambda c: -views[c].numel())
+            heads_of = {}
+            fork = torch.cuda.Event()
+            fork.record(main)
+            for rank, c in enumerate(order):
+                if rank == 0:
+                    heads_of[c] = det.forward_heads(views[c])                 # biggest class on the main stream
+                    continue
+                side = self._side_streams[(rank - 1) % len(self._side_streams)]
+                side.wait_event(fork)
+                with torch.cuda.stream(side):
+                    heads_of[c] = det.forward_heads(views[c])
+                for hd in heads_of[c]:
+                    hd.record_stream(main)
+            for side in self._side_streams:
+                main.wait_stream(side)
+            for c in range(len(views)):
+                meta_h, meta_d = det._meta_dev(plan, c)
+                *_, state = det._decode(heads_of[c], meta_h, meta_d, n_slots, out=out)
+                states.append(state)
+        else:
+            for c, x in enumerate(views):
+                heads = det.forward_heads(x)
+                meta_h, meta_d = det._meta_dev(plan, c)
+                *_, state = det._decode(heads, meta_h, meta_d, n_slots, out=out)
+                states.append(state)
         xyxy, cf, cl, cnt = out
         key = ("slot_off", id(plan))
         if key not in det._meta:
