@@ -332,8 +332,32 @@ def run_hvb(args, rank, world):
         k5 = {"launches_per_step": len(log) // 3, "bytes_per_step": k5_bytes // 3, "ms_per_step": k5_ms / 3,
               "achieved": k5_bytes / (k5_ms / 1e3) / 1e9}
 
+    # ---- per-stage device times of one chunk (CUDA events on the main stream, stages run back to back without the
+    # side-stream overlap) — the GPU column next to cpu_baseline.stage_ms_per_frame
+    det = path.detector
+    ev = [torch.cuda.Event(enable_timing=True) for _ in range(5)]
+    acc = [0.0, 0.0, 0.0, 0.0]
+    for it in range(4):
+        plan = det.plan(F, H, W, _ffi.LB_WHOLE)
+        ev[0].record()
+        x = plan.class_views(plan.run(frames_dev))[0]
+        ev[1].record()
+        heads = det.forward_heads(x)
+        ev[2].record()
+        meta_h, meta_d = det._meta_dev(plan, 0)
+        det._decode(heads, meta_h, meta_d, F)
+        ev[3].record()
+        path.team_device(frames_dev, boxes_dev, fidx_dev)
+        ev[4].record()
+        torch.cuda.synchronize()
+        if it:                                     # first pass is a warm-up
+            for k in range(4):
+                acc[k] += ev[k].elapsed_time(ev[k + 1]) / 3 / F
+    gpu_stage_ms = {"letterbox+preprocess (K1a)": round(acc[0], 5), "yolo_forward (cuDNN convs + K5)": round(acc[1], 5),
+                    "decode+nms+scale (K2a)": round(acc[2], 5), "crops+team_predict (K3a/K3b, MobileNetV3, K4a)": round(acc[3], 5)}
+
     # ---- secondary workload: 4K sliced puck path (C4), reported in `extra`
-    extra = {"fit_ms": fit_ms}
+    extra = {"fit_ms": fit_ms, "gpu_stage_ms_per_frame": gpu_stage_ms}
     # frame-at-a-time use of the drop-in (what process_frame does per frame: host frame in, Detections out)
     if rank == 0:
         one = frames[0]
