@@ -34,9 +34,11 @@ constexpr int kCapLarge = 8192;
 constexpr float kMaxWH = 7680.0f;
 
 struct Levels {
-    const float* ptr[3];
+    const float* ptr[3];          // box-bin channels (64 per anchor)
+    const float* cls[3];          // class-logit channel 0 (same tensor + 64 channels, or a separate dense tensor)
     int32_t h[3], w[3];
     int64_t bstride[3], cstride[3], astride[3];
+    int64_t cls_bstride[3], cls_cstride[3], cls_astride[3];
     int32_t base[4];      // anchor index base per level, base[3] = A
 };
 
@@ -202,9 +204,9 @@ decode_nms_kernel(Levels L, int nc, float conf_thres, float pre_gate, float iou_
         if (a < A) {
             int lvl, q;
             locate(L, a, lvl, q);
-            const float* p = L.ptr[lvl] + (int64_t)b * L.bstride[lvl] + (int64_t)q * L.astride[lvl] + 64 * L.cstride[lvl];
+            const float* p = L.cls[lvl] + (int64_t)b * L.cls_bstride[lvl] + (int64_t)q * L.cls_astride[lvl];
             for (int c = 0; c < nc; c++) {
-                const float x = __ldg(p + (int64_t)c * L.cstride[lvl]);
+                const float x = __ldg(p + (int64_t)c * L.cls_cstride[lvl]);
                 // a logit at or below the pre-gate has sigmoid <= conf_thres, so it can neither pass nor be the max of a
                 // passing anchor; the exact sigmoid (expf + IEEE division) is evaluated only above it
                 if (x > pre_gate) {
@@ -318,8 +320,8 @@ decode_only_kernel(Levels L, int nc, float* __restrict__ out) {
     decode_xywh(L, b, lvl, q, cx, cy, w, h);
     float* o = out + (int64_t)b * (4 + nc) * A + a;
     o[0] = cx; o[(int64_t)A] = cy; o[2 * (int64_t)A] = w; o[3 * (int64_t)A] = h;
-    const float* p = L.ptr[lvl] + (int64_t)b * L.bstride[lvl] + (int64_t)q * L.astride[lvl] + 64 * L.cstride[lvl];
-    for (int c = 0; c < nc; c++) o[(int64_t)(4 + c) * A] = sigmoidf_exact(__ldg(p + (int64_t)c * L.cstride[lvl]));
+    const float* p = L.cls[lvl] + (int64_t)b * L.cls_bstride[lvl] + (int64_t)q * L.cls_astride[lvl];
+    for (int c = 0; c < nc; c++) o[(int64_t)(4 + c) * A] = sigmoidf_exact(__ldg(p + (int64_t)c * L.cls_cstride[lvl]));
 }
 
 // NMS on caller-provided candidates of one image (test hook for the margin-free keep-set test).
@@ -358,11 +360,24 @@ int fill_levels(Levels& L, const float* const level_dev[3], const int32_t level_
         if (!level_dev[i] || level_h[i] <= 0 || level_w[i] <= 0) { hvb_set_error("bad level %d", i); return HVB_ERR_ARG; }
         L.ptr[i] = level_dev[i]; L.h[i] = level_h[i]; L.w[i] = level_w[i];
         L.bstride[i] = batch_stride[i]; L.cstride[i] = chan_stride[i]; L.astride[i] = anchor_stride[i];
+        // class logits: channels 64.. of the same tensor unless fill_cls() points them at a separate one
+        L.cls[i] = level_dev[i] + 64 * chan_stride[i];
+        L.cls_bstride[i] = batch_stride[i]; L.cls_cstride[i] = chan_stride[i]; L.cls_astride[i] = anchor_stride[i];
         L.base[i] = base;
         base += level_h[i] * level_w[i];
     }
     L.base[3] = base;
     if (base >= (1 << 24)) { hvb_set_error("more than 2^24 anchors per image"); return HVB_ERR_CAPACITY; }
+    return HVB_OK;
+}
+
+int fill_cls(Levels& L, const float* const cls_dev[3], const int64_t batch_stride[3], const int64_t chan_stride[3],
+             const int64_t anchor_stride[3]) {
+    for (int i = 0; i < 3; i++) {
+        if (!cls_dev[i]) { hvb_set_error("null class-logit tensor for level %d", i); return HVB_ERR_ARG; }
+        L.cls[i] = cls_dev[i];
+        L.cls_bstride[i] = batch_stride[i]; L.cls_cstride[i] = chan_stride[i]; L.cls_astride[i] = anchor_stride[i];
+    }
     return HVB_OK;
 }
 
@@ -417,6 +432,50 @@ int hvb_nms_capacity(int* out_max_candidates) {
     if (!out_max_candidates) { hvb_set_error("null argument"); return HVB_ERR_ARG; }
     *out_max_candidates = kCapLarge;
     return HVB_OK;
+}
+
+static int decode_nms_impl(hvb_ctx* ctx, const float* const level_dev[3], const float* const cls_dev[3],
+                           const int32_t level_h[3], const int32_t level_w[3], const int64_t batch_stride[3],
+                           const int64_t chan_stride[3], const int64_t anchor_stride[3], const int64_t cls_batch_stride[3],
+                           const int64_t cls_chan_stride[3], const int64_t cls_anchor_stride[3], const int32_t* images_dev,
+                           int batch, int nc, float conf_thres, float iou_thres, int max_det, int agnostic,
+                           const hvb_img_meta* meta_dev, float* out_xyxy_dev, float* out_conf_dev, int32_t* out_cls_dev,
+                           int32_t* out_count_dev) {
+    HVB_CHECK_CTX(ctx);
+    HVB_ARG(batch >= 0 && nc >= 1 && nc <= 256, "bad batch/nc");
+    HVB_ARG(max_det >= 1 && max_det <= 2048, "max_det out of range [1,2048]");
+    if (batch == 0) return HVB_OK;
+    HVB_ARG(meta_dev && out_xyxy_dev && out_conf_dev && out_cls_dev && out_count_dev, "null pointer");
+    HVB_ARG(batch <= 65535, "more than 65535 images in one launch");
+    Levels L;
+    HVB_TRY(fill_levels(L, level_dev, level_h, level_w, batch_stride, chan_stride, anchor_stride));
+    if (cls_dev) HVB_TRY(fill_cls(L, cls_dev, cls_batch_stride, cls_chan_stride, cls_anchor_stride));
+    const int cap = images_dev ? kCapLarge : kCapSmall;           // the retry tier works on a list of images
+    const size_t sm = nms_smem_bytes(cap, max_det);
+    HVB_TRY(set_smem(decode_nms_kernel, sm));
+    unsigned long long* keys = nullptr;
+    int32_t* ctr = nullptr;
+    HVB_TRY(k2_work(ctx, batch, cap, &keys, &ctr));
+    dim3 grid(hvb_div_up(L.base[3], kChunk), batch);
+    decode_nms_kernel<<<grid, kThreads, sm, ctx->stream>>>(L, nc, conf_thres, logit_pre_gate(conf_thres), iou_thres, max_det,
+                                                           agnostic, cap, meta_dev, out_xyxy_dev, out_conf_dev, out_cls_dev,
+                                                           out_count_dev, images_dev, keys, ctr);
+    HVB_LAUNCHED(ctx);
+    return HVB_OK;
+}
+
+int hvb_decode_nms_split(hvb_ctx* ctx, const float* const box_level_dev[3], const float* const cls_level_dev[3],
+                         const int32_t level_h[3], const int32_t level_w[3], const int64_t box_batch_stride[3],
+                         const int64_t box_chan_stride[3], const int64_t box_anchor_stride[3],
+                         const int64_t cls_batch_stride[3], const int64_t cls_chan_stride[3],
+                         const int64_t cls_anchor_stride[3], const int32_t* images_dev, int batch, int nc, float conf_thres,
+                         float iou_thres, int max_det, int agnostic, const hvb_img_meta* meta_dev, float* out_xyxy_dev,
+                         float* out_conf_dev, int32_t* out_cls_dev, int32_t* out_count_dev) {
+    if (!cls_level_dev) { hvb_set_error("hvb_decode_nms_split: null class-logit tensors"); return HVB_ERR_ARG; }
+    return decode_nms_impl(ctx, box_level_dev, cls_level_dev, level_h, level_w, box_batch_stride, box_chan_stride,
+                           box_anchor_stride, cls_batch_stride, cls_chan_stride, cls_anchor_stride, images_dev, batch, nc,
+                           conf_thres, iou_thres, max_det, agnostic, meta_dev, out_xyxy_dev, out_conf_dev, out_cls_dev,
+                           out_count_dev);
 }
 
 int hvb_decode_nms(hvb_ctx* ctx, const float* const level_dev[3], const int32_t level_h[3], const int32_t level_w[3],

@@ -80,6 +80,7 @@ PROTOTYPES = {
     "hvb_lb_plan_run_u8": [_vp, _vp, _vp],
     "hvb_decode_nms": [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _f, _f, _i, _i, _vp, _vp, _vp, _vp, _vp],
     "hvb_decode_nms_large": [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _f, _f, _i, _i, _vp, _vp, _vp, _vp, _vp],
+    "hvb_decode_nms_split": [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _f, _f, _i, _i, _vp, _vp, _vp, _vp, _vp],
     "hvb_decode_only": [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _vp],
     "hvb_nms_f32": [_vp, _vp, _vp, _vp, _i, _f, _i, _i, _vp, _vp],
     "hvb_nms_capacity": [C.POINTER(_i)],

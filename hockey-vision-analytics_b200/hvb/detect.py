@@ -15,7 +15,7 @@ import torch
 
 from . import _ffi
 from .detections import Detections
-from .runtime import Context, LetterboxPlan, get_context, nvtx
+from .runtime import Context, LetterboxPlan, SplitHeads, get_context, nvtx
 
 PLAYER_CLASS_ID = 0
 GOALKEEPER_CLASS_ID = 1
@@ -153,11 +153,13 @@ class Detector:
 
                 def step(f):
                     xyxy, cf, cl, cnt, (heads, _, _) = self.detect_device(f, graph=False)
-                    return (xyxy, cf, cl, cnt) + tuple(heads)
+                    flat = tuple(heads.box) + tuple(heads.cls) if isinstance(heads, SplitHeads) else tuple(heads)
+                    return (xyxy, cf, cl, cnt) + flat
                 self._graphs[key] = GraphedStep(self.ctx, step, [frames_dev])
             out = self._graphs[key](frames_dev)          # static outputs: valid until the next call with this shape
             meta_h, meta_d = self._meta_dev(plan, 0)
-            return out[0], out[1], out[2], out[3], (list(out[4:]), meta_h, meta_d)
+            heads = SplitHeads(out[4:7], out[7:10]) if len(out) == 10 else list(out[4:])
+            return out[0], out[1], out[2], out[3], (heads, meta_h, meta_d)
         with nvtx("hvb:K1a letterbox"):
             x = plan.class_views(plan.run(frames_dev))[0]
         with nvtx("hvb:yolo forward (cuDNN convs + K5)"):
@@ -168,7 +170,6 @@ class Detector:
 
     def _decode(self, heads, meta_h, meta_d, n_slots, out=None):
         # meta stays resident on the device; the host copy is only used by the overflow retry
-        B = heads[0].shape[0]
         ctx = self.ctx
         with ctx.lock:
             ctx._enter()
@@ -176,10 +177,7 @@ class Detector:
                 out = (ctx.empty((n_slots, self.max_det, 4), torch.float32), ctx.empty((n_slots, self.max_det), torch.float32),
                        ctx.empty((n_slots, self.max_det), torch.int32), torch.zeros((n_slots,), dtype=torch.int32, device=ctx.device))
             xyxy, cf, cl, cnt = out
-            args = ctx._level_args(heads)
-            _ffi.check(ctx.lib.hvb_decode_nms(ctx.handle, *args, B, self.nc, self.conf, self.iou, self.max_det,
-                                              int(self.agnostic), _ffi.ptr(meta_d), _ffi.ptr(xyxy), _ffi.ptr(cf), _ffi.ptr(cl),
-                                              _ffi.ptr(cnt)))
+            ctx.decode_nms_call(heads, self.nc, self.conf, self.iou, self.max_det, self.agnostic, meta_d, xyxy, cf, cl, cnt)
         return xyxy, cf, cl, cnt, (heads, meta_h, meta_d)
 
     def _retry_overflow(self, xyxy, cf, cl, cnt, state, cnt_host: np.ndarray):
@@ -192,9 +190,8 @@ class Detector:
         with ctx.lock:
             ctx._enter()
             bad_dev = ctx.to_device(bad)
-            _ffi.check(ctx.lib.hvb_decode_nms_large(ctx.handle, *ctx._level_args(heads), _ffi.ptr(bad_dev), int(len(bad)),
-                                                    self.nc, self.conf, self.iou, self.max_det, int(self.agnostic),
-                                                    _ffi.ptr(meta_d), _ffi.ptr(xyxy), _ffi.ptr(cf), _ffi.ptr(cl), _ffi.ptr(cnt)))
+            ctx.decode_nms_call(heads, self.nc, self.conf, self.iou, self.max_det, self.agnostic, meta_d, xyxy, cf, cl, cnt,
+                                images_dev=bad_dev, n_images=int(len(bad)))
         cnt_host = cnt.cpu().numpy()
         if (cnt_host[meta_h["out_slot"]] < 0).any():
             raise _ffi.HvbError(_ffi.HVB_ERR_CAPACITY, "more than 8192 candidates above conf=%g in one image" % self.conf)

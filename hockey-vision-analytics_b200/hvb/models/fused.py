@@ -11,7 +11,8 @@ buffer); SPPF's four-way concat is one `hvb_concat_nhwc` pass; layer 0 reads K1'
 
 The layer graph is ultralytics 8.3.148 `yolov8.yaml` (the model the reference loads at
 hockey/main.py:77 and runs at :179-184), same as hvb.models.yolov8.YOLOv8 whose (conv+bn folded)
-weights this runner borrows.  Returns the three raw Detect tensors [B, 64+nc, H_i, W_i], channels-last.
+weights this runner borrows.  Returns the raw Detect outputs as SplitHeads (box bins [B,64,H_i,W_i] and class logits
+[B,nc,H_i,W_i], channels-last).
 """
 from __future__ import annotations
 
@@ -145,16 +146,16 @@ class FusedYOLOv8:
         return out
 
     def _detect(self, feats):
-        det, outs = self.m.detect, []
+        """Detect: the 64 box-bin channels and the nc class channels stay in their own dense tensors (SplitHeads): the
+        bias add runs in place on each convolution output, and K2a's confidence scan reads contiguous class logits."""
+        from ..runtime import SplitHeads
+        det, boxes, clss = self.m.detect, [], []
         for i, x in enumerate(feats):
-            n, _, h, w = x.shape
-            head = self._buf(n, 64 + self.nc, h, w)
-            for branch, off in ((det.cv2[i], 0), (det.cv3[i], 64)):
+            for branch, dst in ((det.cv2[i], boxes), (det.cv3[i], clss)):
                 t = self._cba(branch[1], self._cba(branch[0], x))
                 k = self.convs[branch[2]]
-                self._epi(k.raw(t), k.b, act=_NONE, out1=head, off1=off)
-            outs.append(head)
-        return outs
+                dst.append(self._epi(k.raw(t), k.b, act=_NONE))
+        return SplitHeads(boxes, clss)
 
     # ------------------------------------------------------------------ forward
     @torch.no_grad()

@@ -51,6 +51,24 @@ def get_context(device: int | str | torch.device | None = None) -> "Context":
         return _contexts[idx]
 
 
+class SplitHeads:
+    """Raw Detect outputs with the class logits in their own dense tensors: box[i] is [B, 64, H_i, W_i], cls[i] is
+    [B, nc, H_i, W_i] (any strides with jointly contiguous spatial dims; channels-last is what the K5 runner writes)."""
+
+    def __init__(self, box: Sequence[torch.Tensor], cls: Sequence[torch.Tensor]):
+        self.box, self.cls = list(box), list(cls)
+
+    def __len__(self):
+        return 3
+
+    def tensors(self) -> List[torch.Tensor]:
+        return self.box + self.cls
+
+    def __iter__(self):
+        """Combined [B, 64+nc, H, W] tensors (for code that wants the plain Detect output)."""
+        return iter(torch.cat((b, c), 1) for b, c in zip(self.box, self.cls))
+
+
 class Context:
     def __init__(self, device: int = 0):
         self.lib = _ffi.lib()
@@ -119,6 +137,23 @@ class Context:
                 raise ValueError("head tensor spatial dims must be jointly contiguous")
         as_ = (C.c_int64 * 3)(*[lv.stride(3) for lv in levels])
         return ptrs, hs, ws, bs, cs, as_
+
+    def decode_nms_call(self, heads, nc, conf, iou, max_det, agnostic, meta_dev, xyxy, cf, cl, cnt, images_dev=None, n_images=None):
+        """One K2a launch for either head layout (list of combined tensors, or SplitHeads).  Caller holds the lock."""
+        if isinstance(heads, SplitHeads):
+            bp, hs, ws, bb, bc, ba = self._level_args(heads.box)
+            cp, _, _, cb, cc, ca = self._level_args(heads.cls)
+            batch = heads.box[0].shape[0] if images_dev is None else n_images
+            check(self.lib.hvb_decode_nms_split(self.handle, bp, cp, hs, ws, bb, bc, ba, cb, cc, ca, ptr(images_dev), batch, nc,
+                                                conf, iou, max_det, int(agnostic), ptr(meta_dev), ptr(xyxy), ptr(cf), ptr(cl), ptr(cnt)))
+            return
+        args = self._level_args(heads)
+        if images_dev is None:
+            check(self.lib.hvb_decode_nms(self.handle, *args, heads[0].shape[0], nc, conf, iou, max_det, int(agnostic),
+                                          ptr(meta_dev), ptr(xyxy), ptr(cf), ptr(cl), ptr(cnt)))
+        else:
+            check(self.lib.hvb_decode_nms_large(self.handle, *args, ptr(images_dev), n_images, nc, conf, iou, max_det,
+                                                int(agnostic), ptr(meta_dev), ptr(xyxy), ptr(cf), ptr(cl), ptr(cnt)))
 
     def decode_nms(self, levels: Sequence[torch.Tensor], nc: int, conf: float, iou: float = 0.7, max_det: int = 300,
                    agnostic: bool = False, meta: Optional[np.ndarray] = None, n_slots: Optional[int] = None,

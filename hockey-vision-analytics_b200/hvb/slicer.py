@@ -132,7 +132,7 @@ class B200InferenceSlicer:
                 side.wait_event(fork)
                 with torch.cuda.stream(side):
                     heads_of[c] = det.forward_heads(views[c])
-                for hd in heads_of[c]:
+                for hd in (heads_of[c].tensors() if hasattr(heads_of[c], "tensors") else heads_of[c]):
                     hd.record_stream(main)
             for side in self._side_streams:
                 main.wait_stream(side)

@@ -167,6 +167,19 @@ HVB_API int hvb_decode_nms_large(hvb_ctx* ctx, const float* const level_dev[3], 
                          float conf_thres, float iou_thres, int max_det, int agnostic,
                          const hvb_img_meta* meta_dev, float* out_xyxy_dev, float* out_conf_dev,
                          int32_t* out_cls_dev, int32_t* out_count_dev);
+/* The same with the class logits in their own tensors (box_level_dev: the 64 box-bin channels; cls_level_dev: the nc
+ * class channels, channel c of anchor a of image b at  b*cls_batch_stride + c*cls_chan_stride + a*cls_anchor_stride).
+ * A dense [B, H, W, nc] class tensor makes the confidence scan — the only pass that touches every anchor — read
+ * contiguous memory (a channels-last [B, H, W, 64+nc] head costs a 32-byte sector per anchor for nc*4 useful bytes).
+ * images_dev: NULL = all `batch` images with the 1024-candidate tier; else int32[batch] image indices to (re)run with
+ * the 8192-candidate tier (what hvb_decode_nms_large does for the combined layout). */
+HVB_API int hvb_decode_nms_split(hvb_ctx* ctx, const float* const box_level_dev[3], const float* const cls_level_dev[3],
+                         const int32_t level_h[3], const int32_t level_w[3], const int64_t box_batch_stride[3],
+                         const int64_t box_chan_stride[3], const int64_t box_anchor_stride[3],
+                         const int64_t cls_batch_stride[3], const int64_t cls_chan_stride[3],
+                         const int64_t cls_anchor_stride[3], const int32_t* images_dev, int batch, int nc,
+                         float conf_thres, float iou_thres, int max_det, int agnostic, const hvb_img_meta* meta_dev,
+                         float* out_xyxy_dev, float* out_conf_dev, int32_t* out_cls_dev, int32_t* out_count_dev);
 /* Test hooks: decode only (float32[batch, 4+nc, A] like Detect._inference) and NMS only on
  * caller-provided candidates (boxes xyxy float32[n,4], scores, classes; one image). */
 HVB_API int hvb_decode_only(hvb_ctx* ctx, const float* const level_dev[3], const int32_t level_h[3],

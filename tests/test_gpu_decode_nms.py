@@ -140,3 +140,35 @@ def test_channels_last_heads_give_identical_results(ctx):
     for i in range(2):
         for x, y in zip(a[:3], b[:3]):
             assert torch.equal(x[i, :cnt[i]], y[i, :cnt[i]])
+
+
+def test_split_heads_layout_gives_identical_results(ctx):
+    """hvb_decode_nms_split (box bins and class logits in separate tensors, class logits dense channels-last — what the
+    K5 runner writes) == hvb_decode_nms on the combined [B, 64+nc, H, W] tensors, bit for bit, including the retry tier."""
+    from hvb.runtime import SplitHeads
+    levels = [l.cuda() for l in make_heads(11, 3, (736, 1280), 2)]
+    meta = meta_for(3, (736, 1280), (1080, 1920))
+    want = ctx.decode_nms(levels, 2, 0.4, 0.7, 300, False, meta=meta)
+    split = SplitHeads([l[:, :64].contiguous(memory_format=torch.channels_last) for l in levels],
+                       [l[:, 64:].contiguous(memory_format=torch.channels_last) for l in levels])
+    meta_d = ctx.struct_to_device(meta)
+    out = (ctx.empty((3, 300, 4), torch.float32), ctx.empty((3, 300), torch.float32), ctx.empty((3, 300), torch.int32),
+           torch.zeros((3,), dtype=torch.int32, device="cuda"))
+    with ctx.lock:
+        ctx._enter()
+        ctx.decode_nms_call(split, 2, 0.4, 0.7, 300, False, meta_d, *out)
+    k = want[3].cpu().numpy()
+    assert np.array_equal(out[3].cpu().numpy(), k) and k.min() > 0
+    for a, b in zip(out[:3], want[:3]):
+        for i in range(3):
+            assert torch.equal(a[i, :k[i]], b[i, :k[i]])
+    # the combined view of SplitHeads is the plain Detect output
+    for c, l in zip(split, levels):
+        assert torch.equal(c, l)
+    # retry tier on a list of images
+    with ctx.lock:
+        ctx._enter()
+        out[3].zero_()
+        ctx.decode_nms_call(split, 2, 0.4, 0.7, 300, False, meta_d, *out, images_dev=torch.tensor([2, 0], dtype=torch.int32, device="cuda"), n_images=2)
+    got = out[3].cpu().numpy()
+    assert got[0] == k[0] and got[2] == k[2] and got[1] == 0
