@@ -5,7 +5,7 @@ roofline of the dominant libhvb kernel and the CPU reference path timed beside i
     python bench.py [--gpus N] [--steps K] [--warmup W] [--impl hvb|reference] [--chunk F]
     torchrun --nnodes=1 --nproc-per-node N ... bench.py --gpus N ...
 
-A "step" is one pass of the hot path over one chunk of F synthetic 1080p frames per GPU
+A "step" is one pass of the hot path over one chunk of F (default 64) synthetic 1080p frames per GPU
 (BASELINE.json configs[1] + configs[2]):
     K1a letterbox -> YOLOv8m forward (torch fp32, random init) -> K2a decode+NMS ->
     K3a colour features + K3b crop preprocessing on 12 player boxes / frame -> MobileNetV3 (torch fp32) ->
