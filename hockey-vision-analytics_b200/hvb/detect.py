@@ -93,10 +93,16 @@ class Detector:
         n = len(frames)
         h, w = frames[0].shape[:2]
         key = (n, h, w)
-        slot = self._staging.get(key)
+        slot = self._staging.pop(key, None)
         if slot is None:
-            slot = self._staging[key] = {"bufs": [torch.empty((n, h, w, 3), dtype=torch.uint8).pin_memory() for _ in range(2)],
-                                         "events": [None, None], "next": 0}
+            while len(self._staging) >= 4:                  # keep the pinned buffers of the four most recent shapes only
+                old = self._staging.pop(next(iter(self._staging)))
+                for e in old["events"]:
+                    if e is not None:
+                        e.synchronize()
+            slot = {"bufs": [torch.empty((n, h, w, 3), dtype=torch.uint8).pin_memory() for _ in range(2)],
+                    "events": [None, None], "next": 0}
+        self._staging[key] = slot                           # most recently used last
         i = slot["next"]
         slot["next"] = i ^ 1
         if slot["events"][i] is not None:
