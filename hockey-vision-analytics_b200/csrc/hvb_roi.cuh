@@ -24,6 +24,13 @@ __device__ __forceinline__ hvb_rect hvb_roi_rect(int h, int w, int mode) {
         s.right = (int)__dmul_rn((double)w, 0.7);
         if ((s.bottom - s.top) * (s.right - s.left) == 0) return r;   // empty slice -> whole crop
         return s;
+    } else if (mode == HVB_ROI_SEGMENT) {
+        // fallback mask of SegmentationTeamClassifier.segment_player (team_segmentation.py:87-96); an empty
+        // rectangle stays empty (the reference then reports its "not enough pixels" defaults)
+        r.top = (int)__dmul_rn((double)h, 0.2);
+        r.bottom = (int)__dmul_rn((double)h, 0.6);
+        r.left = (int)__dmul_rn((double)w, 0.3);
+        r.right = (int)__dmul_rn((double)w, 0.7);
     }
     return r;
 }

@@ -26,6 +26,7 @@ struct ColorTables {
     uint16_t ctab[3072];
 };
 static_assert(sizeof(ColorTables) == HVB_TAB_BYTES, "table layout");
+static_assert(sizeof(hvb_jersey_raw) == 120 && sizeof(hvb_color_raw) == 272, "raw struct layout");
 
 __device__ __forceinline__ void load_tables(ColorTables* dst, const uint8_t* src_dev) {
     const uint4* s = reinterpret_cast<const uint4*>(src_dev);
@@ -211,6 +212,109 @@ color_features_kernel(const uint8_t* __restrict__ pixels, const hvb_crop_desc* _
     }
 }
 
+// ---- SegmentationTeamClassifier.extract_jersey_colors (team_segmentation.py:98-148) over a rectangular mask.
+// Same structure as color_features_kernel: private packed counters for <= 255 pixels per thread, one REDUX per
+// quantity per warp, then shared-memory totals.
+struct JerseyAcc {
+    unsigned long long h0, h1, h2;      // packed 8-bit hue bins of the non-white pixels
+    uint32_t white, sat_col, sat_all, val_all;
+    __device__ __forceinline__ void clear() { h0 = h1 = h2 = 0ull; white = sat_col = sat_all = val_all = 0; }
+};
+
+__device__ __forceinline__ void jersey_flush(JerseyAcc& a, uint32_t* s_u32, unsigned long long* s_u64) {
+    const unsigned full = 0xffffffffu;
+    const int lane = threadIdx.x & 31;
+    uint32_t mine = 0;
+#pragma unroll
+    for (int k = 0; k < 18; k++) {
+        unsigned long long w = (k < 8) ? a.h0 : (k < 16) ? a.h1 : a.h2;
+        uint32_t tot = __reduce_add_sync(full, (uint32_t)(w >> (8 * (k & 7))) & 0xffu);
+        if (lane == k) mine = tot;
+    }
+    {
+        uint32_t tot = __reduce_add_sync(full, a.white);
+        if (lane == 18) mine = tot;
+    }
+    if (lane < 19 && mine) atomicAdd(&s_u32[lane], mine);
+    uint32_t t0 = __reduce_add_sync(full, a.sat_col);
+    uint32_t t1 = __reduce_add_sync(full, a.sat_all);
+    uint32_t t2 = __reduce_add_sync(full, a.val_all);
+    unsigned long long m64 = lane == 0 ? t0 : lane == 1 ? t1 : t2;
+    if (lane < 3 && m64) atomicAdd(&s_u64[lane], m64);
+    a.clear();
+}
+
+__global__ void __launch_bounds__(kThreads)
+jersey_color_stats_kernel(const uint8_t* __restrict__ pixels, const hvb_crop_desc* __restrict__ crops, int n,
+                          int roi_mode, const uint8_t* __restrict__ tables_dev, hvb_jersey_raw* __restrict__ out_raw) {
+    __shared__ __align__(16) ColorTables tab;
+    __shared__ uint32_t s_u32[32];
+    __shared__ unsigned long long s_u64[4];
+    load_tables(&tab, tables_dev);
+
+    for (int ci = blockIdx.x; ci < n; ci += gridDim.x) {
+        if (threadIdx.x < 32) s_u32[threadIdx.x] = 0;
+        if (threadIdx.x < 4) s_u64[threadIdx.x] = 0ull;
+        __syncthreads();
+
+        const hvb_crop_desc cd = crops[ci];
+        const hvb_rect rc = hvb_roi_rect(cd.h, cd.w, roi_mode);
+        const int rw = max(rc.right - rc.left, 0), rh = max(rc.bottom - rc.top, 0);
+        const int npx = rw * rh;
+        const uint8_t* base = pixels + cd.offset + (int64_t)rc.top * cd.pitch + (int64_t)rc.left * 3;
+        const float inv_rw = rw > 0 ? 1.0f / (float)rw : 0.0f;
+
+        JerseyAcc acc;
+        acc.clear();
+        const int n_iter = (npx + kThreads - 1) / kThreads;          // uniform trip count, see color_features_kernel
+        for (int it0 = 0; it0 < n_iter; it0 += kBatch) {
+            const int it1 = min(it0 + kBatch, n_iter);
+            for (int it = it0; it < it1; ++it) {
+                const int p = it * kThreads + threadIdx.x;
+                if (p < npx) {
+                    int row = (int)((float)p * inv_rw);
+                    int col = p - row * rw;
+                    if (col < 0) { row--; col += rw; }
+                    if (col >= rw) { row++; col -= rw; }
+                    const uint8_t* px = base + (int64_t)row * cd.pitch + col * 3;
+                    int b = __ldg(px), g = __ldg(px + 1), r = __ldg(px + 2);
+                    int h, s, v, L, A, B;
+                    bgr_to_hsv(tab, b, g, r, h, s, v);
+                    bgr_to_lab(tab, b, g, r, L, A, B);
+                    // np.abs(a - 128) < 10 on uint8 arrays: a < 128 wraps to >= 128, so only 128..137 pass
+                    const bool white = (L > 200) && (A >= 128 && A < 138) && (B >= 128 && B < 138);
+                    if (white) {
+                        acc.white += 1;
+                    } else {
+                        int hb = (h * 205) >> 11;                    // h / 10 for 0 <= h < 180
+                        unsigned long long one = 1ull << ((hb & 7) * 8);
+                        acc.h0 += (hb < 8) ? one : 0ull;
+                        acc.h1 += (hb >= 8 && hb < 16) ? one : 0ull;
+                        acc.h2 += (hb >= 16) ? one : 0ull;
+                        acc.sat_col += s;
+                    }
+                    acc.sat_all += s;
+                    acc.val_all += v;
+                }
+            }
+            __syncwarp();
+            jersey_flush(acc, s_u32, s_u64);
+        }
+        __syncthreads();
+
+        const int f = threadIdx.x;
+        hvb_jersey_raw* o = out_raw + ci;
+        if (f < 18) o->hue_hist[f] = s_u32[f];
+        if (f == 18) o->white = s_u32[18];
+        if (f == 19) o->n = (uint32_t)npx;
+        if (f == 20) o->sat_colored = s_u64[0];
+        if (f == 21) o->sat_all = s_u64[1];
+        if (f == 22) o->val_all = s_u64[2];
+        if (f == 23) { o->roi[0] = rc.top; o->roi[1] = rc.bottom; o->roi[2] = rc.left; o->roi[3] = rc.right; }
+        __syncthreads();
+    }
+}
+
 __global__ void __launch_bounds__(256)
 cvt_hsv_lab_kernel(const uint8_t* __restrict__ bgr, int64_t n_px, const uint8_t* __restrict__ tables_dev,
                    uint8_t* __restrict__ out_hsv, uint8_t* __restrict__ out_lab) {
@@ -324,6 +428,42 @@ int hvb_color_features_host(hvb_ctx* ctx, const uint8_t* pixels_host, size_t pix
     if (out_raw_host)
         HVB_CUDA(cudaMemcpyAsync(out_raw_host, d + off_raw, (size_t)n * sizeof(hvb_color_raw), cudaMemcpyDeviceToHost,
                                  ctx->stream));
+    HVB_CUDA(cudaStreamSynchronize(ctx->stream));
+    return HVB_OK;
+}
+
+int hvb_jersey_color_stats(hvb_ctx* ctx, const uint8_t* pixels_dev, const hvb_crop_desc* crops_dev, int n, int roi_mode,
+                           hvb_jersey_raw* out_raw_dev) {
+    HVB_CHECK_CTX(ctx);
+    HVB_ARG(n >= 0, "n < 0");
+    HVB_ARG(roi_mode >= 0 && roi_mode <= 3, "bad roi_mode");
+    if (n == 0) return HVB_OK;
+    HVB_ARG(pixels_dev && crops_dev && out_raw_dev, "null pointer");
+    int grid = n < ctx->sm_count * 8 ? n : ctx->sm_count * 8;
+    jersey_color_stats_kernel<<<grid, kThreads, 0, ctx->stream>>>(pixels_dev, crops_dev, n, roi_mode,
+                                                                  (const uint8_t*)ctx->tables_dev, out_raw_dev);
+    HVB_LAUNCHED(ctx);
+    return HVB_OK;
+}
+
+int hvb_jersey_color_stats_host(hvb_ctx* ctx, const uint8_t* pixels_host, size_t pixel_bytes,
+                                const hvb_crop_desc* crops_host, int n, int roi_mode, hvb_jersey_raw* out_raw_host) {
+    HVB_CHECK_CTX(ctx);
+    HVB_ARG(n >= 0, "n < 0");
+    if (n == 0) return HVB_OK;
+    HVB_ARG(pixels_host && crops_host && out_raw_host, "null pointer");
+    size_t off_crops = (pixel_bytes + 255) & ~(size_t)255;
+    size_t off_raw = off_crops + (((size_t)n * sizeof(hvb_crop_desc) + 255) & ~(size_t)255);
+    size_t total = off_raw + (size_t)n * sizeof(hvb_jersey_raw);
+    uint8_t* d = nullptr;
+    HVB_TRY(hvb_scratch(ctx, total, (void**)&d));
+    HVB_CUDA(cudaMemcpyAsync(d, pixels_host, pixel_bytes, cudaMemcpyHostToDevice, ctx->stream));
+    HVB_CUDA(cudaMemcpyAsync(d + off_crops, crops_host, (size_t)n * sizeof(hvb_crop_desc), cudaMemcpyHostToDevice,
+                             ctx->stream));
+    HVB_TRY(hvb_jersey_color_stats(ctx, d, (const hvb_crop_desc*)(d + off_crops), n, roi_mode,
+                                   (hvb_jersey_raw*)(d + off_raw)));
+    HVB_CUDA(cudaMemcpyAsync(out_raw_host, d + off_raw, (size_t)n * sizeof(hvb_jersey_raw), cudaMemcpyDeviceToHost,
+                             ctx->stream));
     HVB_CUDA(cudaStreamSynchronize(ctx->stream));
     return HVB_OK;
 }

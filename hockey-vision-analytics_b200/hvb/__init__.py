@@ -27,6 +27,9 @@ def __getattr__(name):
     if name == "TeamClassifier":
         from .team import TeamClassifier
         return TeamClassifier
+    if name == "SegmentationTeamClassifier":
+        from .team_segmentation import SegmentationTeamClassifier
+        return SegmentationTeamClassifier
     if name in ("VideoProcessor", "Config", "FrameResult"):
         from . import video
         return getattr(video, name)

@@ -23,7 +23,7 @@ class HvbError(RuntimeError):
 
 HVB_ERR_CUDA, HVB_ERR_ARG, HVB_ERR_NO_DEVICE, HVB_ERR_CAPACITY, HVB_ERR_UNSUPPORTED = -1, -2, -3, -4, -5
 LB_WHOLE, LB_SLICE_EXACT, LB_SLICE_UNIFORM = 0, 1, 2
-ROI_HYBRID, ROI_SIMPLE, ROI_WHOLE = 0, 1, 2
+ROI_HYBRID, ROI_SIMPLE, ROI_WHOLE, ROI_SEGMENT = 0, 1, 2, 3
 
 # numpy mirrors of the C structs -------------------------------------------------------------
 LB_CLASS = np.dtype([("out_h", "<i4"), ("out_w", "<i4"), ("tiles_per_frame", "<i4"), ("batch", "<i4"),
@@ -40,7 +40,9 @@ CROP_DESC = np.dtype([("offset", "<i8"), ("pitch", "<i4"), ("h", "<i4"), ("w", "
 COLOR_RAW = np.dtype([("hist", "<u4", (34,)), ("counts", "<u4", (3,)), ("n", "<u4"), ("roi", "<u4", (4,)),
                       ("pad_", "<u4", (2,)), ("sums", "<u8", (6,)), ("sumsq", "<u8", (6,))], align=True)
 assert LB_CLASS.itemsize == 24 and LB_TILE.itemsize == 68 and IMG_META.itemsize == 32
-assert CROP_DESC.itemsize == 24 and COLOR_RAW.itemsize == 272
+JERSEY_RAW = np.dtype([("n", "<u4"), ("white", "<u4"), ("hue_hist", "<u4", (18,)), ("sat_colored", "<u8"),
+                       ("sat_all", "<u8"), ("val_all", "<u8"), ("roi", "<i4", (4,))], align=True)
+assert CROP_DESC.itemsize == 24 and COLOR_RAW.itemsize == 272 and JERSEY_RAW.itemsize == 120
 
 _vp, _i, _i64, _f, _d, _sz = C.c_void_p, C.c_int, C.c_int64, C.c_float, C.c_double, C.c_size_t
 _pp = C.POINTER(C.c_void_p)
@@ -100,6 +102,8 @@ PROTOTYPES = {
     "hvb_sppf_pool_concat": [_vp, _vp, _i, _i, _i, _i, _vp],
     "hvb_stem_conv": [_vp, _vp, _vp, _vp, _i, _i, _i, _i, _vp],
     "hvb_color_features_host": [_vp, _vp, _sz, _vp, _i, _i, _vp, _vp],
+    "hvb_jersey_color_stats": [_vp, _vp, _vp, _i, _i, _vp],
+    "hvb_jersey_color_stats_host": [_vp, _vp, _sz, _vp, _i, _i, _vp],
     "hvb_mnv3_preprocess_host": [_vp, _vp, _sz, _vp, _i, _i, _vp, _vp],
     "hvb_merge_nms_host": [_vp, _vp, _vp, _vp, _i, _d, _i, _vp],
     "hvb_iou_cost_host": [_vp, _vp, _i, _vp, _i, _vp, _i, _vp],

@@ -259,6 +259,14 @@ class Context:
             check(self.lib.hvb_color_features(self.handle, ptr(pixels), ptr(crops), n, roi_mode, ptr(out_feat), feat_stride, ptr(raw)))
         return (out_feat, raw) if want_raw else out_feat
 
+    def jersey_color_stats(self, pixels: torch.Tensor, crops: torch.Tensor, n: int, roi_mode: int = _ffi.ROI_SEGMENT):
+        """hvb_jersey_raw[n] as a device uint8 tensor (view it with ``_ffi.JERSEY_RAW`` after ``.cpu().numpy()``)."""
+        with self.lock:
+            self._enter()
+            raw = self.empty((max(n, 1) * _ffi.JERSEY_RAW.itemsize,), torch.uint8)
+            check(self.lib.hvb_jersey_color_stats(self.handle, ptr(pixels), ptr(crops), n, roi_mode, ptr(raw)))
+        return raw
+
     def cvt_hsv_lab(self, bgr: torch.Tensor):
         n_px = bgr.numel() // 3
         with self.lock:
@@ -415,6 +423,15 @@ class Context:
                 check(self.lib.hvb_color_features_host(self.handle, ptr(pixels), pixels.nbytes, ptr(crops), n, roi_mode,
                                                        ptr(feat), ptr(raw)))
         return (feat, raw) if want_raw else feat
+
+    def jersey_color_stats_host(self, pixels: np.ndarray, crops: np.ndarray, roi_mode: int = _ffi.ROI_SEGMENT) -> np.ndarray:
+        n = len(crops)
+        raw = np.zeros((n,), _ffi.JERSEY_RAW)
+        if n:
+            with self.lock:
+                self._enter()
+                check(self.lib.hvb_jersey_color_stats_host(self.handle, ptr(pixels), pixels.nbytes, ptr(crops), n, roi_mode, ptr(raw)))
+        return raw
 
     def mnv3_preprocess_host(self, pixels: np.ndarray, crops: np.ndarray, roi_mode: int = _ffi.ROI_HYBRID):
         n = len(crops)

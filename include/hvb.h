@@ -229,7 +229,11 @@ HVB_API int hvb_crops_from_boxes(hvb_ctx* ctx, const float* xyxy_dev, const int3
 typedef enum {
     HVB_ROI_HYBRID = 0,          /* HybridTeamClassifier.extract_jersey_region, team_hybrid.py:49-64  */
     HVB_ROI_SIMPLE = 1,          /* TeamClassifier.extract_jersey_region, team.py:76-99               */
-    HVB_ROI_WHOLE = 2
+    HVB_ROI_WHOLE = 2,
+    HVB_ROI_SEGMENT = 3          /* the rectangle SegmentationTeamClassifier.segment_player falls back to
+                                  * when GrabCut is unavailable (team_segmentation.py:87-96): rows
+                                  * [int(0.2h), int(0.6h)), cols [int(0.3w), int(0.7w)); only
+                                  * hvb_jersey_color_stats accepts it                                  */
 } hvb_roi_mode;
 
 typedef struct {
@@ -249,6 +253,22 @@ typedef struct {
 HVB_API int hvb_color_features(hvb_ctx* ctx, const uint8_t* pixels_dev, const hvb_crop_desc* crops_dev, int n,
                        int roi_mode, double* out_feat_dev, int64_t feat_row_stride /*doubles, >=49*/,
                        hvb_color_raw* out_raw_dev);
+/* SegmentationTeamClassifier.extract_jersey_colors (team_segmentation.py:98-148) over a rectangular
+ * mask (the colour features without GrabCut).  Same bit-exact HSV / LAB pass as
+ * hvb_color_features, different statistics; the four dictionary values are one division each on the
+ * host (hvb/team_segmentation.py). */
+typedef struct {
+    uint32_t n;                  /* pixels under the mask                                             */
+    uint32_t white;              /* L>200 & 0<=a-128<10 & 0<=b-128<10: the reference subtracts 128 from
+                                  * UINT8 arrays, so a,b below 128 wrap and never count as white        */
+    uint32_t hue_hist[18];       /* np.histogram(H, 18, (0,180)) of the NON-white pixels              */
+    uint64_t sat_colored;        /* sum of S over the non-white pixels                                */
+    uint64_t sat_all;            /* sum of S over all pixels                                          */
+    uint64_t val_all;            /* sum of V over all pixels                                          */
+    int32_t roi[4];              /* top, bottom, left, right actually used                            */
+} hvb_jersey_raw;                /* 120 bytes */
+HVB_API int hvb_jersey_color_stats(hvb_ctx* ctx, const uint8_t* pixels_dev, const hvb_crop_desc* crops_dev, int n,
+                           int roi_mode, hvb_jersey_raw* out_raw_dev);
 /* Test hook: plain per-pixel conversion of n_px BGR pixels (the 2^24 colour-cube test). */
 HVB_API int hvb_cvt_hsv_lab(hvb_ctx* ctx, const uint8_t* bgr_dev, int64_t n_px, uint8_t* out_hsv_dev,
                     uint8_t* out_lab_dev);
@@ -329,6 +349,9 @@ HVB_API int hvb_stem_conv(hvb_ctx* ctx, const float* in_nchw_dev, const float* w
 HVB_API int hvb_color_features_host(hvb_ctx* ctx, const uint8_t* pixels_host, size_t pixel_bytes,
                             const hvb_crop_desc* crops_host, int n, int roi_mode,
                             double* out_feat_host /*[n,49]*/, hvb_color_raw* out_raw_host /*or NULL*/);
+HVB_API int hvb_jersey_color_stats_host(hvb_ctx* ctx, const uint8_t* pixels_host, size_t pixel_bytes,
+                                const hvb_crop_desc* crops_host, int n, int roi_mode,
+                                hvb_jersey_raw* out_raw_host /*[n]*/);
 HVB_API int hvb_mnv3_preprocess_host(hvb_ctx* ctx, const uint8_t* pixels_host, size_t pixel_bytes,
                              const hvb_crop_desc* crops_host, int n, int roi_mode,
                              float* out_host /*[n,3,128,64]*/, uint8_t* out_valid_host /*or NULL*/);
