@@ -123,6 +123,10 @@ def main():
         report("K3a colour features %d crops" % m, timed(lambda: ctx.color_features(frames, cd, m, out_feat=feat), R),
                roi_px * 3 + m * 392, roi_kpx_per_crop=round(roi_px / m / 1e3, 2))
         report("K3b MobileNetV3 prep %d crops" % m, timed(lambda: ctx.mnv3_preprocess(frames, cd, m), R), roi_px * 3 + m * 98304)
+        seg_px = sum((int(h * 0.6) - int(h * 0.2)) * (int(w * 0.7) - int(w * 0.3)) for h, w in zip(desc["h"], desc["w"]))
+        report("K3c jersey colour stats (segmentation rectangle) %d crops" % m,
+               timed(lambda: ctx.jersey_color_stats(frames, cd, m, _ffi.ROI_SEGMENT), R), seg_px * 3 + m * 120,
+               roi_kpx_per_crop=round(seg_px / m / 1e3, 2))
         report("crops_from_boxes %d" % m, timed(lambda: ctx.crops_from_boxes(bx, fi, 1080, 1920), R))
 
     def sec_k4():
