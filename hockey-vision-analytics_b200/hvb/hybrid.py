@@ -9,7 +9,8 @@ Where the arithmetic runs:
   MobileNetV3-small trunk (batched, fp32, TF32 off)                               PyTorch (backbone only)
   StandardScaler fit/transform                                                    K4a kernels
   RBF affinity (tcgen05 Gram + float64 refinement)                                K4a kernels
-  spectral embedding + k-means on the precomputed affinity                        scikit-learn on host (as in the reference)
+  spectral embedding + k-means on the precomputed affinity                        scikit-learn on host (as in the reference);
+                                                                                   opt-in spectral="device": dense eigh on the GPU
   similarity rule + temporal vote (a few integers per crop)                       host
 
 The list-of-numpy-views call surface is kept (crops are packed once and uploaded); the
@@ -48,7 +49,10 @@ class _Scaler:
 
 class HybridTeamClassifier:
     def __init__(self, device: str = "cuda:0", n_clusters: int = 2, trunk: Optional[torch.nn.Module] = None,
-                 seed: int = 0, affinity_mode: int = 0, fold_batchnorm: bool = True):
+                 seed: int = 0, affinity_mode: int = 0, fold_batchnorm: bool = True, spectral: str = "sklearn",
+                 affinity_gamma=1.0):
+        if spectral not in ("sklearn", "device"):
+            raise ValueError("spectral must be 'sklearn' (the reference's solver) or 'device'")
         self.ctx: Context = get_context(device)
         self.device = device
         self.n_clusters = n_clusters
@@ -67,6 +71,8 @@ class HybridTeamClassifier:
         self.cluster_labels = None
         self.affinity_matrix_ = None
         self.affinity_mode = affinity_mode      # 0 = tcgen05 Gram + fp64 refine, 1 = fp64 only
+        self.spectral = spectral                # "device": dense eigensolver on the GPU (hvb/spectral.py), opt-in
+        self.affinity_gamma = affinity_gamma    # 1.0 = the reference; "scale" = 1 / n_features (does not underflow), opt-in
 
     # ------------------------------------------------------------------ geometry (host, O(1))
     def extract_jersey_region(self, crop: np.ndarray) -> np.ndarray:
@@ -168,18 +174,27 @@ class HybridTeamClassifier:
             pn = (p - pmin) / (pmax - pmin + 1e-7) * 0.1
             xs = torch.cat([xs, ctx.to_device(pn.astype(np.float64))], 1).contiguous()
         self.features_normalized_ = xs
-        _, a = ctx.gram_affinity(xs, 1.0, self.affinity_mode, want_d2=False, want_a=True)
+        gamma = 1.0 / xs.shape[1] if self.affinity_gamma == "scale" else float(self.affinity_gamma)
+        _, a = ctx.gram_affinity(xs, gamma, self.affinity_mode, want_d2=False, want_a=True)
         if not cluster:                      # scaler + affinity only (multi-GPU ranks other than the one that clusters)
             self.affinity_matrix_dev_ = a
             self.clusterer = "affinity-only"
             return
         self.affinity_matrix_ = a.cpu().numpy()
         import warnings
-        from sklearn.cluster import SpectralClustering
-        self.clusterer = SpectralClustering(n_clusters=self.n_clusters, affinity="precomputed", n_init=10, random_state=42)
-        with warnings.catch_warnings():
-            warnings.simplefilter("ignore")
-            self.cluster_labels = self.clusterer.fit_predict(self.affinity_matrix_)
+        if self.spectral == "device":
+            from .spectral import DeviceSpectralClustering
+            self.clusterer = DeviceSpectralClustering(n_clusters=self.n_clusters, n_init=10, random_state=42)
+            self.clusterer.affinity_matrix_ = self.affinity_matrix_
+            with warnings.catch_warnings():
+                warnings.simplefilter("ignore")
+                self.cluster_labels = self.clusterer.fit_predict(a)
+        else:
+            from sklearn.cluster import SpectralClustering
+            self.clusterer = SpectralClustering(n_clusters=self.n_clusters, affinity="precomputed", n_init=10, random_state=42)
+            with warnings.catch_warnings():
+                warnings.simplefilter("ignore")
+                self.cluster_labels = self.clusterer.fit_predict(self.affinity_matrix_)
         if raw_stats is not None:
             self._analyze_clusters(raw_stats, self.cluster_labels)
 
