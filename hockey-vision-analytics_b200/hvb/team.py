@@ -8,6 +8,10 @@ the simple HSV rule (team.py:192-198, 264-271).  The segmentation (GrabCut), int
 robust (SigLIP + HDBSCAN) classifiers are outside the hot path and are reported as
 unavailable, exactly as the reference behaves when their imports fail; the hybrid classifier is
 therefore what the default flags route to.
+
+Opt-in: ``use_segmentation="rectangle"`` routes to the GrabCut-free segmentation classifier
+(hvb/team_segmentation.py, K3c) with the reference's cascade for that branch (team.py:141-154, 227-238):
+a failure downgrades to the interactive classifier, which is unavailable, so to the simple rule.
 """
 from __future__ import annotations
 
@@ -33,7 +37,7 @@ class TeamClassifier:
         self.device = device
         self.batch_size = batch_size
         self.ctx = get_context(device)
-        self.use_segmentation = use_segmentation and SEGMENTATION_AVAILABLE
+        self.use_segmentation = bool(use_segmentation == "rectangle" or (use_segmentation and SEGMENTATION_AVAILABLE))
         self.use_interactive = use_interactive and INTERACTIVE_AVAILABLE and not self.use_segmentation
         self.use_robust = use_robust and ROBUST_AVAILABLE and not self.use_interactive and not self.use_segmentation
         self.use_hybrid = (use_hybrid and HYBRID_AVAILABLE and not self.use_robust and not self.use_interactive
@@ -44,7 +48,10 @@ class TeamClassifier:
         self.player_history: Dict[int, List[int]] = defaultdict(list)
         self.history_window = 10
         self.team_assignments = {0: "away", 1: "home"}
-        if self.use_hybrid:
+        if self.use_segmentation:
+            from .team_segmentation import SegmentationTeamClassifier
+            self.segmentation_classifier = SegmentationTeamClassifier(device=device, visualize_segmentation=True)
+        elif self.use_hybrid:
             self.hybrid_classifier = HybridTeamClassifier(device=device, trunk=trunk)
 
     # ------------------------------------------------------------------ simple HSV rule
@@ -81,7 +88,15 @@ class TeamClassifier:
     # ------------------------------------------------------------------ fit / predict routing
     def fit(self, crops: List[np.ndarray], positions: Optional[List[tuple]] = None, frame: Optional[np.ndarray] = None,
             detections=None) -> None:
-        if self.use_hybrid:
+        if self.use_segmentation:
+            try:
+                self.segmentation_classifier.fit(crops, positions=positions)
+            except Exception as e:                          # noqa: BLE001 - mirrors the reference cascade
+                print(f"Segmentation classifier failed: {e}")
+                print("Falling back to interactive classifier")
+                self.use_segmentation = False              # INTERACTIVE_AVAILABLE is False -> simple rule (team.py:147-154)
+                self._simple_fit(crops)
+        elif self.use_hybrid:
             try:
                 self.hybrid_classifier.fit(crops)          # positions are NOT forwarded (team.py:193)
             except Exception as e:                          # noqa: BLE001 - mirrors the reference cascade
@@ -104,6 +119,13 @@ class TeamClassifier:
                 positions: Optional[List[tuple]] = None) -> np.ndarray:
         if not len(crops):
             return np.array([])
+        if self.use_segmentation:
+            try:
+                return self.segmentation_classifier.predict(crops, tracker_ids, positions)
+            except Exception as e:                          # noqa: BLE001
+                print(f"Segmentation prediction failed: {e}")
+                print("Falling back to interactive classifier")
+                self.use_segmentation = False
         if self.use_hybrid:
             try:
                 return self.hybrid_classifier.predict(crops, tracker_ids)
@@ -133,6 +155,15 @@ class TeamClassifier:
         rule, which packs host crops."""
         if xyxy.shape[0] == 0:
             return np.array([])
+        if self.use_segmentation:
+            try:
+                boxes_h = xyxy.cpu().numpy() if hasattr(xyxy, "cpu") else np.asarray(xyxy)
+                fi_h = frame_idx.cpu().numpy() if hasattr(frame_idx, "cpu") else frame_idx
+                return self.segmentation_classifier.predict_from_frames(frames_dev, boxes_h, fi_h, tracker_ids)
+            except Exception as e:                          # noqa: BLE001
+                print(f"Segmentation prediction failed: {e}")
+                print("Falling back to interactive classifier")
+                self.use_segmentation = False
         if self.use_hybrid:
             try:
                 return self.hybrid_classifier.predict_from_frame(frames_dev, xyxy, frame_idx, tracker_ids)
@@ -149,6 +180,8 @@ class TeamClassifier:
         return self.predict([crop_image(frames[int(f)], b) for f, b in zip(fi, boxes)], tracker_ids)
 
     def get_segmentation_masks(self, tracker_ids: List[int]):
+        if self.use_segmentation and hasattr(self, "segmentation_classifier"):
+            return self.segmentation_classifier.get_segmentation_masks(tracker_ids)
         return None
 
     def set_team_names(self, team_names: Dict[int, str]) -> None:

@@ -122,3 +122,30 @@ def test_device_resident_frames_give_the_same_features(ctx, data):
     a = clf.predict_from_frames(torch.from_numpy(np.stack(frames)).cuda(), xyxy, fidx)
     b = clf.predict([crop_image(frames[f], b) for f, b in zip(fidx, xyxy)])
     assert np.array_equal(a, b) and set(a) == {0, 1}
+
+
+def test_router_opt_in_and_cascade(ctx, data, capsys):
+    """TeamClassifier(use_segmentation="rectangle") routes like the reference's default flags do when
+    team_segmentation imports (team.py:47-56, 141-154, 227-238), and a failure lands on the simple HSV rule."""
+    from hvb import TeamClassifier
+    _, crops, tids, n_fit, gold = data
+    tc = TeamClassifier("cuda:0", use_segmentation="rectangle")
+    assert tc.use_segmentation and not tc.use_hybrid and not hasattr(tc, "hybrid_classifier")
+    tc.fit(list(crops[:n_fit]), positions=[(0.0, 0.0)] * n_fit)
+    per = n_fit // 4
+    got = np.concatenate([tc.predict(list(crops[f * per:(f + 1) * per]), tids[f * per:(f + 1) * per]) for f in range(4)])
+    assert np.array_equal(got, gold["predict"])
+    masks = tc.get_segmentation_masks([int(tids[0])])
+    assert set(masks) == {int(tids[0])} and masks[int(tids[0])].dtype == bool
+    assert TeamClassifier("cuda:0").get_segmentation_masks([1]) is None            # default flags: hybrid route
+
+    tc2 = TeamClassifier("cuda:0", use_segmentation="rectangle")
+
+    def boom(*a, **k):
+        raise RuntimeError("planted failure")
+    tc2.segmentation_classifier.predict = boom
+    team_gold = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "team_reference.npz"))
+    out = tc2.predict(list(crops[:n_fit]), tids[:n_fit])
+    assert "Segmentation prediction failed: planted failure" in capsys.readouterr().out
+    assert not tc2.use_segmentation and not tc2.use_hybrid
+    assert np.array_equal(out, team_gold["simple_predict"])                          # the simple rule of team.py
