@@ -83,3 +83,34 @@ def test_restatement_matches_a_live_import_of_the_reference(data):
         a = clf.extract_jersey_colors(crop, clf.segment_player(crop))
         b = sr.extract_jersey_colors(crop, sr.fallback_mask(h, w))
         assert sr.feature_row(a) == sr.feature_row(b)
+
+
+def test_host_side_feature_arithmetic_of_the_product_matches_the_golden_features(data):
+    """hvb.team_segmentation.features_from_raw (host logic of the product, no GPU): exact integer statistics, here
+    produced by real cv2 conversions instead of the K3c kernel, must give the golden float64 features bit for bit."""
+    import cv2
+    from hvb import _ffi
+    from hvb.team_segmentation import DEFAULTS, features_from_raw
+    crops, _, _, gold = data
+    raw = np.zeros(len(crops), _ffi.JERSEY_RAW)
+    for i, c in enumerate(crops):
+        px = c[sr.fallback_mask(*c.shape[:2])]
+        raw[i]["n"] = len(px)
+        if len(px) == 0:
+            continue
+        hsv = cv2.cvtColor(px.reshape(-1, 1, 3), cv2.COLOR_BGR2HSV).reshape(-1, 3).astype(np.int64)
+        lab = cv2.cvtColor(px.reshape(-1, 1, 3), cv2.COLOR_BGR2LAB).reshape(-1, 3).astype(np.int64)
+        white = (lab[:, 0] > 200) & (lab[:, 1] >= 128) & (lab[:, 1] < 138) & (lab[:, 2] >= 128) & (lab[:, 2] < 138)
+        raw[i]["white"] = white.sum()
+        raw[i]["hue_hist"] = np.bincount(hsv[~white, 0] // 10, minlength=18)
+        raw[i]["sat_colored"], raw[i]["sat_all"], raw[i]["val_all"] = hsv[~white, 1].sum(), hsv[:, 1].sum(), hsv[:, 2].sum()
+    got = features_from_raw(raw)
+    assert np.array_equal(got, gold["features"])
+    # fewer than 100 masked pixels -> the reference's defaults; 100+ pixels but <= 50 non-white -> hue 0, mean S of ALL pixels
+    few = np.zeros(2, _ffi.JERSEY_RAW)
+    few[0]["n"], few[0]["white"], few[0]["sat_all"], few[0]["val_all"] = 99, 99, 990, 9900
+    few[1]["n"], few[1]["white"], few[1]["sat_all"], few[1]["sat_colored"], few[1]["val_all"] = 120, 70, 1200, 1100, 24000
+    few[1]["hue_hist"][5] = 50
+    out = features_from_raw(few)
+    assert tuple(out[0]) == DEFAULTS
+    assert tuple(out[1]) == (70 / 120, 0.0, 1200 / 120, 200.0)
