@@ -101,6 +101,7 @@ PROTOTYPES = {
     "hvb_concat_nhwc": [_vp, _vp, _vp, _vp, _i, _i, _i, _i, _vp],
     "hvb_sppf_pool_concat": [_vp, _vp, _i, _i, _i, _i, _vp],
     "hvb_stem_conv": [_vp, _vp, _vp, _vp, _i, _i, _i, _i, _vp],
+    "hvb_pointwise_conv": [_vp, _vp, _i, _vp, _vp, _i64, _i, _i, _i, _vp, _i, _i, _vp, _i, _i, _i, _i],
     "hvb_color_features_host": [_vp, _vp, _sz, _vp, _i, _i, _vp, _vp],
     "hvb_jersey_color_stats": [_vp, _vp, _vp, _i, _i, _vp],
     "hvb_jersey_color_stats_host": [_vp, _vp, _sz, _vp, _i, _i, _vp],

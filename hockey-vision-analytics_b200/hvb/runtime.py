@@ -365,6 +365,30 @@ class Context:
                                         ptr(out2), out2.shape[1] if out2 is not None else 0, out2_off, c2_begin, c2, uh, uw))
         return out1 if out1 is not None else out2
 
+    def pointwise_conv(self, x: torch.Tensor, weight: torch.Tensor, bias: torch.Tensor, act: str = "silu_fast",
+                       out1: Optional[torch.Tensor] = None, out1_off: int = 0, out2: Optional[torch.Tensor] = None,
+                       out2_off: int = 0, c2_begin: int = 0, c2_count: Optional[int] = None) -> torch.Tensor:
+        """K6: 1x1 convolution (weight [c_out, c_in] or [c_out, c_in, 1, 1]) + bias + activation of a channels-last
+        tensor in one tcgen05 GEMM; destinations as in bias_act.  Raises HvbError(UNSUPPORTED) for channel counts the
+        kernel does not tile (the caller then keeps conv2d + bias_act)."""
+        npix, cin = self._nhwc(x)
+        cout = weight.shape[0]
+        if weight.numel() != cout * cin or not weight.is_contiguous() and not weight.is_contiguous(memory_format=torch.channels_last):
+            raise ValueError("weight must be a dense [c_out, c_in(,1,1)] tensor")
+        if out1 is None:
+            out1 = torch.empty((x.shape[0], cout, x.shape[2], x.shape[3]), dtype=torch.float32, device=x.device,
+                               memory_format=torch.channels_last)
+        for t in (out1, out2):
+            if t is not None and self._nhwc(t)[0] != npix:
+                raise ValueError("pixel count mismatch")
+        c2 = (cout if c2_count is None else c2_count) if out2 is not None else 0
+        with self.lock:
+            self._enter()
+            check(self.lib.hvb_pointwise_conv(self.handle, ptr(x), cin, ptr(weight), ptr(bias), npix, cin, cout, self.ACT[act],
+                                              ptr(out1), out1.shape[1], out1_off, ptr(out2),
+                                              out2.shape[1] if out2 is not None else 0, out2_off, c2_begin, c2))
+        return out1
+
     def concat_nhwc(self, sources: Sequence[torch.Tensor], shifts: Optional[Sequence[int]] = None,
                     out: Optional[torch.Tensor] = None) -> torch.Tensor:
         """Channel concat of up to 4 channels-last tensors; source i is nearest-upsampled by 2**shifts[i]."""

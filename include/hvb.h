@@ -343,6 +343,18 @@ HVB_API int hvb_sppf_pool_concat(hvb_ctx* ctx, const float* y0_dev, int n, int h
 HVB_API int hvb_stem_conv(hvb_ctx* ctx, const float* in_nchw_dev, const float* weight_host, const float* bias_host,
                   int n, int h, int w, int c_out, float* out_nhwc_dev);
 
+/* ---------------------------------------------------------------- K6: pointwise convolution + epilogue
+ * A 1x1 convolution of the YOLO forward (ultralytics Conv / C2f.cv1 / C2f.cv2 / SPPF / the last Conv2d of a Detect
+ * branch; hockey/main.py:179-184) on NHWC float32 as one tcgen05 TF32 GEMM with the K5 epilogue fused in:
+ *   out[p, co] = act(sum_ci x[p * x_ld + ci] * w[co * c_in + ci] + bias[co])
+ * written to out1[p * out1_ld + out1_off + co] and, for co in [c2_begin, c2_begin + c2_count), also to
+ * out2[p * out2_ld + out2_off + co - c2_begin] (out2 may be NULL).  act: 0 none, 1 SiLU, 4 fast SiLU (as hvb_bias_act).
+ * c_in must be a multiple of 32 and c_out of 96 or 64 (HVB_ERR_UNSUPPORTED otherwise: the caller keeps the
+ * cuDNN convolution + hvb_bias_act for that layer); pointers 16-byte aligned, pitches / offsets multiples of 4. */
+HVB_API int hvb_pointwise_conv(hvb_ctx* ctx, const float* x_dev, int x_ld, const float* w_dev, const float* bias_dev,
+                       int64_t npix, int c_in, int c_out, int act, float* out1_dev, int out1_ld, int out1_off,
+                       float* out2_dev, int out2_ld, int out2_off, int c2_begin, int c2_count);
+
 /* ---------------------------------------------------------------- host-buffer entry points
  * What a non-Python binding (cgo / JNI / N-API) would call: host in, host out, synchronous.
  * They stage through context-owned pinned + device scratch and run the same kernels. */

@@ -48,7 +48,7 @@ def report(name, ms, nbytes=None, flops=None, **kw):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--reps", type=int, default=20)
-    ap.add_argument("--only", default="", help="comma-separated sections: k1,k2,k3,k4,k4b,track,k5")
+    ap.add_argument("--only", default="", help="comma-separated sections: k1,k2,k3,k4,k4b,track,k5,k6")
     ap.add_argument("--profile", action="store_true", help="one launch per kernel configuration, no timing (for ncu)")
     args = ap.parse_args()
     if args.profile:
@@ -233,8 +233,29 @@ def main():
         sec_k1()
     if want('k2'):
         sec_k2()
+    def sec_k6():
+        # K6 fused pointwise conv vs what it replaces (cuDNN TF32 conv2d + K5 epilogue), YOLOv8m layers at 32 x 1080p
+        CL = torch.channels_last
+        torch.backends.cudnn.allow_tf32 = True
+        torch.backends.cudnn.benchmark = True
+        for tag, hw, cin, cout in (("L2.cv1 96->96 @184x320", (184, 320), 96, 96), ("L2.cv2 192->96 @184x320", (184, 320), 192, 96),
+                                   ("L4.cv1 192->192 @92x160", (92, 160), 192, 192), ("L4.cv2 576->192 @92x160", (92, 160), 576, 192),
+                                   ("L6.cv2 1152->384 @46x80", (46, 80), 1152, 384), ("L8.cv2 1152->576 @23x40", (23, 40), 1152, 576),
+                                   ("Detect 64->64 @92x160", (92, 160), 64, 64)):
+            x = torch.randn((32, cin, hw[0], hw[1]), device="cuda").contiguous(memory_format=CL)
+            w = (torch.randn((cout, cin, 1, 1), device="cuda") / cin ** 0.5).contiguous(memory_format=CL)
+            b = torch.randn(cout, device="cuda")
+            out = torch.empty((32, cout, hw[0], hw[1]), device="cuda").contiguous(memory_format=CL)
+            npix = 32 * hw[0] * hw[1]
+            alg = npix * (cin + cout) * 4
+            report("K6 fused " + tag, timed(lambda: ctx.pointwise_conv(x, w, b, "silu_fast", out1=out), R), alg)
+            report("   cuDNN conv2d + K5 " + tag, timed(lambda: ctx.bias_act(torch.conv2d(x, w), b, "silu_fast"), R), alg)
+            del x, out
+
     if want('k3'):
         sec_k3()
+    if want('k6'):
+        sec_k6()
     if want('k4'):
         sec_k4()
     if want('k4b'):
