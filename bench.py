@@ -38,14 +38,18 @@ METRIC = "hot_path_frames_per_sec_1080p"
 UNIT = "frames/s"
 
 
-def ncu_traffic(kernel_key: str):
+def ncu_traffic(kernel_key: str, launches=None):
     """DRAM bytes per launch (dram__bytes_read.sum + dram__bytes_write.sum) of the roofline kernel from the
-    committed `ncu --set full` capture (profiles/ncu_traffic.json, written from tools/ncu_summary.py output)."""
+    committed `ncu --set full` capture (profiles/ncu_traffic.json, written from tools/ncu_summary.py output).
+    `launches`: only use a per-step capture if it was taken with the same number of launches per step as now."""
     p = os.path.join(ROOT, "profiles", "ncu_traffic.json")
     if not os.path.exists(p):
         return None
     try:
-        return json.load(open(p)).get(kernel_key, {}).get("traffic_bytes")
+        e = json.load(open(p)).get(kernel_key, {})
+        if launches is not None and e.get("launches") != launches:
+            return None
+        return e.get("traffic_bytes")
     except Exception:
         return None
 
@@ -466,7 +470,7 @@ def run_hvb(args, rank, world):
                "traffic": ncu_traffic("K1a_1080p_x%d" % F), "algorithmic_bytes_per_launch": int(k1_bytes), "avg_launch_ms": k1_ms}
     if k5 is not None:
         n5 = k5["launches_per_step"]
-        t5 = ncu_traffic("K5_bias_act_step_x%d" % F)          # summed over the launches of one step
+        t5 = ncu_traffic("K5_bias_act_step_x%d" % F, launches=n5)   # summed over the launches of one step
         roofline = {"kernel": "bias_act_kernel (K5 conv epilogue: bias + SiLU + residual -> dense / concat-slice destinations), "
                               "%d launches per step of %d frames" % (n5, F),
                     "bound": "hbm", "achieved": k5["achieved"], "peak": peak, "peak_source": peak_src, "unit": "GB/s",

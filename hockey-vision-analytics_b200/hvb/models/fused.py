@@ -7,7 +7,8 @@ SiLU, adds the Bottleneck residual and writes the result both where the next con
 into its slice of the C2f / Detect concat buffer; the neck's Upsample + Concat never run as passes of
 their own either (the producing epilogue writes the 2x2-replicated pixels straight into the concat
 buffer); SPPF's four-way concat is one `hvb_concat_nhwc` pass; layer 0 reads K1's NCHW output directly
-(`hvb_stem_conv`).
+(`hvb_stem_conv`); pointwise (1x1) layers with up to 192 output channels skip cuDNN altogether and run as one
+`hvb_pointwise_conv` launch (K6: tcgen05 TF32 GEMM with the same epilogue and destinations).
 
 The layer graph is ultralytics 8.3.148 `yolov8.yaml` (the model the reference loads at
 hockey/main.py:77 and runs at :179-184), same as hvb.models.yolov8.YOLOv8 whose (conv+bn folded)
@@ -38,6 +39,18 @@ class _Conv:
         b = conv.bias.detach() if conv.bias is not None else torch.zeros(conv.out_channels)
         self.b = b.to(device).float().contiguous()
         self.stride, self.padding, self.cout = conv.stride, conv.padding, conv.out_channels
+        self.cin = conv.in_channels
+        # pointwise layers can run as one K6 launch (tcgen05 GEMM + epilogue); measured faster than cuDNN + K5 up to
+        # 192 output channels, beyond that one 128 x 96 tile per CTA re-reads too much from L2
+        self.pointwise = (tuple(conv.kernel_size) == (1, 1) and tuple(conv.stride) == (1, 1) and tuple(conv.padding) == (0, 0)
+                          and tuple(conv.dilation) == (1, 1) and conv.groups == 1 and self.cin % 32 == 0
+                          and (self.cout % 96 == 0 or self.cout % 64 == 0) and self.cout <= 192)
+        # K6 feeds fp32 bits to the tensor core, which drops the low 13 mantissa bits; the (static) weights are rounded
+        # to TF32 here once, to nearest, so only the activations are truncated
+        self.w_tf32 = None
+        if self.pointwise:
+            bits = self.w.reshape(self.cout, self.cin).contiguous().view(torch.int32)
+            self.w_tf32 = ((bits + 0x1000) & ~0x1FFF).view(torch.float32).contiguous()
 
     def raw(self, x):
         y = torch.conv2d(x, self.w, None, self.stride, self.padding)
@@ -47,7 +60,7 @@ class _Conv:
 
 
 class FusedYOLOv8:
-    def __init__(self, model: YOLOv8, ctx, stem_kernel: bool = True, exact_silu: bool = False):
+    def __init__(self, model: YOLOv8, ctx, stem_kernel: bool = True, exact_silu: bool = False, pointwise_kernel=None):
         import copy
         m = copy.deepcopy(model).eval()
         if any(isinstance(x.bn, torch.nn.BatchNorm2d) for x in m.modules() if isinstance(x, ConvBnAct)):
@@ -62,6 +75,10 @@ class FusedYOLOv8:
         self.stem_b = m.b0.conv.bias.detach().float().cpu().contiguous().numpy()
         self.use_stem = stem_kernel and self.stem_w.shape[0] in (16, 32, 48, 64)
         self._lib, self._h = ctx.lib, ctx.handle
+        # K6 computes in TF32 like cuDNN's default convolutions; when the caller has turned TF32 off (fp32 convolutions
+        # requested) the pointwise layers stay on cuDNN + K5.  None = follow torch.backends.cudnn.allow_tf32 as of now.
+        self.use_pointwise = bool(torch.backends.cudnn.allow_tf32) if pointwise_kernel is None else bool(pointwise_kernel)
+        self.pw_launches = 0
         # SiLU flavour of the epilogue: the approximate-unit version (<= 1e-6 relative error) keeps the pass HBM-bound
         self._silu = _SILU_EXACT if exact_silu else _SILU_FAST
         # measurement hook (bench.py): when set to a list, every epilogue launch is bracketed by CUDA events on the
@@ -94,11 +111,34 @@ class FusedYOLOv8:
             log.append((nbytes, e0, e1))
         return out1
 
+    def _pw_ok(self, k: _Conv, x, off1=0, out2=None, off2=0, c2b=0, c2n=None, up2=False, res=None, **_):
+        return (self.use_pointwise and k.pointwise and not up2 and res is None and x.shape[1] == k.cin
+                and x.is_contiguous(memory_format=CL) and off1 % 4 == 0 and off2 % 4 == 0 and c2b % 4 == 0
+                and (c2n is None or c2n % 4 == 0) and (out2 is None or out2.shape[1] % 4 == 0))
+
+    def _pw(self, k: _Conv, x, act=None, out1=None, off1=0, out2=None, off2=0, c2b=0, c2n=None, up2=False, res=None):
+        """K6: the whole Conv (1x1 convolution + bias + SiLU, same destinations as _epi) in one launch."""
+        n, _, h, w = x.shape
+        if act is None:
+            act = self._silu
+        if out1 is None:
+            out1 = self._buf(n, k.cout, h, w)
+        if c2n is None:
+            c2n = k.cout
+        p = lambda t: C.c_void_p(t.data_ptr()) if t is not None else C.c_void_p(0)
+        _ffi.check(self._lib.hvb_pointwise_conv(self._h, p(x), k.cin, p(k.w_tf32), p(k.b), n * h * w, k.cin, k.cout, act,
+                                                p(out1), out1.shape[1], off1, p(out2),
+                                                out2.shape[1] if out2 is not None else 0, off2, c2b, c2n if out2 is not None else 0))
+        self.pw_launches += 1
+        return out1
+
     def _buf(self, n, c, h, w):
         return torch.empty((n, c, h, w), dtype=torch.float32, device=self.ctx.device, memory_format=CL)
 
     def _cba(self, mod: ConvBnAct, x, dest=None):
         k = self.convs[mod.conv]
+        if self._pw_ok(k, x, **(dest or {})):
+            return self._pw(k, x, **(dest or {}))
         return self._epi(k.raw(x), k.b, **(dest or {}))
 
     def _c2f(self, mod: C2f, x, dest=None):
@@ -108,7 +148,10 @@ class FusedYOLOv8:
         k = self.convs[mod.cv1.conv]
         y = self._buf(n, c, h, w)
         # cv1: both halves into the concat buffer, second half also dense for the first Bottleneck
-        self._epi(k.raw(x), k.b, out1=cat, off1=0, out2=y, off2=0, c2b=c, c2n=c)
+        if self._pw_ok(k, x, out2=y, c2b=c, c2n=c):
+            self._pw(k, x, out1=cat, off1=0, out2=y, off2=0, c2b=c, c2n=c)
+        else:
+            self._epi(k.raw(x), k.b, out1=cat, off1=0, out2=y, off2=0, c2b=c, c2n=c)
         for i, bt in enumerate(mod.m):
             a = self._cba(bt.cv1, y)
             k2 = self.convs[bt.cv2.conv]
@@ -154,7 +197,7 @@ class FusedYOLOv8:
             for branch, dst in ((det.cv2[i], boxes), (det.cv3[i], clss)):
                 t = self._cba(branch[1], self._cba(branch[0], x))
                 k = self.convs[branch[2]]
-                dst.append(self._epi(k.raw(t), k.b, act=_NONE))
+                dst.append(self._pw(k, t, act=_NONE) if self._pw_ok(k, t) else self._epi(k.raw(t), k.b, act=_NONE))
         return SplitHeads(boxes, clss)
 
     # ------------------------------------------------------------------ forward

@@ -71,3 +71,58 @@ def test_unsupported_channel_counts_fail_loudly(ctx):
     x = torch.randn((1, 64, 8, 8), device="cuda").contiguous(memory_format=CL)
     with pytest.raises(HvbError):
         ctx.pointwise_conv(x, torch.randn(80, 64, device="cuda"), torch.zeros(80, device="cuda"))
+
+
+def test_fused_forward_routes_pointwise_layers_through_k6(ctx):
+    """YOLOv8m forward with the <= 192-channel pointwise layers on K6 vs the same runner on cuDNN TF32 + K5, both against
+    the fp32 module: K6 must stay in the precision class of the library path it replaces."""
+    import copy
+    from hvb.models import build_yolov8
+    from hvb.models.fused import FusedYOLOv8
+    from hvb.models.yolov8 import fuse_conv_bn
+    prev = torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32
+    try:
+        model = build_yolov8("m", 2, 3)
+        x = torch.rand(2, 3, 96, 160, generator=torch.Generator().manual_seed(9)).cuda()
+        torch.backends.cudnn.allow_tf32 = False
+        torch.backends.cuda.matmul.allow_tf32 = False
+        with torch.no_grad():
+            ref = fuse_conv_bn(copy.deepcopy(model)).cuda()(x)
+        off = FusedYOLOv8(model, ctx)                                  # TF32 off at construction: K6 must not be used
+        off(x)
+        assert not off.use_pointwise and off.pw_launches == 0
+        torch.backends.cudnn.allow_tf32 = True
+        lib_run, k6_run = FusedYOLOv8(model, ctx, pointwise_kernel=False), FusedYOLOv8(model, ctx)
+        assert k6_run.use_pointwise
+        lib, k6 = lib_run(x), k6_run(x)
+        # C2f.cv1 + C2f.cv2 of b2, b4, h15 and the three 64 -> 64 Detect convolutions
+        assert lib_run.pw_launches == 0 and k6_run.pw_launches == 9
+        errs = []
+        for r, a, b in zip(ref, lib, k6):
+            scale = r.abs().max().item()
+            errs.append(((a - r).abs().max().item() / scale, (b - r).abs().max().item() / scale))
+        print("relative error vs fp32 per head (cuDNN TF32 path, K6 path):", [(round(a, 6), round(b, 6)) for a, b in errs])
+        for e_lib, e_k6 in errs:
+            assert e_k6 <= 5 * e_lib + 5e-3
+    finally:
+        torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32 = prev
+
+
+def test_detector_with_k6_agrees_with_the_library_path(ctx):
+    """Through Detector (K1a -> forward -> K2a), CUDA-graph replay included: strongest detections agree."""
+    from hvb import Detector
+    from hvb.models import build_yolov8
+    from hvb.synth import rink_frame
+    rng = np.random.default_rng(3)
+    frame = rink_frame(rng, 720, 1280, 8)[0]
+    model = build_yolov8("m", 2, 1)
+    a = Detector(model, "cuda:0", imgsz=640, conf=2e-3, fuse=True, channels_last=True, cuda_graph=False)
+    g = Detector(model, "cuda:0", imgsz=640, conf=2e-3, fuse=True, channels_last=True, cuda_graph=True)
+    b = Detector(model, "cuda:0", imgsz=640, conf=2e-3, fuse=True, channels_last=True, cuda_graph=False)
+    b.runner.use_pointwise = False
+    da, dg, db = a(frame), g(frame), b(frame)
+    assert a.runner.pw_launches > 0 and b.runner.pw_launches == 0
+    assert len(da) == len(dg) and np.array_equal(da.xyxy, dg.xyxy) and np.array_equal(da.confidence, dg.confidence)
+    k = min(10, len(da), len(db))
+    ia, ib = np.argsort(-da.confidence)[:k], np.argsort(-db.confidence)[:k]
+    np.testing.assert_allclose(da.confidence[ia], db.confidence[ib], rtol=0, atol=2e-3)
