@@ -7,7 +7,7 @@ SiLU, adds the Bottleneck residual and writes the result both where the next con
 into its slice of the C2f / Detect concat buffer; the neck's Upsample + Concat never run as passes of
 their own either (the producing epilogue writes the 2x2-replicated pixels straight into the concat
 buffer); SPPF's four-way concat is one `hvb_concat_nhwc` pass; layer 0 reads K1's NCHW output directly
-(`hvb_stem_conv`); pointwise (1x1) layers with up to 192 output channels skip cuDNN altogether and run as one
+(`hvb_stem_conv`); the pointwise (1x1) layers where it is faster (few channels, many pixels) skip cuDNN and run as one
 `hvb_pointwise_conv` launch (K6: tcgen05 TF32 GEMM with the same epilogue and destinations).
 
 The layer graph is ultralytics 8.3.148 `yolov8.yaml` (the model the reference loads at
@@ -40,11 +40,14 @@ class _Conv:
         self.b = b.to(device).float().contiguous()
         self.stride, self.padding, self.cout = conv.stride, conv.padding, conv.out_channels
         self.cin = conv.in_channels
-        # pointwise layers can run as one K6 launch (tcgen05 GEMM + epilogue); measured faster than cuDNN + K5 up to
-        # 192 output channels, beyond that one 128 x 96 tile per CTA re-reads too much from L2
+        # pointwise layers can run as one K6 launch (tcgen05 GEMM + epilogue).  Routing follows the per-layer times
+        # measured INSIDE the YOLOv8m forward (profiles/r01_k6_pointwise.md): K6 wins for c_out <= 96 and (on par) for
+        # 192 -> 192; with more input channels one 128 x 96 tile per CTA re-reads X and W from L2 too
+        # often (9 TB/s of L2 traffic at 576 -> 192) and cuDNN + K5 stays ahead
         self.pointwise = (tuple(conv.kernel_size) == (1, 1) and tuple(conv.stride) == (1, 1) and tuple(conv.padding) == (0, 0)
                           and tuple(conv.dilation) == (1, 1) and conv.groups == 1 and self.cin % 32 == 0
-                          and (self.cout % 96 == 0 or self.cout % 64 == 0) and self.cout <= 192)
+                          and (self.cout % 96 == 0 or self.cout % 64 == 0)
+                          and (self.cout <= 96 or (self.cout == 192 and self.cin <= 192)))    # only what was measured
         # K6 feeds fp32 bits to the tensor core, which drops the low 13 mantissa bits; the (static) weights are rounded
         # to TF32 here once, to nearest, so only the activations are truncated
         self.w_tf32 = None

@@ -95,8 +95,9 @@ def test_fused_forward_routes_pointwise_layers_through_k6(ctx):
         lib_run, k6_run = FusedYOLOv8(model, ctx, pointwise_kernel=False), FusedYOLOv8(model, ctx)
         assert k6_run.use_pointwise
         lib, k6 = lib_run(x), k6_run(x)
-        # C2f.cv1 + C2f.cv2 of b2, b4, h15 and the three 64 -> 64 Detect convolutions
-        assert lib_run.pw_launches == 0 and k6_run.pw_launches == 9
+        # C2f.cv1 + C2f.cv2 of b2 (96->96, 192->96), C2f.cv1 of b4 (192->192) and the three 64 -> 64 Detect convolutions;
+        # the 576->192 / 384->192 layers stay on cuDNN + K5 (measured faster there)
+        assert lib_run.pw_launches == 0 and k6_run.pw_launches == 6
         errs = []
         for r, a, b in zip(ref, lib, k6):
             scale = r.abs().max().item()
