@@ -46,10 +46,12 @@ def ncu_traffic(kernel_key: str, launches=None):
     if not os.path.exists(p):
         return None
     try:
-        e = json.load(open(p)).get(kernel_key, {})
-        if launches is not None and e.get("launches") != launches:
-            return None
-        return e.get("traffic_bytes")
+        d = json.load(open(p))
+        for key in (kernel_key, kernel_key + "_k6"):      # "_k6": the capture minus the launches K6 now replaces
+            e = d.get(key, {})
+            if e and (launches is None or e.get("launches") == launches):
+                return e.get("traffic_bytes")
+        return None
     except Exception:
         return None
 
@@ -491,7 +493,7 @@ def run_hvb(args, rank, world):
                        "frames_per_step_per_gpu": F, "players_per_frame": PLAYERS, "team_boxes": "planted",
                        "backbones": "convolutions in torch/cuDNN (fp32 storage, conv+bn folded, channels_last, cudnn.benchmark, TF32 for YOLO / "
                                     "TF32 off for MobileNetV3); everything between the YOLO convolutions (bias, SiLU, residual, concat, "
-                                    "upsample, layer 0) in libhvb K5 kernels",
+                                    "upsample, layer 0) in libhvb K5 kernels; the pointwise convolutions with few channels as single K6 launches (tcgen05 TF32 GEMM + epilogue)",
                        "l2": "inputs larger than L2 (%.0f MB frames + %.0f MB letterboxed per step)" % (frames.nbytes / 1e6, k1_bytes / 1e6),
                        "parallelism": "frame chunks sharded per GPU, no data-path collective; one NCCL feature all-gather at fit"},
             "e2e": {"value": fps_e2e, "unit": UNIT, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h)},
