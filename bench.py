@@ -324,7 +324,7 @@ def run_hvb(args, rank, world):
     achieved = k1_bytes / (k1_ms / 1e3) / 1e9
 
     # ---- roofline of the DOMINANT libhvb kernel of the step: the K5 conv epilogue (bias_act_kernel, ~28 % of the step,
-    # 82 launches).  Every launch of three more steps is bracketed by CUDA events on its launching stream.
+    # 82 launches, 76 since K6 took six of them together with their convolutions).  Every launch of three more steps is bracketed by CUDA events on its launching stream.
     runner = path.detector.runner
     k5 = None
     if runner is not None:
