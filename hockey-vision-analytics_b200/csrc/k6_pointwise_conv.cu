@@ -120,11 +120,11 @@ __device__ __forceinline__ void st256(float* p, const float4& a, const float4& b
 
 // STAGES = 3: two CTAs per SM; STAGES = 2 (short c_in loops): three CTAs per SM
 template <int BN, int ACT, int kStages>
-__global__ void __launch_bounds__(kThreads, kStages == 2 ? 3 : 2)
+__global__ void __launch_bounds__(kThreads, (kStages == 2 && BN <= 128) ? 3 : 2)
 pointwise_conv_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant__ CUtensorMap tmap_w,
                       const __grid_constant__ PwArgs a) {
     constexpr int kWTileBytes = BN * kBK * 4;
-    constexpr uint32_t kTmemCols = BN <= 64 ? 64 : 128;
+    constexpr uint32_t kTmemCols = BN <= 64 ? 64 : BN <= 128 ? 128 : 256;
     constexpr uint32_t kIdesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(kBM >> 4) << 24);
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
@@ -322,7 +322,11 @@ int hvb_pointwise_conv(hvb_ctx* ctx, const float* x_dev, int x_ld, const float* 
         HVB_ARG(out2_ld >= out2_off + c2_count && (out2_ld & 3) == 0 && (out2_off & 3) == 0 && ((uintptr_t)out2_dev & 15) == 0, "out2 pitch / offset / alignment");
     }
     HVB_ARG(npix < ((int64_t)1 << 31), "npix too large for one tensor map");
-    const int bn = (c_out % 96 == 0) ? 96 : 64;
+    // HVB_PW_TILE=192 (experimental, not validated on hardware in round 1): one 128 x 192 tile per CTA for c_out % 192 == 0,
+    // i.e. 29 % less L2 -> SM traffic per output than two 128 x 96 tiles; TMEM 256 columns, two CTAs per SM
+    static int wide_tile = -1;
+    if (wide_tile < 0) { const char* e = getenv("HVB_PW_TILE"); wide_tile = (e && atoi(e) == 192) ? 1 : 0; }
+    const int bn = (wide_tile && c_out % 192 == 0) ? 192 : (c_out % 96 == 0) ? 96 : 64;
     EncodeTiledFn encode = nullptr;
     HVB_TRY(pw_encode_fn(&encode));
     CUtensorMap mx, mw;
@@ -338,6 +342,7 @@ int hvb_pointwise_conv(hvb_ctx* ctx, const float* x_dev, int x_ld, const float* 
                                    ((uintptr_t)out2_dev & 31) == 0));
     const int64_t tiles = ((npix + kBM - 1) / kBM) * a.n_tiles_n;
     HVB_ARG(tiles < ((int64_t)1 << 31), "too many tiles");
+    if (bn == 192) return pw_dispatch<192>(ctx, act, mx, mw, a, tiles);
     return bn == 96 ? pw_dispatch<96>(ctx, act, mx, mw, a, tiles) : pw_dispatch<64>(ctx, act, mx, mw, a, tiles);
 }
 
