@@ -5,10 +5,25 @@
 #include <stdint.h>
 #include <stdio.h>
 #include <stdarg.h>
+#include <map>
 #include <string>
+#include <utility>
 #include <vector>
 
 #include "hvb.h"
+
+// Device work areas of the multi-kernel ops (K2a's counters + candidate key lists, hvb_gather_tiles' slot bases, the
+// Gram operands).  One set per (stream, stream-capture id): launches that libhvb's caller issues on different streams,
+// or captures into different CUDA graphs, never share an area, so they may run concurrently; launches on one stream
+// are ordered by the stream.
+struct hvb_work_area {
+    void* k2 = nullptr;                 // [ctr | keys]
+    size_t k2_bytes = 0, k2_ctr_bytes = 0;
+    void* s2 = nullptr;
+    size_t s2_bytes = 0;
+    void* s3 = nullptr;
+    size_t s3_bytes = 0;
+};
 
 struct hvb_ctx {
     int device = 0;
@@ -23,15 +38,9 @@ struct hvb_ctx {
     // growable scratch used by the *_host entry points and by multi-kernel ops
     void* scratch_dev = nullptr;
     size_t scratch_bytes = 0;
-    void* scratch2_dev = nullptr;
-    size_t scratch2_bytes = 0;
-    void* scratch3_dev = nullptr;
-    size_t scratch3_bytes = 0;
     void* pinned = nullptr;
     size_t pinned_bytes = 0;
-    // K2a split-scan work area: device counters (kept zero between launches) + per-image candidate key lists
-    void* k2_work_dev = nullptr;
-    size_t k2_work_bytes = 0, k2_ctr_bytes = 0;
+    std::map<std::pair<uintptr_t, unsigned long long>, hvb_work_area> work;   // key: (stream handle, capture id or 0)
     // CUDA-graph support: once set, work buffers replaced by growth are kept alive (captured graphs may point at them)
     bool retain_buffers = false;
     std::vector<void*> retired;
@@ -39,9 +48,11 @@ struct hvb_ctx {
 
 void hvb_set_error(const char* fmt, ...);
 int hvb_cuda_fail(cudaError_t e, const char* what, const char* file, int line);
-int hvb_scratch(hvb_ctx* ctx, size_t bytes, void** out);     // device scratch #1 (grow-only)
-int hvb_scratch2(hvb_ctx* ctx, size_t bytes, void** out);    // device scratch #2 (grow-only)
-int hvb_scratch3(hvb_ctx* ctx, size_t bytes, void** out);    // device scratch #3 (grow-only)
+int hvb_scratch(hvb_ctx* ctx, size_t bytes, void** out);     // device scratch #1 (grow-only; only the synchronous *_host entry points)
+int hvb_scratch2(hvb_ctx* ctx, size_t bytes, void** out);    // device scratch #2 of the current stream's work area (grow-only)
+int hvb_scratch3(hvb_ctx* ctx, size_t bytes, void** out);    // device scratch #3 of the current stream's work area (grow-only)
+// K2a work area of the current stream: counters (zero between launches) + [images][cap] 64-bit keys
+int hvb_k2_work(hvb_ctx* ctx, int images, int cap, unsigned long long** keys, int32_t** ctr);
 int hvb_pinned(hvb_ctx* ctx, size_t bytes, void** out);      // pinned host staging (grow-only)
 int hvb_capturing(hvb_ctx* ctx, const char* what);           // HVB_ERR_UNSUPPORTED (with message) if ctx->stream is being captured
 

@@ -56,14 +56,85 @@ int hvb_scratch(hvb_ctx* ctx, size_t bytes, void** out) {
     *out = ctx->scratch_dev;
     return HVB_OK;
 }
+// ---- per-(stream, capture) work areas -------------------------------------------------------------------------------
+static int capture_id(hvb_ctx* ctx, unsigned long long* id) {
+    cudaStreamCaptureStatus st = cudaStreamCaptureStatusNone;
+    unsigned long long cid = 0;
+    *id = 0;
+    if (cudaStreamGetCaptureInfo(ctx->stream, &st, &cid) != cudaSuccess) { (void)cudaGetLastError(); return HVB_OK; }
+    if (st == cudaStreamCaptureStatusActive) *id = cid;
+    return HVB_OK;
+}
+
+static hvb_work_area* work_area(hvb_ctx* ctx, bool* capturing) {
+    unsigned long long cid = 0;
+    capture_id(ctx, &cid);
+    *capturing = cid != 0;
+    return &ctx->work[std::make_pair((uintptr_t)ctx->stream, cid)];
+}
+
+// (Re)allocate one buffer of a work area.  Outside capture the stream that owns the area is drained before the old
+// buffer goes away; during capture earlier nodes of the graph may point at the old buffer, so it is retired (kept until
+// the context is destroyed), and the allocation itself runs with this thread's capture mode relaxed (cudaMalloc is a
+// "potentially unsafe" call under the global mode torch.cuda.graph uses).
+static int work_grow(hvb_ctx* ctx, bool capturing, void** buf, size_t* have, size_t want, size_t zero_bytes) {
+    if (*buf && *have >= want) return HVB_OK;
+    const size_t n = want + want / 4 + 4096;
+    cudaStreamCaptureMode mode = cudaStreamCaptureModeRelaxed;
+    if (capturing) HVB_CUDA(cudaThreadExchangeStreamCaptureMode(&mode));
+    cudaError_t e = cudaSuccess;
+    if (*buf) {
+        if (capturing || ctx->retain_buffers) {
+            ctx->retired.push_back(*buf);
+        } else {
+            e = cudaStreamSynchronize(ctx->stream);
+            if (e == cudaSuccess) e = cudaFree(*buf);
+        }
+        *buf = nullptr;
+        *have = 0;
+    }
+    if (e == cudaSuccess) e = cudaMalloc(buf, n);
+    if (capturing) (void)cudaThreadExchangeStreamCaptureMode(&mode);
+    if (e != cudaSuccess) return hvb_cuda_fail(e, "work area allocation", __FILE__, __LINE__);
+    *have = n;
+    // stream-ordered before the first kernel that uses it (inside a capture: a memset node at the head of every replay)
+    if (zero_bytes) HVB_CUDA(cudaMemsetAsync(*buf, 0, zero_bytes, ctx->stream));
+    return HVB_OK;
+}
+
 int hvb_scratch2(hvb_ctx* ctx, size_t bytes, void** out) {
-    HVB_TRY(grow(ctx, &ctx->scratch2_dev, &ctx->scratch2_bytes, bytes, false));
-    *out = ctx->scratch2_dev;
+    bool cap = false;
+    hvb_work_area* w = work_area(ctx, &cap);
+    HVB_TRY(work_grow(ctx, cap, &w->s2, &w->s2_bytes, bytes, 0));
+    *out = w->s2;
     return HVB_OK;
 }
 int hvb_scratch3(hvb_ctx* ctx, size_t bytes, void** out) {
-    HVB_TRY(grow(ctx, &ctx->scratch3_dev, &ctx->scratch3_bytes, bytes, false));
-    *out = ctx->scratch3_dev;
+    bool cap = false;
+    hvb_work_area* w = work_area(ctx, &cap);
+    HVB_TRY(work_grow(ctx, cap, &w->s3, &w->s3_bytes, bytes, 0));
+    *out = w->s3;
+    return HVB_OK;
+}
+int hvb_k2_work(hvb_ctx* ctx, int images, int cap, unsigned long long** keys, int32_t** ctr) {
+    const size_t ctr_bytes = (((size_t)images * 2 * sizeof(int32_t)) + 255) & ~(size_t)255;
+    const size_t key_bytes = (size_t)images * cap * sizeof(unsigned long long);
+    bool capturing = false;
+    hvb_work_area* w = work_area(ctx, &capturing);
+    if (!w->k2 || ctr_bytes > w->k2_ctr_bytes || key_bytes > w->k2_bytes - w->k2_ctr_bytes) {
+        const size_t ctr_cap = ctr_bytes * 2;
+        size_t have = 0;                                     // force a fresh buffer: the counter / key split moves
+        void* old = w->k2;
+        if (old) {
+            if (capturing || ctx->retain_buffers) ctx->retired.push_back(old);
+            else { HVB_CUDA(cudaStreamSynchronize(ctx->stream)); HVB_CUDA(cudaFree(old)); }
+            w->k2 = nullptr;
+        }
+        HVB_TRY(work_grow(ctx, capturing, &w->k2, &have, ctr_cap + key_bytes * 2, ctr_cap));
+        w->k2_bytes = have; w->k2_ctr_bytes = ctr_cap;
+    }
+    *ctr = reinterpret_cast<int32_t*>(w->k2);
+    *keys = reinterpret_cast<unsigned long long*>(reinterpret_cast<uint8_t*>(w->k2) + w->k2_ctr_bytes);
     return HVB_OK;
 }
 int hvb_pinned(hvb_ctx* ctx, size_t bytes, void** out) {
@@ -128,6 +199,9 @@ int hvb_ctx_create(int device, hvb_ctx** out_ctx) {
     memcpy(tab.data() + HVB_TAB_CTAB, kHvbLabCbrtTab, sizeof(kHvbLabCbrtTab));
     HVB_CUDA(cudaMalloc(&c->tables_dev, HVB_TAB_BYTES));
     HVB_CUDA(cudaMemcpy(c->tables_dev, tab.data(), HVB_TAB_BYTES, cudaMemcpyHostToDevice));
+    // the copy above is ordered on the legacy stream only; the kernels run on non-blocking streams that do not
+    // synchronise with it, so make the upload globally visible before the context is handed out
+    HVB_CUDA(cudaDeviceSynchronize());
     *out_ctx = c;
     return HVB_OK;
 }
@@ -144,9 +218,11 @@ int hvb_ctx_destroy(hvb_ctx* ctx) {
     cudaDeviceSynchronize();
     if (ctx->tables_dev) cudaFree(ctx->tables_dev);
     if (ctx->scratch_dev) cudaFree(ctx->scratch_dev);
-    if (ctx->scratch2_dev) cudaFree(ctx->scratch2_dev);
-    if (ctx->scratch3_dev) cudaFree(ctx->scratch3_dev);
-    if (ctx->k2_work_dev) cudaFree(ctx->k2_work_dev);
+    for (auto& kv : ctx->work) {
+        if (kv.second.k2) cudaFree(kv.second.k2);
+        if (kv.second.s2) cudaFree(kv.second.s2);
+        if (kv.second.s3) cudaFree(kv.second.s3);
+    }
     for (void* p : ctx->retired) cudaFree(p);
     if (ctx->pinned) cudaFreeHost(ctx->pinned);
     if (ctx->ev_start) cudaEventDestroy(ctx->ev_start);

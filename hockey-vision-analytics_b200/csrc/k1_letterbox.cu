@@ -608,6 +608,9 @@ int hvb_lb_plan_create(hvb_ctx* ctx, int n_frames, int frame_h, int frame_w, int
     cudaError_t e = cudaMalloc(&p->dev, total);
     if (e != cudaSuccess) { delete p; return hvb_cuda_fail(e, "cudaMalloc(plan)", __FILE__, __LINE__); }
     e = cudaMemcpy(p->dev, host.data(), total, cudaMemcpyHostToDevice);
+    // a pageable-source cudaMemcpy may return before the DMA lands, and the kernels run on non-blocking streams that do
+    // not order against the legacy stream: finish the upload here (plan creation is a one-off)
+    if (e == cudaSuccess) e = cudaDeviceSynchronize();
     if (e != cudaSuccess) { cudaFree(p->dev); delete p; return hvb_cuda_fail(e, "cudaMemcpy(plan)", __FILE__, __LINE__); }
     p->jobs_dev = (LbJob*)((uint8_t*)p->dev + o_jobs);
     p->blk2job_dev = (LbBlock*)((uint8_t*)p->dev + o_blk);

@@ -390,30 +390,6 @@ float logit_pre_gate(float conf) {
     return (float)(lg - 1e-3 - 1e-5 * fabs(lg));
 }
 
-// Global work area of the split scan: [images][2] int32 counters (zero between launches: zeroed when the
-// buffer is (re)allocated, reset by the finalising CTA after use) followed by [images][cap] 64-bit keys.
-int k2_work(hvb_ctx* ctx, int images, int cap, unsigned long long** keys, int32_t** ctr) {
-    const size_t ctr_bytes = (((size_t)images * 2 * sizeof(int32_t)) + 255) & ~(size_t)255;
-    const size_t key_bytes = (size_t)images * cap * sizeof(unsigned long long);
-    if (ctr_bytes > ctx->k2_ctr_bytes || key_bytes > ctx->k2_work_bytes - ctx->k2_ctr_bytes) {
-        // the stream may still be using the old buffer: drain it before replacing (rare: only on growth)
-        HVB_TRY(hvb_capturing(ctx, "hvb_decode_nms"));
-        HVB_CUDA(cudaStreamSynchronize(ctx->stream));
-        if (ctx->k2_work_dev) {
-            if (ctx->retain_buffers) ctx->retired.push_back(ctx->k2_work_dev);
-            else HVB_CUDA(cudaFree(ctx->k2_work_dev));
-        }
-        ctx->k2_work_dev = nullptr; ctx->k2_work_bytes = 0; ctx->k2_ctr_bytes = 0;
-        const size_t ctr_cap = ctr_bytes * 2, total = ctr_cap + key_bytes * 2;
-        HVB_CUDA(cudaMalloc(&ctx->k2_work_dev, total));
-        HVB_CUDA(cudaMemset(ctx->k2_work_dev, 0, ctr_cap));
-        ctx->k2_work_bytes = total; ctx->k2_ctr_bytes = ctr_cap;
-    }
-    *ctr = reinterpret_cast<int32_t*>(ctx->k2_work_dev);
-    *keys = reinterpret_cast<unsigned long long*>(reinterpret_cast<uint8_t*>(ctx->k2_work_dev) + ctx->k2_ctr_bytes);
-    return HVB_OK;
-}
-
 template <typename K>
 int set_smem(K kernel, size_t bytes) {
     if (bytes > 227 * 1024) {
@@ -455,7 +431,7 @@ static int decode_nms_impl(hvb_ctx* ctx, const float* const level_dev[3], const 
     HVB_TRY(set_smem(decode_nms_kernel, sm));
     unsigned long long* keys = nullptr;
     int32_t* ctr = nullptr;
-    HVB_TRY(k2_work(ctx, batch, cap, &keys, &ctr));
+    HVB_TRY(hvb_k2_work(ctx, batch, cap, &keys, &ctr));
     dim3 grid(hvb_div_up(L.base[3], kChunk), batch);
     decode_nms_kernel<<<grid, kThreads, sm, ctx->stream>>>(L, nc, conf_thres, logit_pre_gate(conf_thres), iou_thres, max_det,
                                                            agnostic, cap, meta_dev, out_xyxy_dev, out_conf_dev, out_cls_dev,
@@ -496,7 +472,7 @@ int hvb_decode_nms(hvb_ctx* ctx, const float* const level_dev[3], const int32_t 
     HVB_TRY(set_smem(decode_nms_kernel, sm1));
     unsigned long long* keys = nullptr;
     int32_t* ctr = nullptr;
-    HVB_TRY(k2_work(ctx, batch, kCapSmall, &keys, &ctr));
+    HVB_TRY(hvb_k2_work(ctx, batch, kCapSmall, &keys, &ctr));
     dim3 grid(hvb_div_up(L.base[3], kChunk), batch);
     decode_nms_kernel<<<grid, kThreads, sm1, ctx->stream>>>(L, nc, conf_thres, logit_pre_gate(conf_thres), iou_thres, max_det,
                                                             agnostic, kCapSmall, meta_dev, out_xyxy_dev, out_conf_dev,
@@ -523,7 +499,7 @@ int hvb_decode_nms_large(hvb_ctx* ctx, const float* const level_dev[3], const in
     HVB_TRY(set_smem(decode_nms_kernel, sm));
     unsigned long long* keys = nullptr;
     int32_t* ctr = nullptr;
-    HVB_TRY(k2_work(ctx, n_images, kCapLarge, &keys, &ctr));
+    HVB_TRY(hvb_k2_work(ctx, n_images, kCapLarge, &keys, &ctr));
     dim3 grid(hvb_div_up(L.base[3], kChunk), n_images);
     decode_nms_kernel<<<grid, kThreads, sm, ctx->stream>>>(L, nc, conf_thres, logit_pre_gate(conf_thres), iou_thres, max_det,
                                                            agnostic, kCapLarge, meta_dev, out_xyxy_dev, out_conf_dev,

@@ -36,7 +36,8 @@ __device__ __forceinline__ bool iou_gt_f64(const DBox& a, const DBox& b, double 
 
 __global__ void __launch_bounds__(kThreads)
 merge_nms_kernel(const double* __restrict__ xyxy, const float* __restrict__ conf, const int32_t* __restrict__ cls,
-                 const int32_t* __restrict__ seg_offsets, double thr, int agnostic, int cap, uint8_t* __restrict__ keep) {
+                 const int32_t* __restrict__ seg_offsets, double thr, int agnostic, int cap, int min_n,
+                 uint8_t* __restrict__ keep) {
     extern __shared__ __align__(16) uint8_t smem[];
     __shared__ int s_nkept;
     __shared__ unsigned s_sup[kWarps];
@@ -46,9 +47,11 @@ merge_nms_kernel(const double* __restrict__ xyxy, const float* __restrict__ conf
     int* kidx = reinterpret_cast<int*>(smem + (size_t)cap * 44);                           // [cap] kept -> sorted index
 
     const int lo = seg_offsets[blockIdx.x], n = seg_offsets[blockIdx.x + 1] - lo;
-    if (n <= 0) return;
-    if (n > cap) {      // capacity exceeded: mark the whole segment 0xFF, the host layer raises
-        for (int i = threadIdx.x; i < n; i += kThreads) keep[lo + i] = 0xFF;
+    if (n <= min_n) return;          // tiered launches: this launch handles segments with min_n < n <= cap
+    if (n > cap) {
+        // left to the next tier; beyond the last tier the whole segment is marked 0xFF and the host layer raises
+        if (cap == kCapLarge)
+            for (int i = threadIdx.x; i < n; i += kThreads) keep[lo + i] = 0xFF;
         return;
     }
     int n_pow2 = 1;
@@ -184,13 +187,20 @@ int hvb_merge_nms(hvb_ctx* ctx, const double* xyxy_dev, const float* conf_dev, c
     HVB_ARG(n_segments >= 0 && n_total >= 0, "negative sizes");
     if (n_segments == 0 || n_total == 0) return HVB_OK;
     HVB_ARG(xyxy_dev && conf_dev && seg_offsets_dev && out_keep_dev, "null pointer");
-    const int cap = n_total <= kCapSmall ? kCapSmall : kCapLarge;
-    const size_t sm = merge_smem(cap);
-    if (sm > 48 * 1024)
-        HVB_CUDA(cudaFuncSetAttribute(merge_nms_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));
-    merge_nms_kernel<<<n_segments, kThreads, sm, ctx->stream>>>(xyxy_dev, conf_dev, cls_dev, seg_offsets_dev, iou_thres,
-                                                                class_agnostic, cap, out_keep_dev);
+    // The tier (shared memory per CTA, bitonic pad) follows the SEGMENT length, which only the device knows when the
+    // caller passes capacities (n_total = slots * max_det on the no-sync path): every segment first meets the 512-row
+    // tier (24 KB, several CTAs per SM); only if n_total allows longer segments a second launch with the 4096-row tier
+    // (192 KB) picks up the ones the first skipped, and its other CTAs exit at once.
+    merge_nms_kernel<<<n_segments, kThreads, merge_smem(kCapSmall), ctx->stream>>>(
+        xyxy_dev, conf_dev, cls_dev, seg_offsets_dev, iou_thres, class_agnostic, kCapSmall, 0, out_keep_dev);
     HVB_LAUNCHED(ctx);
+    if (n_total > kCapSmall) {
+        const size_t sm = merge_smem(kCapLarge);
+        HVB_CUDA(cudaFuncSetAttribute(merge_nms_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));
+        merge_nms_kernel<<<n_segments, kThreads, sm, ctx->stream>>>(
+            xyxy_dev, conf_dev, cls_dev, seg_offsets_dev, iou_thres, class_agnostic, kCapLarge, kCapSmall, out_keep_dev);
+        HVB_LAUNCHED(ctx);
+    }
     return HVB_OK;
 }
 

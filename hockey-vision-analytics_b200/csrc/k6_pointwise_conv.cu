@@ -322,11 +322,9 @@ int hvb_pointwise_conv(hvb_ctx* ctx, const float* x_dev, int x_ld, const float* 
         HVB_ARG(out2_ld >= out2_off + c2_count && (out2_ld & 3) == 0 && (out2_off & 3) == 0 && ((uintptr_t)out2_dev & 15) == 0, "out2 pitch / offset / alignment");
     }
     HVB_ARG(npix < ((int64_t)1 << 31), "npix too large for one tensor map");
-    // HVB_PW_TILE=192 (experimental, not validated on hardware in round 1): one 128 x 192 tile per CTA for c_out % 192 == 0,
-    // i.e. 29 % less L2 -> SM traffic per output than two 128 x 96 tiles; TMEM 256 columns, two CTAs per SM
-    static int wide_tile = -1;
-    if (wide_tile < 0) { const char* e = getenv("HVB_PW_TILE"); wide_tile = (e && atoi(e) == 192) ? 1 : 0; }
-    const int bn = (wide_tile && c_out % 192 == 0) ? 192 : (c_out % 96 == 0) ? 96 : 64;
+    // (a 128 x 192 tile per CTA was measured in round 2 and removed: correct, but slower for 192 -> 192 (208 vs 187 us)
+    // and only ahead for 1152 -> 384, a layer that stays on cuDNN — profiles/r02a_k6_decision.md)
+    const int bn = (c_out % 96 == 0) ? 96 : 64;
     EncodeTiledFn encode = nullptr;
     HVB_TRY(pw_encode_fn(&encode));
     CUtensorMap mx, mw;
@@ -342,7 +340,6 @@ int hvb_pointwise_conv(hvb_ctx* ctx, const float* x_dev, int x_ld, const float* 
                                    ((uintptr_t)out2_dev & 31) == 0));
     const int64_t tiles = ((npix + kBM - 1) / kBM) * a.n_tiles_n;
     HVB_ARG(tiles < ((int64_t)1 << 31), "too many tiles");
-    if (bn == 192) return pw_dispatch<192>(ctx, act, mx, mw, a, tiles);
     return bn == 96 ? pw_dispatch<96>(ctx, act, mx, mw, a, tiles) : pw_dispatch<64>(ctx, act, mx, mw, a, tiles);
 }
 

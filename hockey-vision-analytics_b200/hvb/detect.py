@@ -72,6 +72,10 @@ class Detector:
         self._staging: Dict[Tuple, dict] = {}
         self._plans: Dict[Tuple, LetterboxPlan] = {}
         self._meta: Dict[Tuple, torch.Tensor] = {}
+        # Synthetic-input hook (hvb.synth.DeviceOverlay): an object with begin_chunk(n_frames) — called once per detect
+        # call, outside any CUDA graph — and __call__(heads, cls_index) -> heads, applied to the raw head tensors between
+        # the forward and K2a.  None in production.
+        self.head_hook = None
 
     # -------------------------------------------------------------- plumbing
     def plan(self, n: int, h: int, w: int, mode: int = _ffi.LB_WHOLE, imgsz: Optional[int] = None,
@@ -119,8 +123,15 @@ class Detector:
         slot["events"][i] = ev
         return dev
 
-    def forward_heads(self, x: torch.Tensor) -> List[torch.Tensor]:
-        """Backbone forward (PyTorch).  Returns the 3 raw head tensors as contiguous float32 NCHW."""
+    def forward_heads(self, x: torch.Tensor, cls_index: int = 0) -> List[torch.Tensor]:
+        """Backbone forward (PyTorch).  Returns the 3 raw head tensors (SplitHeads from the K5 runner, else float32
+        tensors with jointly contiguous spatial dims).  `cls_index`: shape class of the batch (slicer), for head_hook."""
+        heads = self._forward_heads(x)
+        if self.head_hook is not None:
+            heads = self.head_hook(heads, cls_index)
+        return heads
+
+    def _forward_heads(self, x: torch.Tensor):
         if self.runner is not None:
             return self.runner(x)
         with torch.no_grad():
@@ -148,17 +159,22 @@ class Detector:
         return self._meta[key]
 
     # -------------------------------------------------------------- whole-frame path
-    def detect_device(self, frames_dev: torch.Tensor, graph: Optional[bool] = None):
+    def detect_device(self, frames_dev: torch.Tensor, graph: Optional[bool] = None, imgsz: Optional[int] = None,
+                      hook_repeat: bool = False):
         """frames_dev uint8[n,H,W,3] on the GPU -> device tensors (xyxy[n,max_det,4], conf, cls, count)."""
         n, h, w, _ = frames_dev.shape
-        plan = self.plan(n, h, w, _ffi.LB_WHOLE)
+        if self.head_hook is not None:
+            self.head_hook.begin_chunk(n, repeat=hook_repeat)
+        imgsz = imgsz or self.imgsz
+        plan = self.plan(n, h, w, _ffi.LB_WHOLE, imgsz)
         if self.cuda_graph if graph is None else graph:
-            key = (n, h, w)
+            # everything the captured K1 plan / K2a launch bakes in is part of the key
+            key = (n, h, w, imgsz, self.conf, self.iou, self.max_det, self.agnostic, id(self.head_hook))
             if key not in self._graphs:
                 from .runtime import GraphedStep
 
                 def step(f):
-                    xyxy, cf, cl, cnt, (heads, _, _) = self.detect_device(f, graph=False)
+                    xyxy, cf, cl, cnt, (heads, _, _) = self._detect_eager(f, plan)
                     flat = tuple(heads.box) + tuple(heads.cls) if isinstance(heads, SplitHeads) else tuple(heads)
                     return (xyxy, cf, cl, cnt) + flat
                 self._graphs[key] = GraphedStep(self.ctx, step, [frames_dev])
@@ -166,6 +182,10 @@ class Detector:
             meta_h, meta_d = self._meta_dev(plan, 0)
             heads = SplitHeads(out[4:7], out[7:10]) if len(out) == 10 else list(out[4:])
             return out[0], out[1], out[2], out[3], (heads, meta_h, meta_d)
+        return self._detect_eager(frames_dev, plan)
+
+    def _detect_eager(self, frames_dev: torch.Tensor, plan: LetterboxPlan):
+        n = frames_dev.shape[0]
         with nvtx("hvb:K1a letterbox"):
             x = plan.class_views(plan.run(frames_dev))[0]
         with nvtx("hvb:yolo forward (cuDNN convs + K5)"):
@@ -203,10 +223,10 @@ class Detector:
             raise _ffi.HvbError(_ffi.HVB_ERR_CAPACITY, "more than 8192 candidates above conf=%g in one image" % self.conf)
         return cnt_host
 
-    def detect_batch(self, frames) -> List[Detections]:
-        """List of Detections (one per frame), equal to from_ultralytics(model(frame)[0]) per frame."""
+    def detect_batch(self, frames, imgsz: Optional[int] = None) -> List[Detections]:
+        """List of Detections (one per frame), equal to from_ultralytics(model(frame, imgsz=imgsz)[0]) per frame."""
         frames_dev = self.upload(frames)
-        xyxy, cf, cl, cnt, state = self.detect_device(frames_dev)
+        xyxy, cf, cl, cnt, state = self.detect_device(frames_dev, imgsz=imgsz)
         cnt_h = cnt.cpu().numpy()
         if (cnt_h < 0).any():
             cnt_h = self._retry_overflow(xyxy, cf, cl, cnt, state, cnt_h)
@@ -234,10 +254,5 @@ class Detector:
         det = self
 
         def callback(tile: np.ndarray) -> Detections:
-            old = det.imgsz
-            det.imgsz = imgsz
-            try:
-                return det(np.ascontiguousarray(tile))
-            finally:
-                det.imgsz = old
+            return det.detect_batch(np.ascontiguousarray(tile), imgsz=imgsz)[0]
         return callback

@@ -81,6 +81,9 @@ class FusedYOLOv8:
         # K6 computes in TF32 like cuDNN's default convolutions; when the caller has turned TF32 off (fp32 convolutions
         # requested) the pointwise layers stay on cuDNN + K5.  None = follow torch.backends.cudnn.allow_tf32 as of now.
         self.use_pointwise = bool(torch.backends.cudnn.allow_tf32) if pointwise_kernel is None else bool(pointwise_kernel)
+        import os
+        if pointwise_kernel is None and os.environ.get("HVB_K6") is not None:       # A/B switch for bench.py runs
+            self.use_pointwise = self.use_pointwise and os.environ["HVB_K6"] not in ("0", "off", "false")
         self.pw_launches = 0
         # SiLU flavour of the epilogue: the approximate-unit version (<= 1e-6 relative error) keeps the pass HBM-bound
         self._silu = _SILU_EXACT if exact_silu else _SILU_FAST

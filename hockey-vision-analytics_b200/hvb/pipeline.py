@@ -74,7 +74,8 @@ class HotPath:
 
     def process_chunk_device(self, frames_dev: torch.Tensor, team_boxes: Optional[torch.Tensor] = None,
                              team_frame_idx: Optional[torch.Tensor] = None):
-        """Everything on the device; returns the tensors a caller would copy back."""
+        """Everything on the device; returns the tensors a caller would copy back (+ `state`, what an overflow retry
+        of K2a needs: the head tensors and the per-image meta)."""
         if team_boxes is not None and self.overlap_team and team_boxes.shape[0]:
             dev = frames_dev.device
             main = torch.cuda.current_stream(dev)
@@ -87,21 +88,37 @@ class HotPath:
             for t in (frames_dev, team_boxes, team_frame_idx):
                 if t is not None:
                     t.record_stream(side)
-            xyxy, conf, cls, cnt, _ = self.detect_device(frames_dev)
+            xyxy, conf, cls, cnt, state = self.detect_device(frames_dev)
             main.wait_stream(side)                                    # team stage finished long before detection does
             tail.record_stream(main)
-            return dict(xyxy=xyxy, conf=conf, cls=cls, count=cnt, team_tail=tail, team_frame_idx=team_frame_idx)
-        xyxy, conf, cls, cnt, _ = self.detect_device(frames_dev)
+            return dict(xyxy=xyxy, conf=conf, cls=cls, count=cnt, team_tail=tail, team_frame_idx=team_frame_idx, state=state,
+                        team_from_detections=False)
+        xyxy, conf, cls, cnt, state = self.detect_device(frames_dev)
+        out = dict(xyxy=xyxy, conf=conf, cls=cls, count=cnt, state=state, team_from_detections=team_boxes is None)
+        self._team_of(out, frames_dev, team_boxes, team_frame_idx)
+        return out
+
+    def _team_of(self, out, frames_dev, team_boxes, team_frame_idx):
         if team_boxes is None:
             # boxes of detected players (class 0), compacted with torch indexing (tiny)
+            conf, cls, cnt, xyxy = out["conf"], out["cls"], out["count"], out["xyxy"]
             n, md = conf.shape
             valid = (torch.arange(md, device=conf.device)[None, :] < cnt[:, None]) & (cls == PLAYER_CLASS_ID)
             fi, ki = torch.nonzero(valid, as_tuple=True)
             team_boxes = xyxy[fi, ki].contiguous()
             team_frame_idx = fi.to(torch.int32)
-        tail = self.team_device(frames_dev, team_boxes, team_frame_idx) if team_boxes.shape[0] else \
+        out["team_tail"] = self.team_device(frames_dev, team_boxes, team_frame_idx) if team_boxes.shape[0] else \
             torch.zeros((0, 10), dtype=torch.float64, device=frames_dev.device)
-        return dict(xyxy=xyxy, conf=conf, cls=cls, count=cnt, team_tail=tail, team_frame_idx=team_frame_idx)
+        out["team_frame_idx"] = team_frame_idx
+
+    def _resolve_overflow(self, out, frames_dev, cnt_host: np.ndarray) -> np.ndarray:
+        """Frames that reported -1 (> 1024 candidates above conf) are re-run with K2a's 8192-candidate tier, like
+        Detector.detect_batch does (ultralytics' NMS, max_nms = 30000, never fails here); raises only if that tier
+        overflows too.  The team stage is redone when its boxes came from the detections."""
+        cnt_host = self.detector._retry_overflow(out["xyxy"], out["conf"], out["cls"], out["count"], out["state"], cnt_host)
+        if out["team_from_detections"]:
+            self._team_of(out, frames_dev, None, None)
+        return cnt_host
 
     @staticmethod
     def rule(tail: np.ndarray) -> np.ndarray:
@@ -122,7 +139,7 @@ class HotPath:
         out = self.process_chunk_device(frames_dev, tb, ti)
         cnt = out["count"].cpu().numpy()
         if (cnt < 0).any():
-            raise _ffi.HvbError(_ffi.HVB_ERR_CAPACITY, "candidate overflow in the chunked path; lower the chunk's conf pressure")
+            cnt = self._resolve_overflow(out, frames_dev, cnt)
         res = dict(count=cnt, xyxy=out["xyxy"].cpu().numpy(), conf=out["conf"].cpu().numpy(), cls=out["cls"].cpu().numpy())
         res["team"] = self.rule(out["team_tail"].cpu().numpy())
         return res
@@ -146,9 +163,12 @@ class HotPath:
             frames, tb, ti = item
             src = frames if isinstance(frames, torch.Tensor) else torch.from_numpy(np.ascontiguousarray(frames)).pin_memory()
             slot = i & 1
-            if bufs[slot] is None or bufs[slot].shape != src.shape:
-                bufs[slot] = torch.empty(src.shape, dtype=torch.uint8, device=dev)
             with torch.cuda.stream(copy_stream):
+                if bufs[slot] is None or bufs[slot].shape != src.shape:
+                    # allocated UNDER the copy stream: a block handed out under the main stream may be one that main-stream
+                    # kernels still in flight are using (the caching allocator reuses host-freed blocks stream-ordered),
+                    # and the copy below would overwrite it concurrently
+                    bufs[slot] = torch.empty(src.shape, dtype=torch.uint8, device=dev)
                 if free_ev[slot] is not None:
                     copy_stream.wait_event(free_ev[slot])            # previous user of this buffer is done
                 bufs[slot].copy_(src, non_blocking=True)
@@ -161,7 +181,7 @@ class HotPath:
         def launch(i, staged):
             slot, tbd, tid, ready, _keep = staged
             main.wait_event(ready)
-            tbd.record_stream(main); tid.record_stream(main)
+            tbd.record_stream(main); tid.record_stream(main); bufs[slot].record_stream(main)
             out = self.process_chunk_device(bufs[slot], tbd, tid)
             ev = torch.cuda.Event()
             ev.record(main)
@@ -174,14 +194,20 @@ class HotPath:
                 host[k].copy_(t, non_blocking=True)
             done = torch.cuda.Event()
             done.record(main)
-            return host, done, _keep
+            return host, done, _keep, out, bufs[slot]
 
         def collect(item):
-            host, done, _keep = item
+            host, done, _keep, out, frames_dev = item
             done.synchronize()
             cnt = host["count"].numpy().copy()
             if (cnt < 0).any():
-                raise _ffi.HvbError(_ffi.HVB_ERR_CAPACITY, "candidate overflow in the chunked path; lower the chunk's conf pressure")
+                # rare: redo K2a for the overflowing frames with the large tier (the chunk's heads and frame buffer are
+                # still alive: the buffer is only recycled two chunks later) and read this chunk's results again
+                cnt = self._resolve_overflow(out, frames_dev, cnt)
+                for k in ("xyxy", "conf", "cls", "team_tail"):
+                    if host[k].shape != out[k].shape:
+                        host[k] = torch.empty(out[k].shape, dtype=out[k].dtype).pin_memory()
+                    host[k].copy_(out[k])
             res = dict(count=cnt, xyxy=host["xyxy"].numpy().copy(), conf=host["conf"].numpy().copy(), cls=host["cls"].numpy().copy())
             res["team"] = self.rule(host["team_tail"].numpy())
             return res
@@ -215,10 +241,12 @@ class SlicedPuckPath:
         CUDA graph captured on first use for this chunk shape — the sliced path is launch-bound otherwise."""
         if not graph or sync:
             return self.slicer.run_device(frames_dev, sync=sync)
-        key = tuple(frames_dev.shape)
+        key = tuple(frames_dev.shape) + (id(self.detector.head_hook),)
+        if self.detector.head_hook is not None:                # outside the graph: stage this chunk's planted tables
+            self.detector.head_hook.begin_chunk(frames_dev.shape[0])
         if key not in self._graphs:
             from .runtime import GraphedStep
-            self._graphs[key] = GraphedStep(self.detector.ctx, lambda f: self.slicer.run_device(f, sync=False), [frames_dev])
+            self._graphs[key] = GraphedStep(self.detector.ctx, lambda f: self.slicer.run_device(f, sync=False, hook=None), [frames_dev])
         return self._graphs[key](frames_dev)
 
     def process_chunk(self, frames: np.ndarray):
@@ -240,9 +268,9 @@ class SlicedPuckPath:
         def stage(i, frames):
             src = frames if isinstance(frames, torch.Tensor) else torch.from_numpy(np.ascontiguousarray(frames)).pin_memory()
             slot = i & 1
-            if bufs[slot] is None or bufs[slot].shape != src.shape:
-                bufs[slot] = torch.empty(src.shape, dtype=torch.uint8, device=dev)
             with torch.cuda.stream(copy_stream):
+                if bufs[slot] is None or bufs[slot].shape != src.shape:
+                    bufs[slot] = torch.empty(src.shape, dtype=torch.uint8, device=dev)     # under the copy stream (see HotPath.process_stream)
                 if free_ev[slot] is not None:
                     copy_stream.wait_event(free_ev[slot])
                 bufs[slot].copy_(src, non_blocking=True)
@@ -253,6 +281,7 @@ class SlicedPuckPath:
         def launch(i, staged):
             slot, ready, keep_alive = staged
             main.wait_event(ready)
+            bufs[slot].record_stream(main)
             out = self.process_chunk_device(bufs[slot], graph=graph)
             ev = torch.cuda.Event()
             ev.record(main)
@@ -271,7 +300,7 @@ class SlicedPuckPath:
             done.synchronize()
             seg, cnt = host["seg"].numpy(), host["count"].numpy()
             if (cnt < 0).any():                                # > 1024 candidates in a tile: redo this chunk with the retry tier
-                return self.slicer.run_batch(frames_dev)
+                return self.slicer.run_batch(frames_dev)          # (planted benchmarks never overflow: the hook is not re-armed here)
             total = int(seg[-1])
             xyxy, conf, cls, keep = (host[k].numpy()[:total] for k in ("xyxy", "conf", "cls", "keep"))
             if (keep == 0xFF).any():

@@ -96,7 +96,7 @@ class B200InferenceSlicer:
         return merged[keep]
 
     # ------------------------------------------------------------------ device path
-    def run_device(self, frames_dev: torch.Tensor, sync: bool = True):
+    def run_device(self, frames_dev: torch.Tensor, sync: bool = True, hook: Optional[str] = "begin"):
         """frames_dev uint8[n,H,W,3] -> (xyxy f64[total,4], conf f32, cls i32, keep u8, seg i32[n+1]) on device.
 
         sync=True: one small D2H of the per-tile counts sizes the outputs exactly and triggers the large-capacity
@@ -106,6 +106,8 @@ class B200InferenceSlicer:
         det = self.detector
         ctx = det.ctx
         n, h, w, _ = frames_dev.shape
+        if det.head_hook is not None and hook is not None:      # hook: "begin" next chunk | "repeat" same chunk | None: caller did it
+            det.head_hook.begin_chunk(n, repeat=hook == "repeat")
         mode = _ffi.LB_SLICE_UNIFORM if self.uniform_tiles else _ffi.LB_SLICE_EXACT
         plan = det.plan(n, h, w, mode, self.tile_imgsz, self.slice_wh, self._overlap())
         views = plan.class_views(plan.run(frames_dev))
@@ -126,12 +128,12 @@ class B200InferenceSlicer:
             fork.record(main)
             for rank, c in enumerate(order):
                 if rank == 0:
-                    heads_of[c] = det.forward_heads(views[c])                 # biggest class on the main stream
+                    heads_of[c] = det.forward_heads(views[c], c)              # biggest class on the main stream
                     continue
                 side = self._side_streams[(rank - 1) % len(self._side_streams)]
                 side.wait_event(fork)
                 with torch.cuda.stream(side):
-                    heads_of[c] = det.forward_heads(views[c])
+                    heads_of[c] = det.forward_heads(views[c], c)
                 for hd in (heads_of[c].tensors() if hasattr(heads_of[c], "tensors") else heads_of[c]):
                     hd.record_stream(main)
             for side in self._side_streams:
@@ -142,7 +144,7 @@ class B200InferenceSlicer:
                 states.append(state)
         else:
             for c, x in enumerate(views):
-                heads = det.forward_heads(x)
+                heads = det.forward_heads(x, c)
                 meta_h, meta_d = det._meta_dev(plan, c)
                 *_, state = det._decode(heads, meta_h, meta_d, n_slots, out=out)
                 states.append(state)
@@ -175,7 +177,7 @@ class B200InferenceSlicer:
         xyxy, conf, cls, keep, seg, cnt = self.run_device(frames_dev, sync=False)      # no host round trip mid-pipeline
         seg_h, cnt_h = seg.cpu().numpy(), cnt.cpu().numpy()
         if (cnt_h < 0).any():                       # a tile overflowed the 1024-candidate tier: redo with the retry path
-            xyxy, conf, cls, keep, seg = self.run_device(frames_dev, sync=True)
+            xyxy, conf, cls, keep, seg = self.run_device(frames_dev, sync=True, hook="repeat")
             seg_h = seg.cpu().numpy()
         total = int(seg_h[-1])
         xyxy_h, conf_h, cls_h, keep_h = (t[:total].cpu().numpy() for t in (xyxy, conf, cls, keep))

@@ -9,7 +9,8 @@ import csv
 
 HVB = ("letterbox_kernel", "decode_nms_kernel", "crops_from_boxes_kernel", "color_features_kernel", "mnv3_prep",
        "scale_transform_kernel", "standardize", "gram_tcgen05", "affinity_from_gram", "d2_f64", "iou_cost_kernel",
-       "merge_nms_kernel", "gather_tiles_kernel", "bias_act_kernel", "concat_nhwc_kernel", "stem_conv_kernel", "sppf_pool_concat_kernel", "cvt_hsv_lab")
+       "merge_nms_kernel", "gather_tiles_kernel", "bias_act_kernel", "concat_nhwc_kernel", "stem_conv_kernel", "sppf_pool_concat_kernel", "cvt_hsv_lab",
+       "pointwise_conv_kernel", "jersey_color_stats_kernel", "bytetrack_kernel", "select_crops_kernel")
 
 
 def short(name):
