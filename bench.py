@@ -1,19 +1,22 @@
 #!/usr/bin/env python
-"""bench.py — hot-path frames/s on synthetic 1080p frames (+ the 4K sliced puck path), with the
+"""bench.py — hot-path frames/s on a synthetic 1080p clip (+ the 4K sliced puck path and the 720p config), with the
 roofline of the dominant libhvb kernel and the CPU reference path timed beside it.
 
     python bench.py [--gpus N] [--steps K] [--warmup W] [--impl hvb|reference] [--chunk F]
     torchrun --nnodes=1 --nproc-per-node N ... bench.py --gpus N ...
 
-A "step" is one pass of the hot path over one chunk of F (default 64) synthetic 1080p frames per GPU
-(BASELINE.json configs[1] + configs[2]):
-    K1a letterbox -> YOLOv8m forward (torch fp32, random init) -> K2a decode+NMS ->
-    K3a colour features + K3b crop preprocessing on 12 player boxes / frame -> MobileNetV3 (torch fp32) ->
-    K4a scale_transform -> similarity rule.
-Random-init YOLO emits no detection above conf=0.4, so the team stage runs on the
-12 planted player boxes of each synthetic frame ("team_boxes": "planted"); the detection stage
-still does all of its work.  `value` has the frames resident in HBM; `e2e` goes through the public
-host API (pinned host frames in, H2D + D2H inside the timed region).
+A "step" is one pass of the reference's per-frame loop (hockey/main.py:259-281) over one chunk of F (default 64)
+consecutive frames of a synthetic 1080p clip per GPU (BASELINE.json configs[1] + configs[2]):
+    K1a letterbox -> YOLOv8m forward (random init) -> planted candidates scattered into the raw head tensors ->
+    K2a decode + NMS + scale_boxes -> K7 ByteTrack (every frame of the chunk, in order) -> crops of the tracked players ->
+    K3a colour features + K3b crop preprocessing -> MobileNetV3 -> K4a scale_transform -> similarity rule + temporal vote
+    -> per-frame results (detections, tracker ids, team ids, labels).
+Random-init YOLO emits no detection above conf 0.4, so AFTER the real forward both arms overwrite the head
+tensors at 36 anchors per frame with the same planted values (hvb.synth.PlantedOverlay: the 12 players of the synthetic
+frame, 3 jittered candidates each, distinct confidences in (0.45, 0.97); 11 skaters + 1 goalie): NMS suppresses 24 of
+36 candidates per frame, ByteTrack tracks 12 objects, and the team stage runs on the 11 tracked skaters the detector
+found ("team_boxes": "detected").  `value` has the clip resident in HBM; `e2e` is the drop-in's public call
+(hvb.VideoProcessor.process_video_chunked: host frames in, H2D inside, per-frame results out).
 """
 from __future__ import annotations
 
@@ -33,34 +36,33 @@ for p in (ROOT, PKG):
     if p not in sys.path:
         sys.path.insert(0, p)
 
-H, W, PLAYERS = 1080, 1920, 12
+H, W, PLAYERS, DUP, IMGSZ = 1080, 1920, 12, 3, 1280
 METRIC = "hot_path_frames_per_sec_1080p"
 UNIT = "frames/s"
+WORKLOAD = ("C2+C3: 1080p player detection (letterbox, YOLOv8m fp32 random-init, %d planted candidates per frame scattered "
+            "into the head tensors, decode + NMS) + ByteTrack + team classification of the tracked players (colour + "
+            "MobileNetV3-small features, scale_transform, rule + temporal vote)" % (PLAYERS * DUP))
 
 
 def ncu_traffic(kernel_key: str, launches=None):
-    """DRAM bytes per launch (dram__bytes_read.sum + dram__bytes_write.sum) of the roofline kernel from the
-    committed `ncu --set full` capture (profiles/ncu_traffic.json, written from tools/ncu_summary.py output).
-    `launches`: only use a per-step capture if it was taken with the same number of launches per step as now."""
+    """DRAM bytes (dram__bytes_read.sum + dram__bytes_write.sum) of the roofline kernel from the committed ncu capture
+    (profiles/ncu_traffic.json).  `launches`: only use a per-step capture taken with the same number of launches per step."""
     p = os.path.join(ROOT, "profiles", "ncu_traffic.json")
     if not os.path.exists(p):
         return None
     try:
-        d = json.load(open(p))
-        for key in (kernel_key, kernel_key + "_k6"):      # "_k6": the capture minus the launches K6 now replaces
-            e = d.get(key, {})
-            if e and (launches is None or e.get("launches") == launches):
-                return e.get("traffic_bytes")
-        return None
+        e = json.load(open(p)).get(kernel_key, {})
+        if e and (launches is None or e.get("launches") == launches):
+            return e.get("traffic_bytes")
     except Exception:
-        return None
+        pass
+    return None
 
 
 def measured_peaks():
     p = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(p):
-        d = json.load(open(p))
-        return float(d["hbm_gbs"]), "measured"
+        return float(json.load(open(p))["hbm_gbs"]), "measured"
     return 6650.0, "fallback"
 
 
@@ -112,62 +114,79 @@ class ClockSampler:
                 "reasons": sorted(reasons), "samples": len(sm)}
 
 
-def synth_chunk(seed: int, n: int):
-    from hvb.synth import rink_frame
-    rng = np.random.default_rng(seed)
-    frames, boxes, fidx = [], [], []
-    for i in range(n):
-        f, b, _, _ = rink_frame(rng, H, W, PLAYERS)
-        frames.append(f); boxes.append(b); fidx.append(np.full(len(b), i, np.int32))
-    return np.stack(frames), np.concatenate(boxes).astype(np.float32), np.concatenate(fidx)
+def synth_clip(seed: int, n: int, h: int = H, w: int = W, scale: float = 1.0):
+    """n consecutive frames of a synthetic clip (players drift <= 8 px / frame), their boxes and classes."""
+    from hvb.synth import rink_clip
+    frames, boxes, _, pucks = rink_clip(seed, n, h, w, PLAYERS, scale)
+    cls = [np.array([0] * (PLAYERS - 1) + [1])] * n                   # 11 skaters + 1 goalie
+    return frames, boxes, cls, pucks
+
+
+def make_overlay(seed: int, boxes, cls):
+    from hvb.synth import PlantedOverlay
+    return PlantedOverlay.whole_frame(seed, (H, W), IMGSZ, boxes, cls, nc=2, dup=DUP)
+
+
+def pingpong(n_frames: int, n_chunks: int, start: int = 0):
+    """Frame ids of chunk start, start+1, ...: the clip forwards, then backwards, ... (continuous motion for the tracker)."""
+    fwd = list(range(n_frames))
+    return [fwd if (start + k) % 2 == 0 else fwd[::-1] for k in range(n_chunks)]
 
 
 # ------------------------------------------------------------------------------------------ reference arm
 class CpuReferencePath:
-    """The reference's own CPU implementation of the path, restated in oracle/ against the same real
-    libraries (cv2, Pillow/torchvision, sklearn, torchvision.ops.nms): kind = "port"."""
+    """The reference's own CPU implementation of the path, restated in oracle/ against the same real libraries (cv2,
+    Pillow/torchvision, sklearn, torchvision.ops.nms, scipy): kind = "port".  One frame at a time, like main.py:321."""
+    STAGES = ("letterbox+preprocess", "yolo_forward", "decode+nms+scale", "bytetrack", "crops+team_predict")
 
-    def __init__(self):
+    def __init__(self, overlay):
         import torch
         from hvb.models import build_trunk, build_yolov8
-        from oracle import team_reference as tr
-        self.torch = torch
         from hvb.models.yolov8 import fuse_conv_bn
+        from oracle import team_reference as tr
+        from oracle.bytetrack_restated import ByteTrack
+        self.torch = torch
         self.yolo = fuse_conv_bn(build_yolov8("m", 2, 0))        # ultralytics fuses conv+bn before inference
         self.trunk = build_trunk(0, calibrate=True)
         self.ref = tr.HybridReference(self.trunk)
-        self.fitted = False
-        self.stage_s = {"letterbox+preprocess": 0.0, "yolo_forward": 0.0, "decode+nms+scale": 0.0, "crops+team_predict": 0.0}
+        self.tracker = ByteTrack(0.25, 30, 0.8, 30, 2)            # main.py:162-168
+        self.overlay = overlay
+        self.stage_s = {k: 0.0 for k in self.STAGES}
         self.stage_frames = 0
+        self.n_tracked = 0
 
-    def fit(self, frames, boxes, fidx):
+    def fit(self, frames, boxes):
         from oracle.supervision_restated import crop_image
-        crops = [crop_image(frames[f], b) for f, b in zip(fidx, boxes)]
+        crops = [crop_image(f, b) for f, bb in zip(frames, boxes) for b in bb[:PLAYERS - 1]]
         self.ref.fit(crops, run_clustering=False)
-        self.fitted = True
 
-    def step(self, frames, boxes, fidx):
+    def step(self, frames, frame_ids):
         from oracle import ultralytics_restated as ur
         from oracle.supervision_restated import crop_image
-        torch = self.torch
-        out = []
-        st = self.stage_s
-        for i, frame in enumerate(frames):
+        torch, st, out = self.torch, self.stage_s, []
+        for frame, fid in zip(frames, frame_ids):
             t0 = time.perf_counter()
-            lb = ur.letterbox(frame, 1280, auto=True)
-            x = torch.from_numpy(ur.preprocess([lb]))
+            x = torch.from_numpy(ur.preprocess([ur.letterbox(frame, IMGSZ, auto=True)]))
             t1 = time.perf_counter()
             with torch.no_grad():
-                heads = self.yolo(x)
+                heads = [t.clone() for t in self.yolo(x)]
+            self.overlay.apply_host(heads, fid)                   # the same planted candidates the GPU arm scatters in
             t2 = time.perf_counter()
-            det = ur.predict_from_head(heads, 2, tuple(x.shape[2:]), [frame.shape[:2]], 0.4)[0]
+            xyxy, conf, cls = ur.predict_from_head(heads, 2, tuple(x.shape[2:]), [frame.shape[:2]], 0.4)[0]
+            m = ((cls == 0) | (cls == 1)) & (conf > 0.4)          # main.py:189-193
+            xyxy, conf, cls = xyxy[m], conf[m], cls[m]
             t3 = time.perf_counter()
-            crops = [crop_image(frame, b) for b in boxes[fidx == i]]
-            out.append((det, self.ref.predict(crops)))
+            keep, ids = self.tracker.update_with_detections(xyxy, conf)
             t4 = time.perf_counter()
-            st["letterbox+preprocess"] += t1 - t0; st["yolo_forward"] += t2 - t1
-            st["decode+nms+scale"] += t3 - t2; st["crops+team_predict"] += t4 - t3
+            pl = cls[keep] == 0
+            crops = [crop_image(frame, b) for b in xyxy[keep][pl]]
+            team = self.ref.predict(crops, tracker_ids=ids[pl])
+            t5 = time.perf_counter()
+            out.append((xyxy[keep], ids, team))
+            for k, dt in zip(self.STAGES, (t1 - t0, t2 - t1, t3 - t2, t4 - t3, t5 - t4)):
+                st[k] += dt
             self.stage_frames += 1
+            self.n_tracked += len(keep)
         return out
 
     def stage_ms_per_frame(self):
@@ -181,25 +200,33 @@ def run_reference(args, rank, world):
         return
     cores = os.cpu_count() or 1
     torch.set_num_threads(cores)
-    path = CpuReferencePath()
-    frames, boxes, fidx = synth_chunk(0, args.ref_frames)
-    path.fit(frames, boxes, fidx)
+    nf = args.ref_frames
+    frames, boxes, cls, _ = synth_clip(1000, nf + 2)
+    path = CpuReferencePath(make_overlay(77, boxes, cls))
+    path.fit(frames, boxes)
+    # untimed: the first two frames of the clip confirm the tracks (minimum_consecutive_frames = 2), so that every
+    # timed frame has tracked players to classify; further warm-up steps repeat frame 1
+    path.step(frames[:2], [0, 1])
     for _ in range(args.warmup):
-        path.step(frames[:1], boxes[fidx == 0], fidx[fidx == 0])
+        path.step(frames[1:2], [1])
+    path.stage_s = {k: 0.0 for k in path.STAGES}; path.stage_frames = 0; path.n_tracked = 0
     t0 = time.perf_counter()
-    for _ in range(args.steps):
-        path.step(frames, boxes, fidx)
+    for k in range(args.steps):
+        ids = list(range(2, nf + 2)) if k % 2 == 0 else list(range(2, nf + 2))[::-1]
+        path.step([frames[i] for i in ids], ids)
     dt = time.perf_counter() - t0
-    fps = args.steps * len(frames) / dt
+    fps = args.steps * nf / dt
     line = {
         "impl": "reference", "metric": METRIC, "value": fps, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "u8/f32", "data": "synthetic",
-        "config": {"workload": "C2+C3 1080p player detection + team classification, CPU reference path",
-                   "frames_per_step": int(len(frames)), "players_per_frame": PLAYERS, "team_boxes": "planted"},
+        "config": {"workload": WORKLOAD + " — CPU reference path, one frame at a time", "frames_per_step": nf,
+                   "players_per_frame": PLAYERS, "planted_candidates_per_frame": PLAYERS * DUP, "team_boxes": "detected"},
         "cpu_baseline": {"value": fps, "unit": UNIT, "cores": cores, "kind": "port", "stage_ms_per_frame": path.stage_ms_per_frame(),
-                         "sample": "%d synthetic 1080p frames per step: cv2 letterbox + YOLOv8m CPU forward + restated "
-                                   "decode/torchvision NMS + reference colour/MobileNetV3 features + predict" % len(frames)},
+                         "tracked_per_frame": path.n_tracked / max(path.stage_frames, 1),
+                         "sample": "%d consecutive synthetic 1080p frames per step: cv2 letterbox + YOLOv8m CPU forward (torch, %d threads) + "
+                                   "planted candidates + restated decode / torchvision NMS + restated ByteTrack (scipy) + reference "
+                                   "colour / MobileNetV3 features + predict" % (nf, cores)},
         "e2e": {"value": fps, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
@@ -213,266 +240,283 @@ def run_hvb(args, rank, world):
     local = int(os.environ.get("LOCAL_RANK", 0))
     torch.cuda.set_device(local)
     dev = "cuda:%d" % local
+    # every rank gets its share of the host cores (all ranks claiming all cores made the host-side API
+    # slower at N > 1); pin the process to a contiguous block when the affinity mask allows it
+    cores = os.cpu_count() or 1
+    per_rank = max(1, cores // max(world, 1))
+    torch.set_num_threads(per_rank)
+    if world > 1 and hasattr(os, "sched_setaffinity"):
+        try:
+            avail = sorted(os.sched_getaffinity(0))
+            if len(avail) >= world:
+                k = len(avail) // world
+                os.sched_setaffinity(0, set(avail[local * k:(local + 1) * k]))
+        except OSError:
+            pass
+    try:
+        import cv2
+        cv2.setNumThreads(per_rank)
+    except Exception:
+        pass
     from hvb import _ffi
     from hvb.pipeline import HotPath, SlicedPuckPath
     from hvb.runtime import get_context
+    from hvb.video import Config, VideoProcessor
 
     ctx = get_context(local)
     F = args.chunk
-    path = HotPath(dev, "m", 2, 1280, 0.4, seed=0)
-    frames, boxes, fidx = synth_chunk(1000 + rank, F)             # each rank owns its own clip chunk (weak scaling)
-    pinned = torch.from_numpy(frames).pin_memory()
-    frames_dev = pinned.to(dev)
-    boxes_dev = torch.from_numpy(boxes).to(dev)
-    fidx_dev = torch.from_numpy(fidx).to(dev)
-
-    # ---- one-off team fit (per job): local crop features -> all-gather (NCCL) -> global standardise + affinity
-    t_fit0 = time.perf_counter()
-    feats, raw, _ = path.classifier.features_from_frame(frames_dev, boxes_dev, fidx_dev)
-    if world > 1:
-        from hvb.dist import all_gather_features
-        feats = all_gather_features(feats)
-    # scaler + RBF affinity on the device on every rank; the spectral embedding / k-means that follow in the
-    # reference's fit run in scikit-learn on the host, are not on the per-frame path and are skipped here
-    path.classifier.fit_features(feats, None, None, cluster=False)
-    torch.cuda.synchronize()
-    fit_ms = 1e3 * (time.perf_counter() - t_fit0)
+    path = HotPath(dev, "m", 2, IMGSZ, 0.4, seed=0)
+    det = path.detector
+    frames, boxes, cls, _ = synth_clip(1000 + rank, F)                 # each rank owns its own clip (weak scaling)
+    overlay = make_overlay(77 + rank, boxes, cls)
+    fwd_dev = torch.from_numpy(frames).to(dev)
+    rev_dev = fwd_dev.flip(0).contiguous()
+    hook_chunks = overlay.to_device(dev, pingpong(F, 2))               # cyclic: forwards, backwards
+    hook_frames = overlay.to_device(dev, [[0]])
 
     def barrier():
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize()
 
-    def timed(fn, steps, warmup, sampler=None, profile=False):
-        for _ in range(warmup):
-            fn()
-        barrier()
-        if sampler:
-            sampler.start()
-        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        if profile:
-            torch.cuda.profiler.start()          # ncu --profile-from-start off: only the timed steps are captured
-        e0.record()
-        for _ in range(steps):
-            fn()
-        e1.record()
-        barrier()
-        if profile:
-            torch.cuda.profiler.stop()
-        ms = e0.elapsed_time(e1)
-        clocks = sampler.stop() if sampler else None
+    def max_over_ranks(ms):
         if world > 1:
             t = torch.tensor([ms], device=dev)
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
-            ms = float(t.item())
-        return ms, clocks
+            return float(t.item())
+        return ms
 
-    # ---- (i) device-resident hot path
-    k1_events = []
+    # ---- one-off team fit (per job): local crop features -> all-gather (NCCL) -> global standardise + affinity.
+    # The spectral embedding / k-means that follow in the reference's fit run in scikit-learn on the host, are not on
+    # the per-frame path and are skipped here.  Run twice: the first pass carries cuDNN autotuning / allocations.
+    skaters = np.concatenate([b[:PLAYERS - 1] for b in boxes]).astype(np.float32)
+    sk_fidx = np.repeat(np.arange(F, dtype=np.int32), PLAYERS - 1)
+    sk_dev, skf_dev = torch.from_numpy(skaters).to(dev), torch.from_numpy(sk_fidx).to(dev)
+    fit = {}
+    for tag in ("cold", "warm"):
+        barrier()
+        t0 = time.perf_counter()
+        feats, _, _ = path.classifier.features_from_frame(fwd_dev, sk_dev, skf_dev)
+        torch.cuda.synchronize()
+        t1 = time.perf_counter()
+        if world > 1:
+            from hvb.dist import all_gather_features
+            feats = all_gather_features(feats)
+            torch.cuda.synchronize()
+        t2 = time.perf_counter()
+        path.classifier.fit_features(feats, None, None, cluster=False)
+        torch.cuda.synchronize()
+        t3 = time.perf_counter()
+        fit[tag] = {"features_ms": 1e3 * (t1 - t0), "all_gather_ms": 1e3 * (t2 - t1), "standardise+affinity_ms": 1e3 * (t3 - t2),
+                    "total_ms": 1e3 * (t3 - t0), "rows": int(feats.shape[0])}
 
-    def step_device():
-        path.process_chunk_device(frames_dev, boxes_dev, fidx_dev)
+    vp = VideoProcessor(device=dev, config=Config(), detector=det, team_classifier=path.classifier_router(), tracker=args.tracker)
+    det.head_hook = hook_chunks
+    state = {"g": 0, "tracked": 0, "players": 0, "frames": 0}
 
+    def run_chunks(n):
+        """n more chunks of the ping-pong clip through the device-resident chunk pipeline."""
+        g0 = state["g"]
+        state["g"] += n
+        for r in vp.process_chunks((fwd_dev if (g0 + k) % 2 == 0 else rev_dev) for k in range(n)):
+            state["tracked"] += len(r.detections); state["players"] += len(r.player_team_ids); state["frames"] += 1
+
+    # ---- (i) device-resident hot path: W warm-up steps, then exactly K timed steps
+    run_chunks(max(args.warmup, 2) + (max(args.warmup, 2) % 2))        # even: the overlay's fwd/rev cycle stays aligned
+    barrier()
+    state.update(tracked=0, players=0, frames=0)
     ctx.launch_count(reset=True)
     sampler = ClockSampler(local) if rank == 0 else None
-    ms_dev, clocks = timed(step_device, args.steps, args.warmup, sampler, profile=args.profile_region and not args.profile_4k)
-    launches = ctx.launch_count() // (args.steps + args.warmup) * args.steps
+    if sampler:
+        sampler.start()
+    if args.profile_region and not args.profile_4k:
+        torch.cuda.profiler.start()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    run_chunks(args.steps)
+    e1.record()
+    barrier()
+    if args.profile_region and not args.profile_4k:
+        torch.cuda.profiler.stop()
+    clocks = sampler.stop() if sampler else None
+    launches = ctx.launch_count()
+    ms_dev = max_over_ranks(e0.elapsed_time(e1))
     fps_dev = world * F * args.steps / (ms_dev / 1e3)
+    per_frame = {"tracked_per_frame": state["tracked"] / max(state["frames"], 1),
+                 "team_classified_per_frame": state["players"] / max(state["frames"], 1),
+                 "candidates_per_frame": overlay.count(0)}
+    if state["g"] % 2:
+        run_chunks(1)
 
-    # ---- (ii) end to end through the public host API (pinned frames, H2D + D2H inside)
-    # Every step copies its own chunk from pinned host memory and reads its results back; the pipelined
-    # API (HotPath.process_stream) overlaps the copy of step i+1 with the kernels of step i.
-    def run_e2e(k):
-        n = 0
-        for res in path.process_stream((pinned, boxes, fidx) for _ in range(k)):
-            n += len(res["team"])
-        return n
+    # ---- (ii) end to end through the drop-in's public call: a clip of host frames in (pinned staging + H2D inside),
+    # per-frame results out
+    def run_e2e(n):
+        g0 = state["g"]
+        state["g"] += n
+        clip = [frames[i] for ids in pingpong(F, n, g0) for i in ids]
+        return sum(1 for _ in vp.process_video_chunked(clip, chunk=F, initialize=False))
 
-    run_e2e(max(2, args.warmup // 2))
+    run_e2e(2)
     barrier()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
-    run_e2e(args.steps)
+    n_out = run_e2e(args.steps)
     e1.record()
     barrier()
-    ms_e2e = e0.elapsed_time(e1)
-    if world > 1:
-        t = torch.tensor([ms_e2e], device=dev)
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        ms_e2e = float(t.item())
+    assert n_out == F * args.steps
+    ms_e2e = max_over_ranks(e0.elapsed_time(e1))
     fps_e2e = world * F * args.steps / (ms_e2e / 1e3)
-    h2d = frames.nbytes + boxes.nbytes + fidx.nbytes
-    md = path.detector.max_det
-    d2h = F * md * (16 + 4 + 4) + F * 4 + len(boxes) * 80
+    if state["g"] % 2:
+        run_e2e(1)
+    md = det.max_det
+    n_team = int(round(per_frame["team_classified_per_frame"] * F))
+    h2d = frames.nbytes + n_team * (16 + 4)
+    d2h = F * md * (16 + 4 + 4) + F * 4 + F * md * 8 + F * 4 + n_team * 80
 
-    # ---- roofline of the dominant libhvb kernel (K1 letterbox), timed live with CUDA events on its stream
-    plan = path.detector.plan(F, H, W, _ffi.LB_WHOLE)
-    out = plan.run(frames_dev)
-    torch.cuda.synchronize()
-    # `reps` back-to-back launches between one pair of CUDA events on the launching stream: the GPU
-    # stays busy, so host launch gaps are not billed to the kernel; inputs+outputs exceed L2.
-    reps = max(args.steps, 20)
-    ea, eb = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    ea.record()
-    for _ in range(reps):
-        plan.run(frames_dev, out)
-    eb.record()
-    torch.cuda.synchronize()
-    k1_ms = ea.elapsed_time(eb) / reps
-    k1_bytes = plan.read_bytes + plan.write_bytes
+    # ---- roofline of the DOMINANT libhvb kernel of the step: the K5 conv epilogue (bias_act_kernel).  Every launch of
+    # three more forwards is bracketed by CUDA events on its launching stream.
     peak, peak_src = measured_peaks()
-    achieved = k1_bytes / (k1_ms / 1e3) / 1e9
-
-    # ---- roofline of the DOMINANT libhvb kernel of the step: the K5 conv epilogue (bias_act_kernel, ~28 % of the step,
-    # 82 launches, 76 since K6 took six of them together with their convolutions).  Every launch of three more steps is bracketed by CUDA events on its launching stream.
-    runner = path.detector.runner
+    det.head_hook = None
+    runner = det.runner
     k5 = None
     if runner is not None:
         runner.epi_log = []
         for _ in range(3):
-            path.detect_device(frames_dev)
+            path.detect_device(fwd_dev)
         torch.cuda.synchronize()
         log, runner.epi_log = runner.epi_log, None
         k5_bytes = sum(b for b, _, _ in log)
         k5_ms = sum(a.elapsed_time(b) for _, a, b in log)
         k5 = {"launches_per_step": len(log) // 3, "bytes_per_step": k5_bytes // 3, "ms_per_step": k5_ms / 3,
               "achieved": k5_bytes / (k5_ms / 1e3) / 1e9}
+    # K1a at the launch size of the step: back-to-back launches between one pair of events (inputs + outputs > L2)
+    plan = det.plan(F, H, W, _ffi.LB_WHOLE)
+    out = plan.run(fwd_dev)
+    torch.cuda.synchronize()
+    reps = max(args.steps, 20)
+    ea, eb = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    ea.record()
+    for _ in range(reps):
+        plan.run(fwd_dev, out)
+    eb.record()
+    torch.cuda.synchronize()
+    k1_ms = ea.elapsed_time(eb) / reps
+    k1_bytes = plan.read_bytes + plan.write_bytes
+    del out
 
-    # ---- per-stage device times of one chunk (CUDA events on the main stream, stages run back to back without the
-    # side-stream overlap) — the GPU column next to cpu_baseline.stage_ms_per_frame
-    det = path.detector
-    ev = [torch.cuda.Event(enable_timing=True) for _ in range(5)]
-    acc = [0.0, 0.0, 0.0, 0.0]
+    # ---- per-stage device times of one chunk (CUDA events on the main stream, stages back to back, no overlap) — the GPU
+    # column next to cpu_baseline.stage_ms_per_frame
+    from hvb.tracker import DeviceByteTrack
+    det.head_hook = overlay.to_device(dev, [list(range(F))])
+    trk = DeviceByteTrack(0.25, 30, 0.8, 30, 2, device=dev)
+    ev = [torch.cuda.Event(enable_timing=True) for _ in range(6)]
+    acc = [0.0] * 5
     for it in range(4):
-        plan = det.plan(F, H, W, _ffi.LB_WHOLE)
+        det.head_hook.begin_chunk(F)
         ev[0].record()
-        x = plan.class_views(plan.run(frames_dev))[0]
+        x = plan.class_views(plan.run(fwd_dev))[0]
         ev[1].record()
         heads = det.forward_heads(x)
         ev[2].record()
         meta_h, meta_d = det._meta_dev(plan, 0)
-        det._decode(heads, meta_h, meta_d, F)
+        xyxy, cf, cl, cnt, _ = det._decode(heads, meta_h, meta_d, F)
         ev[3].record()
-        path.team_device(frames_dev, boxes_dev, fidx_dev)
+        row, tid, tc = trk.update_chunk_device(xyxy, cf, cl, cnt, min_conf=0.4, class_mask=0b11)
         ev[4].record()
+        path.team_device(fwd_dev, sk_dev, skf_dev)
+        ev[5].record()
         torch.cuda.synchronize()
         if it:                                     # first pass is a warm-up
-            for k in range(4):
+            for k in range(5):
                 acc[k] += ev[k].elapsed_time(ev[k + 1]) / 3 / F
-    gpu_stage_ms = {"letterbox+preprocess (K1a)": round(acc[0], 5), "yolo_forward (cuDNN convs + K5)": round(acc[1], 5),
-                    "decode+nms+scale (K2a)": round(acc[2], 5), "crops+team_predict (K3a/K3b, MobileNetV3, K4a)": round(acc[3], 5)}
+    gpu_stage_ms = dict(zip(("letterbox+preprocess (K1a)", "yolo_forward (cuDNN convs + K5/K6, + planted scatter)",
+                             "decode+nms+scale (K2a, %d candidates per frame)" % (PLAYERS * DUP),
+                             "bytetrack (K7, %d frames in order)" % F,
+                             "crops+team_predict (K3a/K3b, MobileNetV3, K4a; %d crops per frame)" % (PLAYERS - 1)),
+                            (round(a, 5) for a in acc)))
+    k7_us_per_frame = 1e3 * acc[3]
+    del trk
 
-    # ---- secondary workload: 4K sliced puck path (C4), reported in `extra`
-    extra = {"fit_ms": fit_ms, "gpu_stage_ms_per_frame": gpu_stage_ms}
-    # frame-at-a-time use of the drop-in (what process_frame does per frame: host frame in, Detections out)
-    if rank == 0:
-        one = frames[0]
-        for tag, flag in (("eager", False), ("cuda_graph", True)):
-            path.detector.cuda_graph = flag
-            for _ in range(3):
-                path.detector.detect_players(one)
-            torch.cuda.synchronize()
-            t0 = time.perf_counter()
-            for _ in range(20):
-                path.detector.detect_players(one)
-            extra["frame_at_a_time_detect_fps_" + tag] = 20 / (time.perf_counter() - t0)
-        path.detector.cuda_graph = False
-        # the whole-loop drop-in on a clip (hvb.VideoProcessor.process_video_chunked: detection per chunk, ByteTrack per
-        # frame on the host, team features per chunk).  Random-init YOLO detects nothing above conf 0.4, so this times the
-        # driver + detection path; the tracker / team stages see empty inputs.
-        from hvb.video import Config, VideoProcessor
-        from hvb.models import build_yolov8
-        vp = VideoProcessor(build_yolov8("m", 2, 0), dev, Config(), team_classifier=path.classifier_router())
-        CH = 32                                                       # process_video_chunked's default chunk
-        clip = [frames[i % F] for i in range(6 * CH)]
-        list(vp.process_video_chunked(clip[:CH], chunk=CH, initialize=False))
+    extra = {"fit": fit, "gpu_stage_ms_per_frame": gpu_stage_ms, "per_frame": per_frame, "tracker": args.tracker,
+             "k7_bytetrack_us_per_frame_step": round(k7_us_per_frame, 2), "host_threads_per_rank": per_rank}
+
+    # ---- the reference's actual loop shape: one frame at a time through process_frame (detect -> track -> crops -> predict)
+    det.head_hook = hook_frames
+    for tag, flag in (("eager", False), ("cuda_graph", True)):
+        det.cuda_graph = flag
+        vpf = VideoProcessor(device=dev, config=Config(), detector=det, team_classifier=path.classifier_router(), tracker=args.tracker)
+        for _ in range(3):
+            vpf.process_frame(frames[0])
+        torch.cuda.synchronize()
         t0 = time.perf_counter()
-        n_out = len(list(vp.process_video_chunked(clip, chunk=CH, initialize=False)))
-        extra["clip_chunked_drop_in_fps"] = n_out / (time.perf_counter() - t0)
-        del vp
-    if args.with_4k:
-        from hvb.synth import rink_frame
-        rng = np.random.default_rng(7 + rank)
-        F4 = args.chunk_4k
-        f4 = np.stack([rink_frame(rng, 2160, 3840, PLAYERS, 2.0)[0] for _ in range(F4)])
-        f4_dev = torch.from_numpy(f4).to(dev)
-        puck = SlicedPuckPath(dev, "n", 1, 0.4)
-        ms4_eager, _ = timed(lambda: puck.process_chunk_device(f4_dev), max(2, args.steps // 2), 2,
-                             profile=args.profile_region and args.profile_4k)
-        # the sliced path is launch-bound (≈900 launches per chunk over 5 tile shape classes): replay it as one CUDA graph
-        ms4, _ = timed(lambda: puck.process_chunk_device(f4_dev, graph=True), max(2, args.steps // 2), 2)
-        # end to end through the public sliced API: pinned 4K frames in, per-frame Detections out
-        pinned4 = torch.from_numpy(f4).pin_memory()
-        k4 = max(2, args.steps // 2)
-
-        def run_e2e4(k):
-            return sum(len(r) for r in puck.process_stream(pinned4 for _ in range(k)))
-
-        run_e2e4(2)
-        barrier()
-        ea, eb = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        ea.record()
-        run_e2e4(k4)
-        eb.record()
-        barrier()
-        ms4_e2e = ea.elapsed_time(eb)
-        if world > 1:
-            t = torch.tensor([ms4_e2e], device=dev)
-            dist.all_reduce(t, op=dist.ReduceOp.MAX)
-            ms4_e2e = float(t.item())
-        extra["c4_4k_sliced_e2e_frames_per_sec"] = world * F4 * k4 / (ms4_e2e / 1e3)
-        extra["c4_e2e_h2d_bytes_per_step"] = int(f4.nbytes)
-        plan4 = puck.detector.plan(F4, 2160, 3840, _ffi.LB_SLICE_EXACT, 640, (640, 640), (128, 128))
-        o4 = plan4.run(f4_dev)
-        torch.cuda.synchronize()
-        ea, eb = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        ea.record()
         for _ in range(20):
-            plan4.run(f4_dev, o4)
-        eb.record()
-        torch.cuda.synchronize()
-        k1b_ms = ea.elapsed_time(eb) / 20
-        extra.update({"c4_4k_sliced_frames_per_sec": world * F4 * max(2, args.steps // 2) / (ms4 / 1e3),
-                      "c4_4k_sliced_frames_per_sec_eager_launches": world * F4 * max(2, args.steps // 2) / (ms4_eager / 1e3),
-                      "c4_mode": "whole chunk replayed as one CUDA graph",
-                      "c4_frames_per_step": F4, "c4_tiles_per_frame": int(plan4.tiles_per_frame),
-                      "k1b_slice_letterbox_gbs": (plan4.read_bytes + plan4.write_bytes) / (k1b_ms / 1e3) / 1e9,
-                      "k1b_frac_of_hbm_peak": (plan4.read_bytes + plan4.write_bytes) / (k1b_ms / 1e3) / 1e9 / peak})
+            vpf.process_frame(frames[0])
+        extra["frame_at_a_time_process_frame_fps_" + tag] = 20 / (time.perf_counter() - t0)
+        del vpf
+    det.cuda_graph = False
+    # the drop-in at its default chunk of 32 frames
+    det.head_hook = overlay.to_device(dev, [list(range(32)), list(range(32, 64))] if F >= 64 else [list(range(F))])
+    ch = 32 if F >= 64 else F
+    clip = [frames[i] for k in range(6) for i in (range(32) if k % 2 == 0 else range(32, 64))] if F >= 64 else [frames[i] for k in range(6) for i in range(F)]
+    vpc = VideoProcessor(device=dev, config=Config(), detector=det, team_classifier=path.classifier_router(), tracker=args.tracker)
+    list(vpc.process_video_chunked(clip[:2 * ch], chunk=ch, initialize=False))
+    barrier()
+    t0 = time.perf_counter()
+    n_out = sum(1 for _ in vpc.process_video_chunked(clip, chunk=ch, initialize=False))
+    extra["clip_chunked_drop_in_fps_chunk32"] = n_out / (time.perf_counter() - t0)
+    del vpc
+    det.head_hook = None
+    if world > 1:                                   # the host-side figures of every rank (VERDICT r1 #7)
+        for k in ("frame_at_a_time_process_frame_fps_cuda_graph", "clip_chunked_drop_in_fps_chunk32"):
+            t = torch.tensor([extra[k]], device=dev)
+            lo, hi = t.clone(), t.clone()
+            dist.all_reduce(lo, op=dist.ReduceOp.MIN); dist.all_reduce(hi, op=dist.ReduceOp.MAX); dist.all_reduce(t, op=dist.ReduceOp.SUM)
+            extra[k + "_ranks"] = {"min": float(lo.item()), "mean": float(t.item()) / world, "max": float(hi.item())}
+
+    # ---- secondary workload: 4K sliced puck path (C4): planted pucks, cross-slice duplicates in the tile overlaps
+    roofline_4k = None
+    if args.with_4k:
+        roofline_4k = bench_4k(args, rank, world, dev, barrier, max_over_ranks, peak, extra)
+    # ---- BASELINE config 1: 1280x720, 60 frames, YOLOv8n (nc=1), sliced puck detection; CPU arm beside it at N=1
+    if args.with_c1 and rank == 0:
+        bench_c1(args, world, dev, extra)
 
     # ---- CPU baseline beside it (rank 0, N=1 only), bounded sample
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
-        cores = os.cpu_count() or 1
-        torch.set_num_threads(cores)
-        ref = CpuReferencePath()
+        cores_all = os.cpu_count() or 1
+        torch.set_num_threads(cores_all)
         nf = args.ref_frames
-        ref.fit(frames[:nf], boxes[fidx < nf], fidx[fidx < nf])
-        ref.step(frames[:1], boxes[fidx == 0], fidx[fidx == 0])
-        ref.stage_s = {k: 0.0 for k in ref.stage_s}; ref.stage_frames = 0
+        ref = CpuReferencePath(overlay)
+        ref.fit(frames[:nf + 2], boxes[:nf + 2])
+        ref.step(frames[:2], [0, 1])                              # untimed: confirms the tracks (minimum_consecutive_frames = 2)
+        ref.stage_s = {k: 0.0 for k in ref.STAGES}; ref.stage_frames = 0; ref.n_tracked = 0
         t0 = time.perf_counter()
-        ref.step(frames[:nf], boxes[fidx < nf], fidx[fidx < nf])
+        ref.step(frames[2:nf + 2], list(range(2, nf + 2)))
         dt = time.perf_counter() - t0
         stage_ms = ref.stage_ms_per_frame()
-        # per-core normalisation: the same path on ONE host thread, one frame
+        tracked_cpu = ref.n_tracked / max(ref.stage_frames, 1)
         import cv2
         cv_threads = cv2.getNumThreads()
-        torch.set_num_threads(1); cv2.setNumThreads(1)
+        torch.set_num_threads(1); cv2.setNumThreads(1)           # per-core normalisation (SURVEY.md §8d)
         t0 = time.perf_counter()
-        ref.step(frames[:1], boxes[fidx == 0], fidx[fidx == 0])
+        ref.step(frames[nf + 2:nf + 3], [nf + 2])
         dt1 = time.perf_counter() - t0
-        torch.set_num_threads(cores); cv2.setNumThreads(cv_threads)
-        cpu = {"value": nf / dt, "unit": UNIT, "cores": cores, "kind": "port", "torch_threads": cores, "cv2_threads": cv_threads,
-               "value_1_thread": 1.0 / dt1, "stage_ms_per_frame": stage_ms,
-               "sample": "%d of the %d synthetic 1080p frames of one step, same stages on the host: cv2 letterbox, YOLOv8m "
-                         "CPU forward (torch, %d threads), restated decode + real torchvision NMS, reference colour + "
-                         "MobileNetV3 features, predict" % (nf, F, cores)}
+        torch.set_num_threads(cores_all); cv2.setNumThreads(cv_threads)
+        cpu = {"value": nf / dt, "unit": UNIT, "cores": cores_all, "kind": "port", "torch_threads": cores_all, "cv2_threads": cv_threads,
+               "value_1_thread": 1.0 / dt1, "stage_ms_per_frame": stage_ms, "tracked_per_frame": tracked_cpu,
+               "sample": "%d consecutive frames of the %d-frame clip, one frame at a time, same stages on the host: cv2 letterbox, "
+                         "YOLOv8m CPU forward (torch, %d threads), the same planted candidates, restated decode + real torchvision "
+                         "NMS, restated ByteTrack (scipy assignment), reference colour + MobileNetV3 features, predict + vote"
+                         % (nf, F, cores_all)}
 
     k1_roof = {"kernel": "letterbox_kernel<false> (K1a, 1080p->736x1280, %d frames/launch)" % F, "bound": "hbm",
-               "achieved": achieved, "peak": peak, "peak_source": peak_src, "unit": "GB/s", "frac": achieved / peak,
-               "traffic": ncu_traffic("K1a_1080p_x%d" % F), "algorithmic_bytes_per_launch": int(k1_bytes), "avg_launch_ms": k1_ms}
+               "achieved": k1_bytes / (k1_ms / 1e3) / 1e9, "peak": peak, "peak_source": peak_src, "unit": "GB/s",
+               "frac": k1_bytes / (k1_ms / 1e3) / 1e9 / peak, "traffic": ncu_traffic("K1a_1080p_x%d_r02a" % F),
+               "algorithmic_bytes_per_launch": int(k1_bytes), "avg_launch_ms": k1_ms}
     if k5 is not None:
         n5 = k5["launches_per_step"]
-        t5 = ncu_traffic("K5_bias_act_step_x%d" % F, launches=n5)   # summed over the launches of one step
+        t5 = ncu_traffic("K5_bias_act_step_x%d_r02a" % F, launches=n5)   # summed over the launches of one step
         roofline = {"kernel": "bias_act_kernel (K5 conv epilogue: bias + SiLU + residual -> dense / concat-slice destinations), "
                               "%d launches per step of %d frames" % (n5, F),
                     "bound": "hbm", "achieved": k5["achieved"], "peak": peak, "peak_source": peak_src, "unit": "GB/s",
@@ -487,23 +531,164 @@ def run_hvb(args, rank, world):
             "metric": METRIC, "value": fps_dev, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": ms_dev / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "u8/f32", "data": "synthetic",
-            "config": {"workload": "C2+C3: 1080p player detection (K1a letterbox, YOLOv8m fp32 random-init, K2a decode+NMS) + "
-                                   "team classification (K3a/K3b on 12 planted player boxes per frame, MobileNetV3-small fp32, "
-                                   "K4a scale_transform, rule)",
-                       "frames_per_step_per_gpu": F, "players_per_frame": PLAYERS, "team_boxes": "planted",
+            "config": {"workload": WORKLOAD, "frames_per_step_per_gpu": F, "players_per_frame": PLAYERS,
+                       "planted_candidates_per_frame": PLAYERS * DUP, "team_boxes": "detected",
                        "backbones": "convolutions in torch/cuDNN (fp32 storage, conv+bn folded, channels_last, cudnn.benchmark, TF32 for YOLO / "
                                     "TF32 off for MobileNetV3); everything between the YOLO convolutions (bias, SiLU, residual, concat, "
-                                    "upsample, layer 0) in libhvb K5 kernels; the pointwise convolutions with few channels as single K6 launches (tcgen05 TF32 GEMM + epilogue)",
+                                    "upsample, layer 0) in libhvb K5 kernels; six pointwise convolutions as single K6 launches (tcgen05 TF32 GEMM + epilogue)",
                        "l2": "inputs larger than L2 (%.0f MB frames + %.0f MB letterboxed per step)" % (frames.nbytes / 1e6, k1_bytes / 1e6),
-                       "parallelism": "frame chunks sharded per GPU, no data-path collective; one NCCL feature all-gather at fit"},
+                       "parallelism": "one clip per GPU, frame chunks in order, no data-path collective; one NCCL feature all-gather at fit"},
             "e2e": {"value": fps_e2e, "unit": UNIT, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h)},
             "gpu_launches": int(launches),
             "clocks": clocks,
             "roofline": roofline,
+            "roofline_4k": roofline_4k,
             "cpu_baseline": cpu,
             "extra": extra,
         }
         print(json.dumps(line))
+
+
+def bench_4k(args, rank, world, dev, barrier, max_over_ranks, peak, extra):
+    """C4: 4K frames -> K1b slice letterbox (40 tiles, 5 shape classes) -> YOLOv8n per class -> planted pucks -> K2a ->
+    gather -> K2b cross-slice merge.  Returns the top-level roofline block of the 4K path (K1b + K2a at 640 tiles)."""
+    import torch
+    from hvb import _ffi
+    from hvb.pipeline import SlicedPuckPath
+    from hvb.synth import PlantedOverlay
+    F4 = args.chunk_4k
+    f4, boxes4, _, pucks = synth_clip(7 + rank, F4, 2160, 3840, 2.0)
+    # per frame: the puck + two more small objects near tile seams, so that overlapping tiles see the same object
+    rng = np.random.default_rng(5 + rank)
+    objs = []
+    for p in pucks:
+        extra_xy = np.stack([rng.choice([512, 1024, 1536, 2048, 2560, 3072], 2) + rng.uniform(20, 100, 2),
+                             rng.choice([512, 1024, 1536], 2) + rng.uniform(20, 100, 2)], 1)
+        eb = np.hstack([extra_xy, extra_xy + rng.uniform(14, 24, (2, 2))])
+        objs.append(np.vstack([p[None], eb]))
+    ov4 = PlantedOverlay.sliced(9 + rank, (2160, 3840), 640, objs, [np.zeros(3, int)] * F4, nc=1, dup=2)
+    f4_dev = torch.from_numpy(f4).to(dev)
+    puck = SlicedPuckPath(dev, "n", 1, 0.4)
+    plan4 = puck.detector.plan(F4, 2160, 3840, _ffi.LB_SLICE_EXACT, 640, (640, 640), (128, 128))
+    puck.detector.head_hook = ov4.to_device(dev, [list(range(F4))], plan=plan4)
+    k4 = max(2, args.steps // 2)
+
+    def timed(fn, steps, warmup, profile=False):
+        for _ in range(warmup):
+            fn()
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        if profile:
+            torch.cuda.profiler.start()
+        e0.record()
+        for _ in range(steps):
+            fn()
+        e1.record()
+        barrier()
+        if profile:
+            torch.cuda.profiler.stop()
+        return max_over_ranks(e0.elapsed_time(e1))
+
+    ms4_eager = timed(lambda: puck.process_chunk_device(f4_dev), k4, 2, profile=args.profile_region and args.profile_4k)
+    # the sliced path is launch-bound (~900 launches per chunk over 5 tile shape classes): replay it as one CUDA graph
+    ms4 = timed(lambda: puck.process_chunk_device(f4_dev, graph=True), k4, 2)
+    res = puck.process_chunk_device(f4_dev, sync=True)
+    keep, seg = res[3].cpu().numpy(), res[4].cpu().numpy()
+    merged_per_frame = float(seg[-1]) / F4
+    kept_per_frame = float((keep == 1).sum()) / F4
+    # end to end through the public sliced API: pinned 4K frames in, per-frame Detections out
+    pinned4 = torch.from_numpy(f4).pin_memory()
+
+    def run_e2e4(k):
+        return sum(len(r) for r in puck.process_stream(pinned4 for _ in range(k)))
+
+    run_e2e4(2)
+    barrier()
+    ea, eb = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    ea.record()
+    run_e2e4(k4)
+    eb.record()
+    barrier()
+    ms4_e2e = max_over_ranks(ea.elapsed_time(eb))
+    # K1b and K2a at the 4K launch sizes, back to back between one pair of events
+    o4 = plan4.run(f4_dev)
+    torch.cuda.synchronize()
+    ea, eb = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    ea.record()
+    for _ in range(20):
+        plan4.run(f4_dev, o4)
+    eb.record()
+    torch.cuda.synchronize()
+    k1b_ms = ea.elapsed_time(eb) / 20
+    k1b_bytes = plan4.read_bytes + plan4.write_bytes
+    extra.update({"c4_4k_sliced_frames_per_sec": world * F4 * k4 / (ms4 / 1e3),
+                  "c4_4k_sliced_e2e_frames_per_sec": world * F4 * k4 / (ms4_e2e / 1e3),
+                  "c4_4k_sliced_frames_per_sec_eager_launches": world * F4 * k4 / (ms4_eager / 1e3),
+                  "c4_e2e_h2d_bytes_per_step": int(f4.nbytes), "c4_mode": "whole chunk replayed as one CUDA graph",
+                  "c4_frames_per_step": F4, "c4_tiles_per_frame": int(plan4.tiles_per_frame),
+                  "c4_merged_detections_per_frame_before_cross_slice_nms": merged_per_frame,
+                  "c4_detections_per_frame_after_cross_slice_nms": kept_per_frame})
+    puck.detector.head_hook = None
+    return {"workload": "C4: 4K sliced puck detection, %d frames = %d tiles per step, 3 planted objects per frame (x2 candidates, cross-slice duplicates)"
+                        % (F4, F4 * int(plan4.tiles_per_frame)),
+            "kernel": "letterbox_kernel<true> (K1b slice letterbox, exact 5-shape-class mode)", "bound": "hbm",
+            "achieved": k1b_bytes / (k1b_ms / 1e3) / 1e9, "peak": peak, "unit": "GB/s", "frac": k1b_bytes / (k1b_ms / 1e3) / 1e9 / peak,
+            "algorithmic_bytes_per_launch": int(k1b_bytes), "avg_launch_ms": k1b_ms, "traffic": None,
+            "frames_per_sec": world * F4 * k4 / (ms4 / 1e3), "e2e_frames_per_sec": world * F4 * k4 / (ms4_e2e / 1e3)}
+
+
+def bench_c1(args, world, dev, extra):
+    """BASELINE config 1: PUCK_DETECTION on a synthetic 1280x720 60-frame clip, random-init YOLOv8n (nc=1), sliced
+    (6 tiles, 0.2 overlap) — the GPU path on the whole clip, and (N=1) the restated CPU slicer beside it on 2 frames."""
+    import torch
+    from hvb import _ffi
+    from hvb.pipeline import SlicedPuckPath
+    from hvb.synth import PlantedOverlay
+    n = 60
+    f1, _, _, pucks = synth_clip(3, n, 720, 1280, 0.67)
+    objs = [p[None] for p in pucks]
+    ov = PlantedOverlay.sliced(4, (720, 1280), 640, objs, [np.zeros(1, int)] * n, nc=1, dup=2)
+    puck = SlicedPuckPath(dev, "n", 1, 0.4)
+    plan = puck.detector.plan(n, 720, 1280, _ffi.LB_SLICE_EXACT, 640, (640, 640), (128, 128))
+    puck.detector.head_hook = ov.to_device(dev, [list(range(n))], plan=plan)
+    pinned = torch.from_numpy(f1).pin_memory()
+    for _ in range(2):
+        list(puck.process_stream([pinned]))
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    k = 4
+    dets = [d for out in puck.process_stream(pinned for _ in range(k)) for d in out]
+    dt = time.perf_counter() - t0
+    c1 = {"workload": "C1: 1280x720, 60-frame clip, YOLOv8n nc=1, sliced (6 tiles per frame), 1 planted puck per frame",
+          "gpu_e2e_frames_per_sec": k * n / dt, "detections_per_frame": sum(len(d) for d in dets) / len(dets)}
+    puck.detector.head_hook = None
+    if world == 1 and not args.no_cpu_baseline:
+        from hvb.models import build_yolov8
+        from hvb.models.yolov8 import fuse_conv_bn
+        from oracle import supervision_restated as svr, ultralytics_restated as ur
+        yolo = fuse_conv_bn(build_yolov8("n", 1, 0)).eval()
+        offs = svr.generate_offsets((1280, 720), (640, 640), (0.2, 0.2))
+
+        def cpu_frame(fid):
+            parts = []
+            for t, off in enumerate(offs):
+                tile = np.ascontiguousarray(svr.crop_image(f1[fid], off))
+                x = torch.from_numpy(ur.preprocess([ur.letterbox(tile, 640, auto=True)]))
+                with torch.no_grad():
+                    heads = [h.clone() for h in yolo(x)]
+                ov.apply_host(heads, fid, t)
+                xyxy, conf, cls = ur.predict_from_head(heads, 1, tuple(x.shape[2:]), [tile.shape[:2]], 0.4)[0]
+                parts.append((svr.move_boxes(xyxy, off[:2]), conf, cls))
+            xy = np.concatenate([p[0] for p in parts]); cf = np.concatenate([p[1] for p in parts]); cl = np.concatenate([p[2] for p in parts])
+            return xy[svr.with_nms(xy, cf, cl, 0.1)] if len(xy) else xy
+
+        cpu_frame(0)
+        t0 = time.perf_counter()
+        nd = sum(len(cpu_frame(i)) for i in (0, 1))
+        c1["cpu_frames_per_sec"] = 2 / (time.perf_counter() - t0)
+        c1["cpu_detections_per_frame"] = nd / 2
+        c1["cpu_cores"] = os.cpu_count()
+    extra["c1_720p_yolov8n_sliced"] = c1
 
 
 def main():
@@ -512,10 +697,12 @@ def main():
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="hvb", choices=["hvb", "reference"])
-    ap.add_argument("--chunk", type=int, default=64, help="1080p frames per step per GPU (64 measured best: 1832 vs 1760 frames/s at 32, 1734 at 48, 1753 at 96)")
+    ap.add_argument("--chunk", type=int, default=64, help="1080p frames per step per GPU")
     ap.add_argument("--chunk-4k", type=int, default=16, help="4K frames per step of the sliced puck path (640 tiles per step)")
     ap.add_argument("--ref-frames", type=int, default=2, help="frames per CPU-reference step (bounded sample)")
+    ap.add_argument("--tracker", default="device", choices=["device", "host"], help="K7 (device ByteTrack) or the host tracker")
     ap.add_argument("--no-4k", dest="with_4k", action="store_false")
+    ap.add_argument("--no-c1", dest="with_c1", action="store_false")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--profile-4k", action="store_true", help="with --profile-region: bracket the eager 4K sliced steps instead of the 1080p steps")
     ap.add_argument("--profile-region", action="store_true", help="cudaProfilerStart/Stop around the timed device steps (for ncu --profile-from-start off)")

@@ -35,6 +35,8 @@ struct hvb_ctx {
     uint64_t launches = 0;
     // colour tables (uploaded once): sdiv int32[256], hdiv int32[256], gtab u16[256], ctab u16[3072]
     void* tables_dev = nullptr;
+    // K3b: Pillow resampling coefficients of every source size the fast kernel accepts (built once, k3_mnv3_prep.cu)
+    void* k3b_tab_dev = nullptr;
     // growable scratch used by the *_host entry points and by multi-kernel ops
     void* scratch_dev = nullptr;
     size_t scratch_bytes = 0;
@@ -54,6 +56,7 @@ int hvb_scratch3(hvb_ctx* ctx, size_t bytes, void** out);    // device scratch #
 // K2a work area of the current stream: counters (zero between launches) + [images][cap] 64-bit keys
 int hvb_k2_work(hvb_ctx* ctx, int images, int cap, unsigned long long** keys, int32_t** ctr);
 int hvb_pinned(hvb_ctx* ctx, size_t bytes, void** out);      // pinned host staging (grow-only)
+int hvb_k3b_build_tables(hvb_ctx* ctx);                      // k3_mnv3_prep.cu, called by hvb_ctx_create
 int hvb_capturing(hvb_ctx* ctx, const char* what);           // HVB_ERR_UNSUPPORTED (with message) if ctx->stream is being captured
 
 #define HVB_CUDA(call)                                                            \

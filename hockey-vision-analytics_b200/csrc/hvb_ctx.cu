@@ -199,6 +199,10 @@ int hvb_ctx_create(int device, hvb_ctx** out_ctx) {
     memcpy(tab.data() + HVB_TAB_CTAB, kHvbLabCbrtTab, sizeof(kHvbLabCbrtTab));
     HVB_CUDA(cudaMalloc(&c->tables_dev, HVB_TAB_BYTES));
     HVB_CUDA(cudaMemcpy(c->tables_dev, tab.data(), HVB_TAB_BYTES, cudaMemcpyHostToDevice));
+    {
+        int st = hvb_k3b_build_tables(c);
+        if (st != HVB_OK) return st;
+    }
     // the copy above is ordered on the legacy stream only; the kernels run on non-blocking streams that do not
     // synchronise with it, so make the upload globally visible before the context is handed out
     HVB_CUDA(cudaDeviceSynchronize());
@@ -217,6 +221,7 @@ int hvb_ctx_destroy(hvb_ctx* ctx) {
     cudaSetDevice(ctx->device);
     cudaDeviceSynchronize();
     if (ctx->tables_dev) cudaFree(ctx->tables_dev);
+    if (ctx->k3b_tab_dev) cudaFree(ctx->k3b_tab_dev);
     if (ctx->scratch_dev) cudaFree(ctx->scratch_dev);
     for (auto& kv : ctx->work) {
         if (kv.second.k2) cudaFree(kv.second.k2);

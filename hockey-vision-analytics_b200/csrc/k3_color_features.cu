@@ -14,7 +14,8 @@
 
 namespace {
 
-constexpr int kThreads = 128;
+constexpr int kThreads = 256;         // 8 warps per crop: with 128 the grid (one CTA per crop) left 3/4 of the warp slots empty
+constexpr int kUnroll = 4;            // pixels whose loads are in flight per thread before the first one is used
 constexpr int kBatch = 255;          // pixels per thread between flushes (8-bit packed counters)
 constexpr int kNumU32 = 34 + 3;      // hist + counts
 constexpr int kNumU64 = 12;          // sums + sums of squares
@@ -151,17 +152,28 @@ color_features_kernel(const uint8_t* __restrict__ pixels, const hvb_crop_desc* _
         const int n_iter = (npx + kThreads - 1) / kThreads;
         for (int it0 = 0; it0 < n_iter; it0 += kBatch) {
             const int it1 = min(it0 + kBatch, n_iter);
-            for (int it = it0; it < it1; ++it) {
-                const int p = it * kThreads + threadIdx.x;
-                if (p < npx) {
-                    int row = (int)((float)p * inv_rw);
-                    int col = p - row * rw;
-                    if (col < 0) { row--; col += rw; }
-                    if (col >= rw) { row++; col -= rw; }
-                    const uint8_t* px = base + (int64_t)row * cd.pitch + col * 3;
-                    int b = __ldg(px), g = __ldg(px + 1), r = __ldg(px + 2);
-                    accumulate_pixel(tab, acc, b, g, r);
+            // ncu (profiles/r02a_ncu_k3.md): the one-pixel-at-a-time loop spent 4.6 of every 5.9 stall cycles per issue on
+            // the pixel loads (long scoreboard) — kUnroll pixels are loaded before the first is consumed
+            for (int it = it0; it < it1; it += kUnroll) {
+                int pb[kUnroll], pg[kUnroll], pr[kUnroll];
+                bool ok[kUnroll];
+#pragma unroll
+                for (int u = 0; u < kUnroll; u++) {
+                    const int p = (it + u) * kThreads + threadIdx.x;
+                    ok[u] = (it + u) < it1 && p < npx;
+                    pb[u] = pg[u] = pr[u] = 0;
+                    if (ok[u]) {
+                        int row = (int)((float)p * inv_rw);
+                        int col = p - row * rw;
+                        if (col < 0) { row--; col += rw; }
+                        if (col >= rw) { row++; col -= rw; }
+                        const uint8_t* px = base + (int64_t)row * cd.pitch + col * 3;
+                        pb[u] = __ldg(px); pg[u] = __ldg(px + 1); pr[u] = __ldg(px + 2);
+                    }
                 }
+#pragma unroll
+                for (int u = 0; u < kUnroll; u++)
+                    if (ok[u]) accumulate_pixel(tab, acc, pb[u], pg[u], pr[u]);
             }
             __syncwarp();
             flush(acc, s_u32, s_u64);
@@ -269,15 +281,27 @@ jersey_color_stats_kernel(const uint8_t* __restrict__ pixels, const hvb_crop_des
         const int n_iter = (npx + kThreads - 1) / kThreads;          // uniform trip count, see color_features_kernel
         for (int it0 = 0; it0 < n_iter; it0 += kBatch) {
             const int it1 = min(it0 + kBatch, n_iter);
-            for (int it = it0; it < it1; ++it) {
-                const int p = it * kThreads + threadIdx.x;
-                if (p < npx) {
-                    int row = (int)((float)p * inv_rw);
-                    int col = p - row * rw;
-                    if (col < 0) { row--; col += rw; }
-                    if (col >= rw) { row++; col -= rw; }
-                    const uint8_t* px = base + (int64_t)row * cd.pitch + col * 3;
-                    int b = __ldg(px), g = __ldg(px + 1), r = __ldg(px + 2);
+            for (int it = it0; it < it1; it += kUnroll) {
+                int pb[kUnroll], pg[kUnroll], pr[kUnroll];
+                bool ok[kUnroll];
+#pragma unroll
+                for (int u = 0; u < kUnroll; u++) {
+                    const int p = (it + u) * kThreads + threadIdx.x;
+                    ok[u] = (it + u) < it1 && p < npx;
+                    pb[u] = pg[u] = pr[u] = 0;
+                    if (ok[u]) {
+                        int row = (int)((float)p * inv_rw);
+                        int col = p - row * rw;
+                        if (col < 0) { row--; col += rw; }
+                        if (col >= rw) { row++; col -= rw; }
+                        const uint8_t* px = base + (int64_t)row * cd.pitch + col * 3;
+                        pb[u] = __ldg(px); pg[u] = __ldg(px + 1); pr[u] = __ldg(px + 2);
+                    }
+                }
+#pragma unroll
+                for (int u = 0; u < kUnroll; u++) {
+                    if (!ok[u]) continue;
+                    const int b = pb[u], g = pg[u], r = pr[u];
                     int h, s, v, L, A, B;
                     bgr_to_hsv(tab, b, g, r, h, s, v);
                     bgr_to_lab(tab, b, g, r, L, A, B);

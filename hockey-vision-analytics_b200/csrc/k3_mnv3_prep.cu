@@ -43,7 +43,8 @@ constexpr int kFastK = 8, kFastRows = 96;         // ROI up to 192 x 384 px (sca
 constexpr int kStageBytes = 20480;                // staged source rows of one row block (fast kernel)
 constexpr int kGenK = 48, kGenRows = 256;         // ROI up to ~1400 x 2900 px
 
-// Pillow precompute_coeffs + normalize_coeffs_8bpc for output sample `o` (bilinear, support 1).
+// Pillow precompute_coeffs + normalize_coeffs_8bpc for output sample `o` (bilinear, support 1); kk = the sample's own row
+// of `ksize` taps.
 __device__ void pil_coeffs(int in_size, int out_size, int o, int ksize, int* bounds, int* kk) {
     const double scale = __ddiv_rn((double)in_size, (double)out_size);
     const double filterscale = scale < 1.0 ? 1.0 : scale;
@@ -67,9 +68,9 @@ __device__ void pil_coeffs(int in_size, int out_size, int o, int ksize, int* bou
         if (t < 0.0) t = -t;
         double w = t < 1.0 ? __dsub_rn(1.0, t) : 0.0;
         if (ww != 0.0) w = __ddiv_rn(w, ww);
-        kk[o * ksize + x] = (int)__dadd_rn(0.5, __dmul_rn(w, (double)(1 << kPrecision)));
+        kk[x] = (int)__dadd_rn(0.5, __dmul_rn(w, (double)(1 << kPrecision)));
     }
-    for (int x = n; x < ksize; x++) kk[o * ksize + x] = 0;
+    for (int x = n; x < ksize; x++) kk[x] = 0;
     bounds[0] = xmin;
     bounds[1] = n;
 }
@@ -95,15 +96,30 @@ __device__ __forceinline__ void write_out(const float (*lut)[256], float* __rest
     }
 }
 
+// ---- fast path, second version (round 2).  What ncu said about the first (profiles/r01c_ncu_k3_k5.md, r02a_ncu_k3.md):
+// 5.6 k instructions per thread per crop — 1.5 k of them the float64 Pillow coefficients recomputed for every crop,
+// the rest inflated by per-tap coefficient / bound loads from shared memory, per-item index divisions, byte-wide
+// intermediate traffic and one 32-bit store per output value; issue slots 54 % busy with barrier and fixed-latency
+// stalls on top (a serial row-block planner ran on thread 0 while 255 threads waited).  This version
+//   * reads the coefficients from a table built ONCE per context for every source size the fast path accepts
+//     (hvb_k3b_build_tables: 384 sizes x (64 + 128) samples x 8 taps, 2.9 MB, L2-resident),
+//   * gives every thread a fixed output column in the horizontal pass, so its bounds and taps live in registers,
+//   * keeps the uint8 intermediate as one packed 32-bit word per pixel (one shared-memory load per tap and pixel in the
+//     vertical pass instead of three, one store per pixel in the horizontal pass instead of three),
+//   * lets a thread produce four adjacent output pixels in the vertical pass: one 128-bit intermediate load per tap
+//     and three 128-bit global stores per item instead of twelve 32-bit ones,
+//   * plans the row blocks with one __syncthreads_count.
+// The integer arithmetic (22-bit coefficients, rounding, uint8 round trip between the passes) is unchanged, so the
+// output stays bit-identical to Pillow / torchvision (tests/test_gpu_mnv3.py).
+constexpr int kTabStride = (kOutW + kOutH) * (2 + kFastK);      // ints per source size: H part (640) then V part (1280)
+constexpr int kTabHInts = kOutW * (2 + kFastK);
+constexpr int kTabSizes = 384;                                  // source sizes 1 .. 384
+
 struct SmemFast {
-    int bh[kOutW][2];
-    int bv[kOutH][2];
-    int kh[kOutW * kFastK];
-    int kv[kOutH * kFastK];
+    int vtab[kOutH * (2 + kFastK)];     // ymin[128], n[128], k[128][8] of this crop's source height
     float lut[3][256];
-    uint8_t inter[kFastRows * kOutW * 3];
+    uint32_t inter[kFastRows * kOutW];  // horizontal-pass result, b | g << 8 | r << 16 per pixel
     uint32_t roi[kStageBytes / 4];      // staged source rows: row r at byte r * pitch_s, ROI byte 0 at + shift_r
-    int blk[4];
 };
 
 __device__ __forceinline__ bool mnv3_fast_case(int rw, int rh, int ksh, int ksv) {
@@ -111,12 +127,44 @@ __device__ __forceinline__ bool mnv3_fast_case(int rw, int rh, int ksh, int ksv)
     return rw <= 0 || rh <= 0 || (ksh <= kFastK && ksv <= kFastK && !(rh > 100 * rw));
 }
 
+// One thread per (source size, output sample): the table rows the fast kernel loads instead of calling pil_coeffs.
+__global__ void __launch_bounds__(kOutW + kOutH)
+k3b_table_kernel(int* __restrict__ tab) {
+    const int s = blockIdx.x + 1;
+    const bool horiz = threadIdx.x < kOutW;
+    const int o = horiz ? threadIdx.x : threadIdx.x - kOutW;
+    const int out_size = horiz ? kOutW : kOutH;
+    int* part = tab + (int64_t)blockIdx.x * kTabStride + (horiz ? 0 : kTabHInts);
+    int bounds[2] = {0, 0};
+    int kk[kFastK];
+#pragma unroll
+    for (int x = 0; x < kFastK; x++) kk[x] = 0;
+    if (pil_ksize(s, out_size) <= kFastK) pil_coeffs(s, out_size, o, kFastK, bounds, kk);     // larger sizes never reach the fast kernel
+    part[o] = bounds[0];
+    part[out_size + o] = bounds[1];
+#pragma unroll
+    for (int x = 0; x < kFastK; x++) part[2 * out_size + o * kFastK + x] = kk[x];
+}
+
+template <int TAPS>
+__device__ __forceinline__ void hpass_item(const uint8_t* __restrict__ src, int cnt, const int (&kk)[kFastK], uint32_t* __restrict__ dst) {
+    int s0 = 1 << (kPrecision - 1), s1 = s0, s2 = s0;
+#pragma unroll
+    for (int x = 0; x < TAPS; x++)
+        if (x < cnt) { s0 += src[3 * x] * kk[x]; s1 += src[3 * x + 1] * kk[x]; s2 += src[3 * x + 2] * kk[x]; }
+    *dst = (uint32_t)clip8(s0) | ((uint32_t)clip8(s1) << 8) | ((uint32_t)clip8(s2) << 16);
+}
+
 __global__ void __launch_bounds__(kThreads, 4)
 mnv3_prep_fast_kernel(const uint8_t* __restrict__ pixels, const hvb_crop_desc* __restrict__ crops, int n, int roi_mode,
-                      float* __restrict__ out, uint8_t* __restrict__ out_u8, uint8_t* __restrict__ out_valid) {
+                      const int* __restrict__ tab, float* __restrict__ out, uint8_t* __restrict__ out_u8,
+                      uint8_t* __restrict__ out_valid) {
     extern __shared__ __align__(16) uint8_t smem_raw[];
     SmemFast& S = *reinterpret_cast<SmemFast*>(smem_raw);
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int* v_ymin = S.vtab;
+    const int* v_n = S.vtab + kOutH;
+    const int* v_k = S.vtab + 2 * kOutH;
 
     bool lut_ready = false;
     for (int ci = blockIdx.x; ci < n; ci += gridDim.x) {
@@ -150,21 +198,31 @@ mnv3_prep_fast_kernel(const uint8_t* __restrict__ pixels, const hvb_crop_desc* _
         const int rmax = min(kFastRows, kStageBytes / pitch_s);    // >= 8 = kFastK source rows always fit
 
         __syncthreads();   // previous crop's readers are done with the tables
-        if (threadIdx.x < kOutW) pil_coeffs(rw, kOutW, threadIdx.x, ksh, S.bh[threadIdx.x], S.kh);
-        else if (threadIdx.x >= 128 && threadIdx.x < 128 + kOutH) pil_coeffs(rh, kOutH, threadIdx.x - 128, ksv, S.bv[threadIdx.x - 128], S.kv);
+        {   // vertical table of this source height -> shared memory; horizontal taps of this thread's column -> registers
+            const int4* tv = reinterpret_cast<const int4*>(tab + (int64_t)(rh - 1) * kTabStride + kTabHInts);
+            int4* dv = reinterpret_cast<int4*>(S.vtab);
+            for (int i = threadIdx.x; i < kOutH * (2 + kFastK) / 4; i += kThreads) dv[i] = __ldg(tv + i);
+        }
+        const int xx = threadIdx.x & (kOutW - 1), hq = threadIdx.x >> 6;
+        const int* th = tab + (int64_t)(rw - 1) * kTabStride;
+        const int hxmin = __ldg(th + xx), hcnt = __ldg(th + kOutW + xx);
+        int hk[kFastK];
+        {
+            const int4 k0 = __ldg(reinterpret_cast<const int4*>(th + 2 * kOutW + xx * kFastK));
+            const int4 k1 = __ldg(reinterpret_cast<const int4*>(th + 2 * kOutW + xx * kFastK) + 1);
+            hk[0] = k0.x; hk[1] = k0.y; hk[2] = k0.z; hk[3] = k0.w; hk[4] = k1.x; hk[5] = k1.y; hk[6] = k1.z; hk[7] = k1.w;
+        }
         __syncthreads();
 
         int y0 = 0;
         while (y0 < kOutH) {
-            // largest block of output rows whose source-row window fits the staging + intermediate buffers
-            if (threadIdx.x == 0) {
-                const int r_lo = S.bv[y0][0];
-                int y1 = y0 + 1;
-                while (y1 < kOutH && S.bv[y1][0] + S.bv[y1][1] - r_lo <= rmax) y1++;
-                S.blk[0] = y1; S.blk[1] = r_lo; S.blk[2] = S.bv[y1 - 1][0] + S.bv[y1 - 1][1];
-            }
-            __syncthreads();
-            const int y1 = S.blk[0], r_lo = S.blk[1], r_hi = S.blk[2];
+            // largest block of output rows whose source-row window fits the staging + intermediate buffers: the window
+            // end ymin + n is non-decreasing in y, so the rows that fit are a prefix and one block-wide count finds it
+            const int r_lo = v_ymin[y0];
+            const int y = threadIdx.x;
+            const int fits = __syncthreads_count(y >= y0 && y < kOutH && v_ymin[y] + v_n[y] - r_lo <= rmax);
+            const int y1 = y0 + max(fits, 1);
+            const int r_hi = v_ymin[y1 - 1] + v_n[y1 - 1];
             const int nrows = r_hi - r_lo;
             // ---- stage rows [r_lo, r_hi): warp per row, lane per aligned 32-bit word; all loads independent
             for (int r = warp; r < nrows; r += kThreads / 32) {
@@ -188,35 +246,55 @@ mnv3_prep_fast_kernel(const uint8_t* __restrict__ pixels, const hvb_crop_desc* _
                 }
             }
             __syncthreads();
-            // ---- horizontal pass out of shared memory: rows [r_lo, r_hi) -> inter[row - r_lo][xx][c]
-            const uint8_t* sroi = reinterpret_cast<const uint8_t*>(S.roi);
-            const int sh0 = (int)(reinterpret_cast<uintptr_t>(base + (int64_t)r_lo * cd.pitch) & 3), dsh = cd.pitch & 3;
-            for (int it = threadIdx.x; it < nrows * kOutW; it += kThreads) {
-                const int row = it >> 6, xx = it & (kOutW - 1);
-                const int xmin = S.bh[xx][0], cnt = S.bh[xx][1];
-                const uint8_t* src = sroi + row * pitch_s + ((sh0 + row * dsh) & 3) + xmin * 3;
-                const int* k = S.kh + xx * ksh;
-                int s0 = 1 << (kPrecision - 1), s1 = s0, s2 = s0;
-                for (int x = 0; x < cnt; x++) {
-                    const int kk = k[x];
-                    s0 += src[3 * x] * kk; s1 += src[3 * x + 1] * kk; s2 += src[3 * x + 2] * kk;
+            // ---- horizontal pass out of shared memory: thread = (column xx, row slot hq); rows hq, hq + 4, ...
+            {
+                const uint8_t* sroi = reinterpret_cast<const uint8_t*>(S.roi);
+                const int sh0 = (int)(reinterpret_cast<uintptr_t>(base + (int64_t)r_lo * cd.pitch) & 3), dsh = cd.pitch & 3;
+                if (ksh <= 4) {
+                    for (int row = hq; row < nrows; row += kThreads / kOutW)
+                        hpass_item<4>(sroi + row * pitch_s + ((sh0 + row * dsh) & 3) + hxmin * 3, hcnt, hk, S.inter + row * kOutW + xx);
+                } else {
+                    for (int row = hq; row < nrows; row += kThreads / kOutW)
+                        hpass_item<kFastK>(sroi + row * pitch_s + ((sh0 + row * dsh) & 3) + hxmin * 3, hcnt, hk, S.inter + row * kOutW + xx);
                 }
-                uint8_t* d = S.inter + (row * kOutW + xx) * 3;
-                d[0] = (uint8_t)clip8(s0); d[1] = (uint8_t)clip8(s1); d[2] = (uint8_t)clip8(s2);
             }
             __syncthreads();
-            // ---- vertical pass: output rows [y0, y1)
-            for (int it = threadIdx.x; it < (y1 - y0) * kOutW; it += kThreads) {
-                const int y = y0 + (it >> 6), x = it & (kOutW - 1);
-                const int ymin = S.bv[y][0], cnt = S.bv[y][1];
-                const int* k = S.kv + y * ksv;
-                const uint8_t* src = S.inter + ((ymin - r_lo) * kOutW + x) * 3;
-                int s0 = 1 << (kPrecision - 1), s1 = s0, s2 = s0;
-                for (int t = 0; t < cnt; t++) {
-                    const int kk = k[t];
-                    s0 += src[t * kOutW * 3] * kk; s1 += src[t * kOutW * 3 + 1] * kk; s2 += src[t * kOutW * 3 + 2] * kk;
+            // ---- vertical pass: thread = (four adjacent output columns 4g .. 4g + 3, row slot yq); rows y0 + yq, + 16, ...
+            {
+                const int g = threadIdx.x & 15, yq = threadIdx.x >> 4;
+                for (int yy = y0 + yq; yy < y1; yy += kThreads / 16) {
+                    const int ymin = v_ymin[yy], cnt = v_n[yy];
+                    const int* k = v_k + yy * kFastK;
+                    const uint4* src = reinterpret_cast<const uint4*>(S.inter + (ymin - r_lo) * kOutW) + g;
+                    int a[4][3];
+#pragma unroll
+                    for (int px = 0; px < 4; px++) { a[px][0] = a[px][1] = a[px][2] = 1 << (kPrecision - 1); }
+                    for (int t = 0; t < cnt; t++) {
+                        const uint4 w4 = src[t * (kOutW / 4)];
+                        const int kk = k[t];
+                        const uint32_t w[4] = {w4.x, w4.y, w4.z, w4.w};
+#pragma unroll
+                        for (int px = 0; px < 4; px++) {
+                            a[px][0] += (int)(w[px] & 0xffu) * kk;
+                            a[px][1] += (int)((w[px] >> 8) & 0xffu) * kk;
+                            a[px][2] += (int)(w[px] >> 16) * kk;
+                        }
+                    }
+                    int v[4][3];
+#pragma unroll
+                    for (int px = 0; px < 4; px++) { v[px][0] = clip8(a[px][0]); v[px][1] = clip8(a[px][1]); v[px][2] = clip8(a[px][2]); }
+#pragma unroll
+                    for (int c = 0; c < 3; c++) {
+                        float4 f;
+                        f.x = S.lut[c][v[0][c]]; f.y = S.lut[c][v[1][c]]; f.z = S.lut[c][v[2][c]]; f.w = S.lut[c][v[3][c]];
+                        *reinterpret_cast<float4*>(o + (c * kOutH + yy) * kOutW + 4 * g) = f;
+                    }
+                    if (o8) {
+                        uint8_t* d8 = o8 + (yy * kOutW + 4 * g) * 3;
+#pragma unroll
+                        for (int px = 0; px < 4; px++) { d8[3 * px] = (uint8_t)v[px][0]; d8[3 * px + 1] = (uint8_t)v[px][1]; d8[3 * px + 2] = (uint8_t)v[px][2]; }
+                    }
                 }
-                write_out(S.lut, o, o8, y, x, clip8(s0), clip8(s1), clip8(s2));
             }
             __syncthreads();
             y0 = y1;
@@ -266,8 +344,8 @@ mnv3_prep_kernel(const uint8_t* __restrict__ pixels, const hvb_crop_desc* __rest
         const uint8_t* base = pixels + cd.offset + (int64_t)rc.top * cd.pitch + (int64_t)rc.left * 3;
 
         __syncthreads();   // previous crop's readers are done with the tables
-        if (threadIdx.x < kOutW) pil_coeffs(rw, kOutW, threadIdx.x, ksh, S.bh[threadIdx.x], S.kh);
-        else if (threadIdx.x >= 128 && threadIdx.x < 128 + kOutH) pil_coeffs(rh, kOutH, threadIdx.x - 128, ksv, S.bv[threadIdx.x - 128], S.kv);
+        if (threadIdx.x < kOutW) pil_coeffs(rw, kOutW, threadIdx.x, ksh, S.bh[threadIdx.x], S.kh + threadIdx.x * ksh);
+        else if (threadIdx.x >= 128 && threadIdx.x < 128 + kOutH) pil_coeffs(rh, kOutH, threadIdx.x - 128, ksv, S.bv[threadIdx.x - 128], S.kv + (threadIdx.x - 128) * ksv);
         __syncthreads();
 
         if (!vfirst) {
@@ -349,6 +427,14 @@ mnv3_prep_kernel(const uint8_t* __restrict__ pixels, const hvb_crop_desc* __rest
 
 }  // namespace
 
+// Called once from hvb_ctx_create: Pillow's coefficients for every source size the fast kernel accepts (2.9 MB).
+int hvb_k3b_build_tables(hvb_ctx* ctx) {
+    HVB_CUDA(cudaMalloc(&ctx->k3b_tab_dev, (size_t)kTabSizes * kTabStride * sizeof(int)));
+    k3b_table_kernel<<<kTabSizes, kOutW + kOutH, 0, ctx->stream>>>((int*)ctx->k3b_tab_dev);
+    HVB_LAUNCHED(ctx);
+    return HVB_OK;
+}
+
 extern "C" {
 
 int hvb_mnv3_preprocess(hvb_ctx* ctx, const uint8_t* pixels_dev, const hvb_crop_desc* crops_dev, int n, int roi_mode,
@@ -359,14 +445,17 @@ int hvb_mnv3_preprocess(hvb_ctx* ctx, const uint8_t* pixels_dev, const hvb_crop_
     if (n == 0) return HVB_OK;
     HVB_ARG(pixels_dev && crops_dev && out_dev, "null pointer");
     typedef SmemT<kGenK, kGenRows> SmemGen;
-    static_assert(sizeof(SmemFast) <= 52 * 1024 && sizeof(SmemGen) < 200 * 1024, "smem budget");
+    static_assert(sizeof(SmemFast) <= 54 * 1024 && sizeof(SmemGen) < 200 * 1024, "smem budget");
+    static_assert(kFastK == 8 && kTabSizes >= 384, "table layout");
+    HVB_ARG(ctx->k3b_tab_dev != nullptr, "context has no K3b coefficient table");
     auto fast = mnv3_prep_fast_kernel;
     auto gen = mnv3_prep_kernel<kGenK, kGenRows, false>;
     HVB_CUDA(cudaFuncSetAttribute(fast, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(SmemFast)));
     HVB_CUDA(cudaFuncSetAttribute(gen, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(SmemGen)));
     // fast pass: one CTA per crop up to the four CTAs (64 registers x 256 threads) resident per SM
     const int gfast = n < ctx->sm_count * 4 ? n : ctx->sm_count * 4;
-    fast<<<gfast, kThreads, sizeof(SmemFast), ctx->stream>>>(pixels_dev, crops_dev, n, roi_mode, out_dev, out_u8_dev, out_valid_dev);
+    fast<<<gfast, kThreads, sizeof(SmemFast), ctx->stream>>>(pixels_dev, crops_dev, n, roi_mode, (const int*)ctx->k3b_tab_dev, out_dev,
+                                                             out_u8_dev, out_valid_dev);
     HVB_LAUNCHED(ctx);
     // general pass: only the crops the fast pass skipped (usually none: its CTAs read the descriptors and exit)
     const int ggen = n < ctx->sm_count ? n : ctx->sm_count;

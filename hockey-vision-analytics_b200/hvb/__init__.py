@@ -33,7 +33,7 @@ def __getattr__(name):
     if name in ("VideoProcessor", "Config", "FrameResult"):
         from . import video
         return getattr(video, name)
-    if name in ("ByteTrack", "MultiClipByteTrack"):
+    if name in ("ByteTrack", "MultiClipByteTrack", "DeviceByteTrack"):
         from . import tracker
         return getattr(tracker, name)
     raise AttributeError(name)

@@ -102,6 +102,10 @@ PROTOTYPES = {
     "hvb_sppf_pool_concat": [_vp, _vp, _i, _i, _i, _i, _vp],
     "hvb_stem_conv": [_vp, _vp, _vp, _vp, _i, _i, _i, _i, _vp],
     "hvb_pointwise_conv": [_vp, _vp, _i, _vp, _vp, _i64, _i, _i, _i, _vp, _i, _i, _vp, _i, _i, _i, _i],
+    "hvb_bytetrack_create": [_vp, _i, _d, _d, _d, _i, _i, _pp],
+    "hvb_bytetrack_destroy": [_vp, _vp],
+    "hvb_bytetrack_reset": [_vp, _vp],
+    "hvb_bytetrack_update": [_vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i64, _i64, _f, C.c_uint32, _i, _vp, _vp, _vp],
     "hvb_color_features_host": [_vp, _vp, _sz, _vp, _i, _i, _vp, _vp],
     "hvb_jersey_color_stats": [_vp, _vp, _vp, _i, _i, _vp],
     "hvb_jersey_color_stats_host": [_vp, _vp, _sz, _vp, _i, _i, _vp],

@@ -225,7 +225,10 @@ class Detector:
 
     def detect_batch(self, frames, imgsz: Optional[int] = None) -> List[Detections]:
         """List of Detections (one per frame), equal to from_ultralytics(model(frame, imgsz=imgsz)[0]) per frame."""
-        frames_dev = self.upload(frames)
+        return self.detect_batch_device(self.upload(frames), imgsz)
+
+    def detect_batch_device(self, frames_dev: torch.Tensor, imgsz: Optional[int] = None) -> List[Detections]:
+        """detect_batch for frames that are already on the device (uint8[n,H,W,3])."""
         xyxy, cf, cl, cnt, state = self.detect_device(frames_dev, imgsz=imgsz)
         cnt_h = cnt.cpu().numpy()
         if (cnt_h < 0).any():
@@ -242,9 +245,10 @@ class Detector:
     def __call__(self, frame: np.ndarray) -> Detections:
         return self.detect_batch(frame)[0]
 
-    def detect_players(self, frame: np.ndarray) -> Detections:
-        """VideoProcessor.detect_players: detection + the class / confidence mask of main.py:189-193."""
-        d = self(frame)
+    def detect_players(self, frame) -> Detections:
+        """VideoProcessor.detect_players: detection + the class / confidence mask of main.py:189-193.  `frame`: a host
+        frame uint8[H,W,3], or the same frame already on the device as uint8[1,H,W,3]."""
+        d = self.detect_batch_device(frame)[0] if isinstance(frame, torch.Tensor) else self(frame)
         keep = ((d.class_id == PLAYER_CLASS_ID) | (d.class_id == GOALKEEPER_CLASS_ID)) & (d.confidence > self.conf)
         return d[keep]
 

@@ -111,13 +111,27 @@ class HybridTeamClassifier:
                                      out_feat=feats[:, N_DEEP:], feat_stride=N_DEEP + N_COLOR)
         if want_raw:
             _, raw = res
+        # The number of crops changes from call to call (tracked players of a chunk / a frame); with cudnn.benchmark on,
+        # every new batch size would re-run the autotuner for each of the trunk's ~50 convolutions (seconds — measured:
+        # the 32-frame drop-in fell to 42 frames/s).  The trunk therefore only ever sees a few bucketed batch sizes: K3b
+        # writes the first n rows of a bucket-sized tensor, the padding rows are zero and their outputs are dropped.
+        nb = self._bucket(n)
         with nvtx("hvb:K3b crop preprocessing"):
-            x, valid = ctx.mnv3_preprocess(pixels, crops_dev, n, _ffi.ROI_HYBRID)
+            x, valid = ctx.mnv3_preprocess(pixels, crops_dev, n, _ffi.ROI_HYBRID, rows=nb)
         with nvtx("hvb:mobilenetv3 trunk"):
-            deep = self._trunk_forward(x)
+            deep = self._trunk_forward(x)[:n]
         deep = deep * (valid == 1).to(deep.dtype).unsqueeze(1)       # failed preprocessing -> zeros(576)
         feats[:, :N_DEEP] = deep.to(torch.float64)
         return feats, raw, valid
+
+    @staticmethod
+    def _bucket(n: int) -> int:
+        """Batch size the trunk runs at for n crops: 16, 64, then multiples of 128."""
+        if n <= 16:
+            return 16
+        if n <= 64:
+            return 64
+        return (n + 127) // 128 * 128
 
     def _raise_on_empty(self, feats_color_first: torch.Tensor):
         # cv2.cvtColor raises on an empty ROI in the reference (no try/except around the colour path)
@@ -129,8 +143,9 @@ class HybridTeamClassifier:
         if not len(crops):
             return np.array([])
         pixels, cd = self._upload_crops(crops)
-        x, valid = self.ctx.mnv3_preprocess(pixels, cd, len(crops), _ffi.ROI_HYBRID)
-        deep = self._trunk_forward(x) * (valid == 1).float().unsqueeze(1)
+        n = len(crops)
+        x, valid = self.ctx.mnv3_preprocess(pixels, cd, n, _ffi.ROI_HYBRID, rows=self._bucket(n))
+        deep = self._trunk_forward(x)[:n] * (valid == 1).float().unsqueeze(1)
         return deep.cpu().numpy()
 
     def extract_color_features(self, crops: List[np.ndarray]) -> np.ndarray:

@@ -277,10 +277,16 @@ class Context:
         return hsv, lab
 
     def mnv3_preprocess(self, pixels: torch.Tensor, crops: torch.Tensor, n: int, roi_mode: int = _ffi.ROI_HYBRID,
-                        want_u8: bool = False):
+                        want_u8: bool = False, rows: Optional[int] = None):
+        """`rows` >= n: allocate that many output rows (the kernel fills the first n, the rest are zero) so that the
+        backbone behind it can run at a bucketed batch size."""
         with self.lock:
             self._enter()
-            out = self.empty((n, 3, 128, 64), torch.float32)
+            if rows is not None and rows > n:
+                out = self.empty((rows, 3, 128, 64), torch.float32)
+                out[n:].zero_()
+            else:
+                out = self.empty((n, 3, 128, 64), torch.float32)
             u8 = self.empty((n, 128, 64, 3), torch.uint8) if want_u8 else None
             valid = self.empty((max(n, 1),), torch.uint8)
             check(self.lib.hvb_mnv3_preprocess(self.handle, ptr(pixels), ptr(crops), n, roi_mode, ptr(out), ptr(u8), ptr(valid)))
@@ -331,6 +337,42 @@ class Context:
             check(self.lib.hvb_iou_cost(self.handle, ptr(a), ptr(b), ptr(scores), ptr(a_off), ptr(b_off), ptr(out_off),
                                         n_problems, max_na, max_nb, flags, ptr(out)))
         return out
+
+    # ------------------------------------------------------------------ K7 (device ByteTrack)
+    def bytetrack_create(self, n_clips: int, track_activation_threshold: float, det_threshold: float,
+                         minimum_matching_threshold: float, max_time_lost: int, minimum_consecutive_frames: int) -> C.c_void_p:
+        h = C.c_void_p()
+        with self.lock:
+            self._enter()
+            check(self.lib.hvb_bytetrack_create(self.handle, n_clips, float(track_activation_threshold), float(det_threshold),
+                                                float(minimum_matching_threshold), int(max_time_lost),
+                                                int(minimum_consecutive_frames), C.byref(h)))
+        return h
+
+    def bytetrack_destroy(self, handle) -> None:
+        with self.lock:
+            check(self.lib.hvb_bytetrack_destroy(self.handle, handle))
+
+    def bytetrack_reset(self, handle) -> None:
+        with self.lock:
+            self._enter()
+            check(self.lib.hvb_bytetrack_reset(self.handle, handle))
+
+    def bytetrack_update(self, handle, xyxy: torch.Tensor, conf: torch.Tensor, cls: Optional[torch.Tensor], count: torch.Tensor,
+                         n_frames: int, clip_stride: int, frame_stride: int = 1, min_conf: float = float("-inf"),
+                         class_mask: int = 0xFFFFFFFF, seq: int = 0):
+        """K2a-layout detections [images, max_det, ...] -> (row i32[images,max_det], tracker_id i32[images,max_det],
+        count i32[images]) on the device; one launch, stream-ordered."""
+        images, max_det = conf.shape
+        with self.lock:
+            self._enter()
+            row = self.empty((images, max_det), torch.int32)
+            tid = self.empty((images, max_det), torch.int32)
+            cnt = torch.zeros((images,), dtype=torch.int32, device=self.device)
+            check(self.lib.hvb_bytetrack_update(self.handle, handle, ptr(xyxy), ptr(conf), ptr(cls), ptr(count), n_frames, max_det,
+                                                clip_stride, frame_stride, float(min_conf), class_mask & 0xFFFFFFFF, int(seq),
+                                                ptr(row), ptr(tid), ptr(cnt)))
+        return row, tid, cnt
 
     # ------------------------------------------------------------------ K5 (backbone glue; NHWC float32)
     ACT = {"none": 0, "silu": 1, "relu": 2, "hardswish": 3, "silu_fast": 4}

@@ -334,6 +334,97 @@ class ByteTrack:
         return empty
 
 
+class DeviceByteTrack:
+    """sv.ByteTrack on the device (K7, csrc/k7_bytetrack.cu): same constructor as ``sv.ByteTrack`` (main.py:162-168), same
+    ``update_with_detections`` — Kalman filter, the three association rounds, the assignment solver and the id
+    bookkeeping all run in one kernel launch per call — plus ``update_chunk_device``, which steps a whole chunk of frames
+    of every clip straight from K2a's device outputs without any host round trip.  ``n_clips`` independent trackers share
+    one object (one warp each, concurrently).  Results equal hvb.tracker.ByteTrack / the restated supervision tracker."""
+
+    def __init__(self, track_activation_threshold: float = 0.25, lost_track_buffer: int = 30,
+                 minimum_matching_threshold: float = 0.8, frame_rate: int = 30, minimum_consecutive_frames: int = 1,
+                 n_clips: int = 1, device="cuda:0"):
+        from .runtime import get_context
+        self.ctx = get_context(device)
+        self.n_clips = n_clips
+        self.track_activation_threshold = track_activation_threshold
+        self.minimum_matching_threshold = minimum_matching_threshold
+        self.det_thresh = track_activation_threshold + 0.1
+        self.max_time_lost = int(frame_rate / 30.0 * lost_track_buffer)
+        self.minimum_consecutive_frames = minimum_consecutive_frames
+        self._h = self.ctx.bytetrack_create(n_clips, track_activation_threshold, self.det_thresh, minimum_matching_threshold,
+                                            self.max_time_lost, minimum_consecutive_frames)
+        self._seq = 0                       # sequence number of the next chunk (the device accepts chunks strictly in order)
+
+    def __del__(self):
+        try:
+            if getattr(self, "_h", None):
+                self.ctx.bytetrack_destroy(self._h)
+                self._h = None
+        except Exception:                                  # noqa: BLE001 - interpreter shutdown
+            pass
+
+    def reset(self) -> None:
+        self.ctx.bytetrack_reset(self._h)
+        self._seq = 0
+
+    def next_seq(self) -> int:
+        s = self._seq
+        self._seq += 1
+        return s
+
+    def update_chunk_device(self, xyxy, conf, cls, count, n_frames: Optional[int] = None, min_conf: float = float("-inf"),
+                            class_mask: int = 0xFFFFFFFF, seq: Optional[int] = None):
+        """K2a outputs of n_frames consecutive frames per clip, clip-major (image = clip * n_frames + frame) ->
+        (row, tracker_id, count) device tensors in the same image order.  count -1 / -2: see include/hvb.h.
+        `seq`: None = the next chunk; an explicit number resubmits a chunk the device rejected (count -2)."""
+        images = conf.shape[0]
+        n_frames = images // self.n_clips if n_frames is None else n_frames
+        if n_frames * self.n_clips != images:
+            raise ValueError("expected n_clips * n_frames = %d images, got %d" % (n_frames * self.n_clips, images))
+        return self.ctx.bytetrack_update(self._h, xyxy, conf, cls, count, n_frames, clip_stride=n_frames, frame_stride=1,
+                                         min_conf=min_conf, class_mask=class_mask, seq=self.next_seq() if seq is None else seq)
+
+    def update_many(self, detections: Sequence[Detections]) -> List[Detections]:
+        """One frame of every clip (detections[i] belongs to clip i), host in / host out, one launch."""
+        import torch
+        from . import _ffi
+        assert len(detections) == self.n_clips
+        n = [len(d) for d in detections]
+        md = max(max(n), 1)
+        xy = np.zeros((self.n_clips, md, 4), np.float32)
+        cf = np.zeros((self.n_clips, md), np.float32)
+        for i, d in enumerate(detections):
+            if n[i]:
+                xy[i, :n[i]] = np.asarray(d.xyxy, np.float32).reshape(-1, 4)
+                cf[i, :n[i]] = np.asarray(d.confidence, np.float32).reshape(-1)
+        dev = self.ctx.device
+        row, tid, cnt = self.ctx.bytetrack_update(self._h, torch.from_numpy(xy).to(dev), torch.from_numpy(cf).to(dev), None,
+                                                  torch.tensor(n, dtype=torch.int32, device=dev), 1, clip_stride=1, frame_stride=1,
+                                                  seq=self.next_seq())
+        row_h, tid_h, cnt_h = row.cpu().numpy(), tid.cpu().numpy(), cnt.cpu().numpy()
+        if (cnt_h < 0).any():
+            raise _ffi.HvbError(_ffi.HVB_ERR_CAPACITY, "ByteTrack capacity exceeded (256 live tracks per clip, 320 detections per frame)")
+        out = []
+        for i, d in enumerate(detections):
+            k = int(cnt_h[i])
+            if k == 0:
+                e = Detections.empty()
+                e.tracker_id = np.array([], dtype=int)
+                out.append(e)
+                continue
+            ids = np.full(n[i], -1, dtype=int)
+            ids[row_h[i, :k]] = tid_h[i, :k]
+            d.tracker_id = ids
+            out.append(d[ids != -1])
+        return out
+
+    def update_with_detections(self, detections: Detections) -> Detections:
+        if self.n_clips != 1:
+            raise ValueError("update_with_detections is the single-clip call; use update_many")
+        return self.update_many([detections])[0]
+
+
 class MultiClipByteTrack:
     """N independent ByteTrack instances (one per clip) stepped in lockstep, one frame of every clip per call.
 

@@ -29,7 +29,7 @@ import torch
 from .detect import Detector, GOALKEEPER_CLASS_ID, PLAYER_CLASS_ID
 from .detections import Detections, crop_image
 from .team import TeamClassifier
-from .tracker import ByteTrack
+from .tracker import ByteTrack, DeviceByteTrack
 
 
 @dataclass
@@ -58,21 +58,37 @@ class FrameResult:
 
 
 class VideoProcessor:
-    def __init__(self, player_model: torch.nn.Module, device: str = "cuda:0", config: Optional[Config] = None,
+    def __init__(self, player_model: Optional[torch.nn.Module] = None, device: str = "cuda:0", config: Optional[Config] = None,
                  team_classifier: Optional[TeamClassifier] = None, trunk: Optional[torch.nn.Module] = None,
-                 team_selector: Optional[Callable] = None, detector_kwargs: Optional[dict] = None):
+                 team_selector: Optional[Callable] = None, detector_kwargs: Optional[dict] = None,
+                 detector: Optional[Detector] = None, tracker: str = "device"):
+        """`tracker`: "device" = K7 (the whole of sv.ByteTrack in one kernel, fed from K2a's device outputs in the chunked
+        path); "host" = hvb.tracker.ByteTrack (numpy bookkeeping, K4b cost matrices).  Same results.
+        `detector`: reuse an existing Detector (its weights, plans and cuDNN autotuning) instead of building one."""
         self.config = config or Config()
         self.device = device
-        kw = dict(fuse=True, channels_last=True, cuda_graph=None)       # frame-at-a-time calls are launch-bound: replay a graph when the forward is capturable
-        kw.update(detector_kwargs or {})
-        self.detector = Detector(player_model, device, imgsz=self.config.detection_imgsz, conf=self.config.detection_confidence,
-                                 class_names={PLAYER_CLASS_ID: "player", GOALKEEPER_CLASS_ID: "goalie"}, **kw)
+        if detector is None:
+            kw = dict(fuse=True, channels_last=True, cuda_graph=None)   # frame-at-a-time calls are launch-bound: replay a graph when the forward is capturable
+            kw.update(detector_kwargs or {})
+            detector = Detector(player_model, device, imgsz=self.config.detection_imgsz, conf=self.config.detection_confidence,
+                                class_names={PLAYER_CLASS_ID: "player", GOALKEEPER_CLASS_ID: "goalie"}, **kw)
+        self.detector = detector
         self.team_classifier = team_classifier if team_classifier is not None else TeamClassifier(device=device, trunk=trunk)
         self.team_selector = team_selector
+        if tracker not in ("device", "host"):
+            raise ValueError("tracker must be 'device' or 'host'")
+        self.tracker_backend = tracker
         c = self.config
-        self.tracker = ByteTrack(track_activation_threshold=c.track_activation_threshold, lost_track_buffer=c.lost_track_buffer,
-                                 minimum_matching_threshold=c.minimum_matching_threshold, frame_rate=c.frame_rate,
-                                 minimum_consecutive_frames=c.minimum_consecutive_frames, device=device)
+        self.tracker = self._make_tracker(track_activation_threshold=c.track_activation_threshold, lost_track_buffer=c.lost_track_buffer,
+                                          minimum_matching_threshold=c.minimum_matching_threshold, frame_rate=c.frame_rate,
+                                          minimum_consecutive_frames=c.minimum_consecutive_frames)
+        self._track_stream = None
+        self._team_stream = None
+
+    def _make_tracker(self, **kw):
+        if self.tracker_backend == "device":
+            return DeviceByteTrack(device=self.device, **kw)
+        return ByteTrack(device=self.device, **kw)
 
     # ------------------------------------------------------------------ main.py:177-195
     def detect_players(self, frame: np.ndarray) -> Detections:
@@ -84,8 +100,8 @@ class VideoProcessor:
         c = self.config
         crops, positions = [], []
         first_frame, first_tracked = None, None
-        temp_tracker = ByteTrack(track_activation_threshold=c.track_activation_threshold, minimum_consecutive_frames=1,
-                                 frame_rate=c.frame_rate, device=self.device)
+        temp_tracker = self._make_tracker(track_activation_threshold=c.track_activation_threshold, minimum_consecutive_frames=1,
+                                          frame_rate=c.frame_rate)
         sampled = (f for k, f in enumerate(frames) if k % c.initialization_stride == 0)    # get_video_frames_generator(stride=)
         for i, frame in enumerate(sampled):
             if i > c.max_initialization_frames:
@@ -110,14 +126,18 @@ class VideoProcessor:
 
     # ------------------------------------------------------------------ main.py:259-313
     def process_frame(self, frame: np.ndarray) -> FrameResult:
-        detections = self.detect_players(frame)
+        # the frame crosses PCIe once: the detector and the team stage both read the device copy (crops are boxes into it,
+        # hvb_crops_from_boxes == sv.crop_image's rounding and slicing), instead of packing host crops and uploading them again
+        frame_dev = self.detector.upload(frame)
+        detections = self.detector.detect_players(frame_dev)
         tracked = self.tracker.update_with_detections(detections)
         players = tracked[tracked.class_id == PLAYER_CLASS_ID]
         goalies = tracked[tracked.class_id == GOALKEEPER_CLASS_ID]
         player_team_ids = np.array([])
         if len(players) > 0:
-            player_team_ids = self.team_classifier.predict(self._get_crops(frame, players), tracker_ids=players.tracker_id,
-                                                           positions=self._get_positions(players))
+            player_team_ids = self.team_classifier.predict_from_frame(
+                frame_dev, torch.from_numpy(np.ascontiguousarray(players.xyxy, np.float32)), None,
+                tracker_ids=players.tracker_id, host_frames=[frame])
         return self._finish(players, goalies, player_team_ids)
 
     def _finish(self, players: Detections, goalies: Detections, player_team_ids: np.ndarray) -> FrameResult:
@@ -136,15 +156,14 @@ class VideoProcessor:
         """Same results as process_video, GPU work batched per chunk of frames (see the module docstring).
 
         Three things run concurrently: a staging thread copies chunk i+1 into a pinned buffer and starts its H2D copy on
-        a side stream; the GPU detects chunk i (its results leave through an asynchronous D2H copy + an event); the main
-        thread runs ByteTrack and the team stage of chunk i-1.  Results are yielded in frame order."""
+        a side stream; the GPU detects and tracks chunk i (results leave through an asynchronous D2H copy + an event);
+        the main thread runs the team stage of chunk i-1.  Results are yielded in frame order."""
         import queue
         import threading
         if initialize:
             self.initialize_team_classifier(frames)
-        det, conf = self.detector, self.config.detection_confidence
+        det = self.detector
         dev = det.device
-        main = torch.cuda.current_stream(dev)
         copy_stream = torch.cuda.Stream(device=dev)
         starts = list(range(0, len(frames), chunk))
         q: "queue.Queue" = queue.Queue(maxsize=2)
@@ -164,66 +183,165 @@ class VideoProcessor:
                 q.put(e)
 
         threading.Thread(target=stager, daemon=True).start()
-        pinned = [dict(), dict()]
+
+        def source():
+            while True:
+                item = q.get()
+                if isinstance(item, BaseException):
+                    raise item
+                if item is None:
+                    return
+                yield item
+
+        yield from self.process_chunks(source())
+
+    def process_chunks(self, chunks: Iterable) -> Iterator[FrameResult]:
+        """The chunk pipeline behind process_video_chunked, for chunks that are (or are being made) resident on the device.
+
+        `chunks` yields either a device tensor uint8[n,H,W,3] or a tuple (host_block | None, frames_dev, ready_event | None)
+        (`ready_event`: the H2D copy of that chunk, recorded on another stream).  Per chunk, stream-ordered and without
+        a host round trip: K1a -> YOLO -> K2a on the main stream, then (device tracker) K7 on a side stream stepping the
+        chunk's frames in order straight from K2a's outputs, then one asynchronous D2H of detections + tracker ids.  The host
+        touches chunk i-1 (player boxes -> team stage K3a/K3b/MobileNetV3/K4a -> rule + temporal vote, FrameResults) while
+        the GPU works on chunk i."""
+        det = self.detector
+        dev = det.device
+        main = torch.cuda.current_stream(dev)
+        if self._track_stream is None:
+            self._track_stream = torch.cuda.Stream(device=dev, priority=-1)
+        side = self._track_stream
+        if self._team_stream is None:
+            # the team stage of chunk i-1 is issued AFTER chunk i's detection has been queued on the main stream; on its
+            # own high-priority stream it runs beside that detection instead of behind it (the host waits for its result)
+            self._team_stream = torch.cuda.Stream(device=dev, priority=-1)
+        team_stream = self._team_stream
+        pinned = [dict(), dict(), dict()]
+        device_tracker = self.tracker_backend == "device"
+        conf_thr = float(self.config.detection_confidence)
+        cmask = (1 << PLAYER_CLASS_ID) | (1 << GOALKEEPER_CLASS_ID)
+
+        def track(ci, dets, seq):
+            """K7 on the tracker stream + the asynchronous D2H of everything the host reads for this chunk."""
+            xyxy, cf, cl, cnt = dets
+            outs = [("xyxy", xyxy), ("conf", cf), ("cls", cl), ("count", cnt)]
+            stream = main
+            if device_tracker:
+                side.wait_stream(main)
+                stream = side
+                with torch.cuda.stream(side):
+                    row, tid, tcnt = self.tracker.update_chunk_device(xyxy, cf, cl, cnt, min_conf=conf_thr, class_mask=cmask, seq=seq)
+                outs += [("row", row), ("tid", tid), ("tcount", tcnt)]
+                for t in dets:
+                    t.record_stream(side)
+            host = pinned[ci % 3]
+            with torch.cuda.stream(stream):
+                for k, t in outs:
+                    if k not in host or host[k].shape != t.shape:
+                        host[k] = torch.empty(t.shape, dtype=t.dtype).pin_memory()
+                    host[k].copy_(t, non_blocking=True)
+                done = torch.cuda.Event()
+                done.record(stream)
+            return host, done
 
         def launch(ci, item):
-            block, frames_dev, ready = item
-            main.wait_event(ready)
-            frames_dev.record_stream(main)
-            xyxy, cf, cl, cnt, _state = det.detect_device(frames_dev)
-            host = pinned[ci & 1]
-            for k, t in (("xyxy", xyxy), ("conf", cf), ("cls", cl), ("count", cnt)):
-                if k not in host or host[k].shape != t.shape:
-                    host[k] = torch.empty(t.shape, dtype=t.dtype).pin_memory()
-                host[k].copy_(t, non_blocking=True)                    # stream-ordered before the next graph replay
-            done = torch.cuda.Event()
-            done.record(main)
-            return block, frames_dev, host, done
+            block, frames_dev, ready = item if isinstance(item, tuple) else (None, item, None)
+            if ready is not None:
+                main.wait_event(ready)
+                frames_dev.record_stream(main)
+            xyxy, cf, cl, cnt, state = det.detect_device(frames_dev)
+            if det.cuda_graph:                                          # static graph outputs: the next replay overwrites them
+                xyxy, cf, cl, cnt = xyxy.clone(), cf.clone(), cl.clone(), cnt.clone()
+            seq = self.tracker.next_seq() if device_tracker else 0
+            host, done = track(ci, (xyxy, cf, cl, cnt), seq)
+            return dict(ci=ci, block=block, frames=frames_dev, host=host, done=done, dets=(xyxy, cf, cl, cnt), state=state,
+                        ready=ready, seq=seq)
 
-        def finish(p):
-            block, frames_dev, host, done = p
-            done.synchronize()
+        def finish(p, nxt):
+            block, frames_dev, host, ready = p["block"], p["frames"], p["host"], p["ready"]
+            xyxy, cf, cl, cnt = p["dets"]
+            p["done"].synchronize()
             cnt_h = host["count"].numpy().copy()
+            redo = False
+            if (cnt_h < 0).any():                                       # > 1024 candidates in a frame: K2a's large tier for those frames
+                state = p["state"]
+                if det.cuda_graph:                                      # the graph's head tensors now hold a later chunk: redo eagerly
+                    if det.head_hook is not None:
+                        raise RuntimeError("candidate overflow with a head_hook under CUDA graphs is not supported")
+                    xyxy, cf, cl, cnt, state = det.detect_device(frames_dev, graph=False)
+                    cnt_h = cnt.cpu().numpy()
+                cnt_h = det._retry_overflow(xyxy, cf, cl, cnt, state, cnt_h)
+                redo = True
+            if device_tracker and (redo or (host["tcount"].numpy() == -2).any()):
+                # K7 rejected this chunk (its own overflow, or it was queued behind a rejected chunk) and left the clip
+                # untouched: step it now, then resubmit the chunk already queued behind it so the pipeline stays in order
+                host, done = track(p["ci"], (xyxy, cf, cl, cnt), p["seq"])
+                done.synchronize()
+                if nxt is not None:
+                    nxt["host"], nxt["done"] = track(nxt["ci"], nxt["dets"], nxt["seq"])
+            elif redo:
+                host = dict(xyxy=xyxy.cpu(), conf=cf.cpu(), cls=cl.cpu())
             xyxy_h, cf_h, cl_h = host["xyxy"].numpy(), host["conf"].numpy(), host["cls"].numpy()
-            if (cnt_h < 0).any():                                       # > 1024 candidates in a frame: redo eagerly with the retry tier
-                xyxy, cf, cl, cnt, state = det.detect_device(frames_dev, graph=False)
-                cnt_h = det._retry_overflow(xyxy, cf, cl, cnt, state, cnt.cpu().numpy())
-                xyxy_h, cf_h, cl_h = xyxy.cpu().numpy(), cf.cpu().numpy(), cl.cpu().numpy()
-            per_frame, boxes, fidx, tids = [], [], [], []
-            for i, k in enumerate(cnt_h):                             # ByteTrack: strictly sequential per frame
-                d = det._to_detections(xyxy_h[i, :k], cf_h[i, :k], cl_h[i, :k])
-                d = d[((d.class_id == PLAYER_CLASS_ID) | (d.class_id == GOALKEEPER_CLASS_ID)) & (d.confidence > conf)]
-                tracked = self.tracker.update_with_detections(d)
-                players = tracked[tracked.class_id == PLAYER_CLASS_ID]
-                goalies = tracked[tracked.class_id == GOALKEEPER_CLASS_ID]
-                per_frame.append((players, goalies))
-                if len(players):
-                    boxes.append(np.asarray(players.xyxy, np.float32)); fidx.append(np.full(len(players), i, np.int32))
-                    tids.append(np.asarray(players.tracker_id))
+            n = len(cnt_h)
+            if device_tracker:
+                tc = host["tcount"].numpy()
+                if (tc < 0).any():
+                    from . import _ffi
+                    raise _ffi.HvbError(_ffi.HVB_ERR_CAPACITY, "ByteTrack capacity exceeded (256 live tracks per clip, 320 detections per frame)")
+                row_h, tid_h = host["row"].numpy(), host["tid"].numpy()
+                fi, pos = np.nonzero(np.arange(row_h.shape[1])[None, :] < tc[:, None])       # frame-major, detection order
+                rows = row_h[fi, pos]
+                t_xyxy, t_conf, t_cls, t_tid = xyxy_h[fi, rows], cf_h[fi, rows], cl_h[fi, rows].astype(int), tid_h[fi, pos].astype(int)
+                seg = np.concatenate([[0], np.cumsum(tc)])
+            else:
+                parts = []
+                for i, k in enumerate(cnt_h):                           # host ByteTrack: strictly sequential per frame
+                    d = det._to_detections(xyxy_h[i, :k], cf_h[i, :k], cl_h[i, :k])
+                    d = d[((d.class_id == PLAYER_CLASS_ID) | (d.class_id == GOALKEEPER_CLASS_ID)) & (d.confidence > conf_thr)]
+                    parts.append(self.tracker.update_with_detections(d))
+                tc = np.array([len(d) for d in parts])
+                fi = np.repeat(np.arange(n), tc)
+                seg = np.concatenate([[0], np.cumsum(tc)])
+                cat = lambda f, dt: np.concatenate([np.asarray(f(d)) for d in parts]).astype(dt) if len(fi) else np.zeros((0,), dt)
+                t_xyxy = np.concatenate([np.asarray(d.xyxy, np.float32).reshape(-1, 4) for d in parts]) if len(fi) else np.zeros((0, 4), np.float32)
+                t_conf, t_cls, t_tid = cat(lambda d: d.confidence, np.float32), cat(lambda d: d.class_id, int), cat(lambda d: d.tracker_id, int)
+            is_player = t_cls == PLAYER_CLASS_ID
             team_ids = np.array([])
-            if boxes:                                                   # one feature pass for every tracked player of the chunk
-                team_ids = self.team_classifier.predict_from_frame(
-                    frames_dev, torch.from_numpy(np.concatenate(boxes)), torch.from_numpy(np.concatenate(fidx)).to(dev),
-                    tracker_ids=np.concatenate(tids), host_frames=block)          # host frames only for the fallback cascade
-            out, pos = [], 0
-            for players, goalies in per_frame:
-                n = len(players)
-                out.append(self._finish(players, goalies, team_ids[pos:pos + n] if n else np.array([])))
-                pos += n
+            if is_player.any():                                         # one feature pass for every tracked player of the chunk
+                if ready is not None:
+                    team_stream.wait_event(ready)                       # the chunk's H2D copy
+                frames_dev.record_stream(team_stream)
+                with torch.cuda.stream(team_stream):
+                    team_ids = self.team_classifier.predict_from_frame(
+                        frames_dev, torch.from_numpy(np.ascontiguousarray(t_xyxy[is_player], np.float32)),
+                        torch.from_numpy(fi[is_player].astype(np.int32)).to(dev), tracker_ids=t_tid[is_player],
+                        host_frames=block)                              # host frames only for the fallback cascade
+            names = det.class_names
+            out, tpos = [], 0
+            for i in range(n):
+                lo, hi = int(seg[i]), int(seg[i + 1])
+                pl = np.nonzero(is_player[lo:hi])[0] + lo
+                gl = np.nonzero(t_cls[lo:hi] == GOALKEEPER_CLASS_ID)[0] + lo
+                order = np.concatenate([pl, gl])                        # Detections.merge([players, goalies])
+                cls_i = t_cls[order]
+                if len(order):
+                    merged = Detections(xyxy=t_xyxy[order], confidence=t_conf[order], class_id=cls_i, tracker_id=t_tid[order],
+                                        data={"class_name": np.array([names.get(int(c), str(int(c))) for c in cls_i], dtype=object)})
+                else:
+                    merged = Detections.empty()
+                ptid = team_ids[tpos:tpos + len(pl)] if len(pl) else np.array([])
+                tpos += len(pl)
+                gtid = np.array([2] * len(gl), dtype=np.int32)
+                out.append(FrameResult(merged, ptid, gtid, self._create_color_lookup(ptid, gtid), self._create_labels(merged, ptid)))
             return out
 
-        pending, ci = None, 0
-        while True:
-            item = q.get()
-            if isinstance(item, BaseException):
-                raise item
-            nxt = launch(ci, item) if item is not None else None        # chunk ci is queued on the GPU ...
-            ci += 1
+        pending = None
+        for ci, item in enumerate(chunks):
+            nxt = launch(ci, item)                                      # chunk ci is queued on the GPU ...
             if pending is not None:
-                yield from finish(pending)                              # ... while the host finishes chunk ci-1
+                yield from finish(pending, nxt)                         # ... while the host finishes chunk ci-1
             pending = nxt
-            if item is None:
-                break
+        if pending is not None:
+            yield from finish(pending, None)
 
     # ------------------------------------------------------------------ main.py:324-358
     @staticmethod

@@ -355,6 +355,36 @@ HVB_API int hvb_pointwise_conv(hvb_ctx* ctx, const float* x_dev, int x_ld, const
                        int64_t npix, int c_in, int c_out, int act, float* out1_dev, int out1_ld, int out1_off,
                        float* out2_dev, int out2_ld, int out2_off, int c2_begin, int c2_count);
 
+/* ---------------------------------------------------------------- K7: device ByteTrack
+ * sv.ByteTrack as the reference constructs it (hockey/main.py:162-168: the main tracker; :207-211: the temporary one of
+ * initialize_team_classifier) and steps it once per frame with update_with_detections (:228, :265).  One tracker object
+ * holds the state of n_clips independent clips (tracking is sequential per clip, clips are independent).
+ *   track_activation_threshold, minimum_matching_threshold, minimum_consecutive_frames: the constructor arguments;
+ *   det_threshold = track_activation_threshold + 0.1 and max_time_lost = int(frame_rate / 30 * lost_track_buffer),
+ *   both evaluated by the caller in double / Python arithmetic exactly like supervision does.
+ * hvb_bytetrack_update consumes the detector's per-image outputs in K2a's layout (xyxy [images, max_det, 4], conf and
+ * cls [images, max_det], count [images]; image of (clip c, frame f) = c * clip_stride + f * frame_stride) for n_frames
+ * consecutive frames of every clip in ONE launch.  A detection enters the tracker iff conf > min_conf and bit cls of
+ * class_mask is set (the mask of main.py:189-193; cls_dev may be NULL when class_mask is all ones).  Per image it
+ * writes the detections supervision's `detections[tracker_id != -1]` keeps, in detection order: their row index
+ * (out_row [images, max_det]), tracker id (out_tid) and number (out_count [images]).  out_count = -1: a capacity was
+ * exceeded (256 live tracks per clip, 320 detections per frame; sticky until hvb_bytetrack_reset); -2: the chunk was
+ * rejected and the clip's state NOT advanced — either one of the clip's input counts was negative (K2a candidate overflow
+ * pending a retry) or `seq` is not the sequence number the clip expects next (0, 1, 2, ... since create / reset: a chunk
+ * queued behind a rejected one); resubmit rejected chunks in order with their own seq.  Stream-ordered on the context's
+ * stream, no host synchronisation.
+ */
+typedef struct hvb_bytetrack hvb_bytetrack;
+HVB_API int hvb_bytetrack_create(hvb_ctx* ctx, int n_clips, double track_activation_threshold, double det_threshold,
+                         double minimum_matching_threshold, int max_time_lost, int minimum_consecutive_frames,
+                         hvb_bytetrack** out_tracker);
+HVB_API int hvb_bytetrack_destroy(hvb_ctx* ctx, hvb_bytetrack* tracker);
+HVB_API int hvb_bytetrack_reset(hvb_ctx* ctx, hvb_bytetrack* tracker);
+HVB_API int hvb_bytetrack_update(hvb_ctx* ctx, hvb_bytetrack* tracker, const float* xyxy_dev, const float* conf_dev,
+                         const int32_t* cls_dev /*or NULL*/, const int32_t* count_dev, int n_frames, int max_det,
+                         int64_t clip_stride, int64_t frame_stride, float min_conf, uint32_t class_mask, int seq,
+                         int32_t* out_row_dev, int32_t* out_tid_dev, int32_t* out_count_dev);
+
 /* ---------------------------------------------------------------- host-buffer entry points
  * What a non-Python binding (cgo / JNI / N-API) would call: host in, host out, synchronous.
  * They stage through context-owned pinned + device scratch and run the same kernels. */

@@ -77,11 +77,12 @@ def _same(got, ref):
     assert got.labels == ref.labels
 
 
-def test_process_video_matches_the_reference_drivers(ctx, clip, reference, capsys):
+@pytest.mark.parametrize("tracker", ["device", "host"])
+def test_process_video_matches_the_reference_drivers(ctx, clip, reference, capsys, tracker):
     from hvb import Config, VideoProcessor
     frames, table = clip
     trunk, ref, ref_out = reference
-    vp = VideoProcessor(PlantedModel(table), "cuda:0", Config(), trunk=trunk)
+    vp = VideoProcessor(PlantedModel(table), "cuda:0", Config(), trunk=trunk, tracker=tracker)
     out = list(vp.process_video(list(frames)))
     assert "Classifier fitted." in capsys.readouterr().out
     assert len(out) == len(ref_out) == len(frames)
@@ -94,14 +95,78 @@ def test_process_video_matches_the_reference_drivers(ctx, clip, reference, capsy
     assert any("Goalie" in r.labels for r in ref_out) and any(len(r.player_team_ids) for r in ref_out)
 
 
-def test_chunked_fast_path_equals_frame_at_a_time(ctx, clip, reference):
+@pytest.mark.parametrize("tracker", ["device", "host"])
+def test_chunked_fast_path_equals_frame_at_a_time(ctx, clip, reference, tracker):
     from hvb import Config, VideoProcessor
     frames, table = clip
     trunk, _, ref_out = reference
-    vp = VideoProcessor(PlantedModel(table), "cuda:0", Config(), trunk=trunk)
+    vp = VideoProcessor(PlantedModel(table), "cuda:0", Config(), trunk=trunk, tracker=tracker)
     before = ctx.launch_count()
     out = list(vp.process_video_chunked(list(frames), chunk=16))
     assert ctx.launch_count() > before
     assert len(out) == len(frames)
     for g, r in zip(out, ref_out):
+        _same(g, r)
+
+
+def test_overlay_on_a_real_forward_equals_the_reference_drivers(ctx):
+    """The benchmark's step (bench.py): a REAL random-init YOLOv8 forward whose head tensors get planted detections
+    scattered in on the device (hvb.synth.PlantedOverlay / DeviceOverlay, Detector.head_hook), then K2a -> K7 -> team
+    stage through VideoProcessor.process_chunks on device-resident chunks — against the reference drivers on the CPU with
+    the same overlay applied to the CPU forward's heads.  The planted anchors carry identical values on both sides and
+    the random-init background stays far below conf, so detections, tracker ids and team ids must agree."""
+    import copy
+    from hvb import Config, VideoProcessor
+    from hvb.models import build_trunk, build_yolov8
+    from hvb.models.yolov8 import fuse_conv_bn
+    from hvb.synth import PlantedOverlay, rink_clip
+    from oracle.video_reference import VideoReference
+    h, w, imgsz, n_pl, n_frames, chunk = 720, 1280, 640, 9, 24, 8
+    frames, boxes, _, _ = rink_clip(11, n_frames, h, w, n_pl)
+    cls = [np.array([0] * (n_pl - 1) + [1])] * n_frames
+    ov = PlantedOverlay.whole_frame(5, (h, w), imgsz, boxes, cls, nc=2, dup=3)
+    model = build_yolov8("n", 2, 0)
+    trunk = build_trunk(0, calibrate=True)
+    cpu_model = fuse_conv_bn(copy.deepcopy(model)).eval()
+    state = {"f": 0}
+
+    def heads_fn(x):
+        with torch.no_grad():
+            heads = [t.clone() for t in cpu_model(x)]
+        ov.apply_host(heads, state["f"])
+        return heads
+
+    ref = VideoReference(heads_fn, 2, trunk, imgsz=imgsz, conf=0.4)
+    # fit both sides on the same crops: the players of frames 0, 10, 20 as the reference's initialisation samples them
+    ref_out = []
+    init_ids = [k for k in range(n_frames) if k % 10 == 0]
+
+    class Seq:                                                     # frames with the cursor the CPU heads_fn needs
+        def __iter__(self_inner):
+            for k, f in enumerate(frames):
+                state["f"] = k
+                yield f
+    ref.initialize_team_classifier(Seq())
+    for k, f in enumerate(frames):
+        state["f"] = k
+        ref_out.append(ref.process_frame(f))
+
+    cfg = Config(detection_imgsz=imgsz)
+    vp = VideoProcessor(model, "cuda:0", cfg, trunk=trunk, detector_kwargs=dict(cuda_graph=False))
+    vp.detector.head_hook = ov.to_device("cuda:0", [[k] for k in init_ids])
+    vp.initialize_team_classifier(list(frames))
+    assert vp.team_classifier.hybrid_classifier.scaler.n_samples_seen_ == ref.n_fit_crops == len(init_ids) * (n_pl - 1)
+    vp.detector.head_hook = ov.to_device("cuda:0", [list(range(lo, lo + chunk)) for lo in range(0, n_frames, chunk)])
+    dev_chunks = [torch.from_numpy(frames[lo:lo + chunk]).cuda() for lo in range(0, n_frames, chunk)]
+    out = list(vp.process_chunks(dev_chunks))
+    assert len(out) == n_frames
+    for g, r in zip(out, ref_out):
+        _same(g, r)
+    assert max(len(r.detections) for r in ref_out) == n_pl and sum(len(r.player_team_ids) for r in ref_out) > 100
+    # the same through the host-frame API with CUDA graphs (the default of the drop-in) and the host tracker
+    vp2 = VideoProcessor(model, "cuda:0", cfg, team_classifier=vp.team_classifier, tracker="host")
+    vp2.team_classifier.hybrid_classifier.player_history.clear()
+    vp2.detector.head_hook = ov.to_device("cuda:0", [list(range(lo, lo + chunk)) for lo in range(0, n_frames, chunk)])
+    out2 = list(vp2.process_video_chunked(list(frames), chunk=chunk, initialize=False))
+    for g, r in zip(out2, ref_out):
         _same(g, r)

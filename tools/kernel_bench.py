@@ -187,6 +187,26 @@ def main():
         print(json.dumps({"kernel": "ByteTrack 8 clips x 40 detections, host logic + K4b costs", "ms_per_frame_independent": round(1e3 * t_single, 3),
                           "ms_per_frame_lockstep_batched_k4b": round(1e3 * t_multi, 3),
                           "clip_frames_per_s_lockstep": round(n_clips / t_multi, 1)}), flush=True)
+        # K7: the same clips through the device tracker — chunks of 32 frames of all 8 clips per launch, and (second line)
+        # the drop-in's shape: ONE clip, 12 detections per frame, 64-frame chunks
+        from hvb.tracker import DeviceByteTrack
+        for tag, nc_, nobj, ch in (("8 clips x 40 detections, 30-frame chunks", n_clips, n_obj, 30), ("1 clip x 12 detections, 60-frame chunks", 1, 12, 60)):
+            trk = DeviceByteTrack(n_clips=nc_, **kw)
+            md = 64
+            packs = []
+            for f0 in range(0, n_frames, ch):
+                xy = np.zeros((nc_ * ch, md, 4), np.float32); cf = np.zeros((nc_ * ch, md), np.float32); cnt = np.zeros(nc_ * ch, np.int32)
+                for c in range(nc_):
+                    for f in range(ch):
+                        xy[c * ch + f, :nobj], cf[c * ch + f, :nobj], cnt[c * ch + f] = clips[c][f0 + f][0][:nobj], clips[c][f0 + f][1][:nobj], nobj
+                packs.append([torch.from_numpy(a).cuda() for a in (xy, cf, cnt)])
+            def run():
+                for xy, cf, cnt in packs:
+                    trk.update_chunk_device(xy, cf, None, cnt)
+            ms = timed(run, max(R // 4, 1) if R > 0 else 0)
+            print(json.dumps({"kernel": "K7 device ByteTrack, " + tag, "us_per_launch": round(1e3 * ms / len(packs), 1),
+                              "us_per_frame_step": round(1e3 * ms / n_frames, 2),
+                              "clip_frames_per_s": round(nc_ * n_frames / (ms / 1e3), 1)}), flush=True)
 
     def sec_k5():
         # K5 backbone glue at the YOLOv8m / 1080p (736x1280 input) layer sizes, 32 frames per launch
