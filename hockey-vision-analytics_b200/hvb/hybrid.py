@@ -47,6 +47,45 @@ class _Scaler:
         return (np.asarray(x, np.float64) - self.mean_) / self.scale_
 
 
+class _TrunkGraph:
+    """Static input / output buffers + the captured forward of the MobileNetV3 trunk at one bucketed batch size.
+    begin() -> the static input (K3b writes it), replay() -> the static output, end() marks both free again; an event
+    orders reuse across streams (the chunk pipeline runs the team stage on its own stream)."""
+    EAGER_CALLS = 2
+
+    def __init__(self, clf: "HybridTeamClassifier", rows: int):
+        self.clf, self.rows, self.calls = clf, rows, 0
+        self.graph = self.x = self.y = self.free = None
+
+    def ready(self) -> bool:
+        if self.graph is not None:
+            return True
+        self.calls += 1
+        if self.calls <= self.EAGER_CALLS:
+            return False
+        dev = self.clf.ctx.device
+        self.x = torch.zeros((self.rows, 3, 128, 64), dtype=torch.float32, device=dev)
+        g = torch.cuda.CUDAGraph()
+        # thread_local: the chunk pipeline's staging thread allocates pinned memory / issues copies while this captures
+        with torch.cuda.graph(g, capture_error_mode="thread_local"):
+            self.y = self.clf._trunk_forward(self.x)
+        self.graph = g
+        return True
+
+    def begin(self) -> torch.Tensor:
+        if self.free is not None:
+            torch.cuda.current_stream(self.x.device).wait_event(self.free)
+        return self.x
+
+    def replay(self) -> torch.Tensor:
+        self.graph.replay()
+        return self.y
+
+    def end(self) -> None:
+        self.free = torch.cuda.Event()
+        self.free.record(torch.cuda.current_stream(self.x.device))
+
+
 class HybridTeamClassifier:
     def __init__(self, device: str = "cuda:0", n_clusters: int = 2, trunk: Optional[torch.nn.Module] = None,
                  seed: int = 0, affinity_mode: int = 0, fold_batchnorm: bool = True, spectral: str = "sklearn",
@@ -73,6 +112,9 @@ class HybridTeamClassifier:
         self.affinity_mode = affinity_mode      # 0 = tcgen05 Gram + fp64 refine, 1 = fp64 only
         self.spectral = spectral                # "device": dense eigensolver on the GPU (hvb/spectral.py), opt-in
         self.affinity_gamma = affinity_gamma    # 1.0 = the reference; "scale" = 1 / n_features (does not underflow), opt-in
+        import os
+        self.graph_trunk = os.environ.get("HVB_TRUNK_GRAPH", "1") != "0"      # replay the trunk forward as a CUDA graph per bucket size
+        self._trunk_graphs: Dict[int, _TrunkGraph] = {}
 
     # ------------------------------------------------------------------ geometry (host, O(1))
     def extract_jersey_region(self, crop: np.ndarray) -> np.ndarray:
@@ -116,13 +158,27 @@ class HybridTeamClassifier:
         # the 32-frame drop-in fell to 42 frames/s).  The trunk therefore only ever sees a few bucketed batch sizes: K3b
         # writes the first n rows of a bucket-sized tensor, the padding rows are zero and their outputs are dropped.
         nb = self._bucket(n)
+        tg = self._trunk_graph(nb)
         with nvtx("hvb:K3b crop preprocessing"):
-            x, valid = ctx.mnv3_preprocess(pixels, crops_dev, n, _ffi.ROI_HYBRID, rows=nb)
+            x, valid = ctx.mnv3_preprocess(pixels, crops_dev, n, _ffi.ROI_HYBRID, rows=nb, out=tg.begin() if tg else None)
         with nvtx("hvb:mobilenetv3 trunk"):
-            deep = self._trunk_forward(x)[:n]
+            deep = (tg.replay() if tg else self._trunk_forward(x))[:n]
         deep = deep * (valid == 1).to(deep.dtype).unsqueeze(1)       # failed preprocessing -> zeros(576)
         feats[:, :N_DEEP] = deep.to(torch.float64)
+        if tg:
+            tg.end()
         return feats, raw, valid
+
+    def _trunk_graph(self, rows: int):
+        """The trunk forward at bucket size `rows` as ONE CUDA-graph replay (frame-at-a-time calls are launch-bound: the
+        ~150 launches of the eager MobileNetV3 forward took 1.72 ms of host time for 11 crops on the B200 box,
+        tools/probe_e2e4k.py).  The first two calls at a bucket size run eagerly (cuDNN autotuning); the third captures."""
+        if not self.graph_trunk:
+            return None
+        g = self._trunk_graphs.get(rows)
+        if g is None:
+            self._trunk_graphs[rows] = g = _TrunkGraph(self, rows)
+        return g if g.ready() else None
 
     @staticmethod
     def _bucket(n: int) -> int:
@@ -252,15 +308,19 @@ class HybridTeamClassifier:
 
     def _predict_device(self, pixels, cd, n, tracker_ids):
         feats, raw, _ = self._features_device(pixels, cd, n, want_raw=self.clusterer is None)
-        self._raise_on_empty(feats[:, N_DEEP])
         if self.clusterer is None:
+            self._raise_on_empty(feats[:, N_DEEP])
             r = raw.cpu().numpy().view(_ffi.COLOR_RAW)[:n]
             sat = r["sums"][:, 1].astype(np.float64) / r["n"]
             white = r["counts"][:, 2].astype(np.float64) / r["n"]
             pred = np.where((white > 0.25) | (sat < 40), 0, 1)          # _simple_classify, :282-306
         else:
             xs = self.ctx.scale_transform(feats, self.scaler._mean_dev, self.scaler._scale_dev)
-            tail = xs[:, -10:].cpu().numpy()                             # only the entries the rule reads
+            # one device -> host read: the entries the rule reads + the first colour feature (NaN = empty jersey region)
+            tail = torch.cat([xs[:, -10:], feats[:, N_DEEP:N_DEEP + 1]], 1).cpu().numpy()
+            if np.isnan(tail[:, 10]).any():
+                raise ValueError("empty jersey region in extract_color_features")
+            tail = tail[:, :10]
             pred = np.array([0 if (t[-1] > 0.3 or np.argmax(t[0:3]) == 0) else 1 for t in tail])
         if tracker_ids is not None:
             pred = self._apply_temporal_consistency(pred, tracker_ids)

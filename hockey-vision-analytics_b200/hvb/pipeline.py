@@ -22,6 +22,18 @@ from .runtime import get_context
 from .slicer import B200InferenceSlicer
 
 
+def _stream_state(owner, dev):
+    """The staging state of a process_stream pipeline, kept on its owner between calls: the copy stream, the two device
+    frame buffers (+ the events that guard their reuse) and the three sets of pinned result buffers.  Measured on the
+    B200 box (tools/probe_e2e4k.py): creating them per call — cudaHostAlloc of the result buffers, cudaMalloc of 2 x 400 MB
+    under a fresh stream — cost ~90 ms, more than three 4K chunks."""
+    st = getattr(owner, "_stream_state_", None)
+    if st is None or st[0] != str(dev):
+        st = (str(dev), torch.cuda.Stream(device=dev), [None, None], [None, None], [dict(), dict(), dict()])
+        owner._stream_state_ = st
+    return st[1:]
+
+
 class HotPath:
     def __init__(self, device="cuda:0", yolo_scale: str = "m", nc: int = 2, imgsz: int = 1280, conf: float = 0.4,
                  seed: int = 0, trunk: Optional[torch.nn.Module] = None, affinity_mode: int = 0, fuse: bool = True,
@@ -154,10 +166,8 @@ class HotPath:
         D2H into pinned buffers + an event).  The host only ever blocks on the *previous* chunk, so the GPU
         always has the next chunk's work queued behind the current one."""
         dev = self.ctx.device
-        copy_stream = torch.cuda.Stream(device=dev)
         main = torch.cuda.current_stream(dev)
-        bufs, free_ev = [None, None], [None, None]
-        pinned_out = [dict(), dict(), dict()]
+        copy_stream, bufs, free_ev, pinned_out = _stream_state(self, dev)
 
         def stage(i, item):
             frames, tb, ti = item
@@ -259,10 +269,8 @@ class SlicedPuckPath:
         results (asynchronous D2H into pinned buffers + an event)."""
         det = self.detector
         dev = det.ctx.device
-        copy_stream = torch.cuda.Stream(device=dev)
         main = torch.cuda.current_stream(dev)
-        bufs, free_ev = [None, None], [None, None]
-        pinned_out = [dict(), dict(), dict()]
+        copy_stream, bufs, free_ev, pinned_out = _stream_state(self, dev)
         names = ("xyxy", "conf", "cls", "keep", "seg", "count")
 
         def stage(i, frames):

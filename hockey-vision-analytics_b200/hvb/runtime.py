@@ -277,12 +277,17 @@ class Context:
         return hsv, lab
 
     def mnv3_preprocess(self, pixels: torch.Tensor, crops: torch.Tensor, n: int, roi_mode: int = _ffi.ROI_HYBRID,
-                        want_u8: bool = False, rows: Optional[int] = None):
+                        want_u8: bool = False, rows: Optional[int] = None, out: Optional[torch.Tensor] = None):
         """`rows` >= n: allocate that many output rows (the kernel fills the first n, the rest are zero) so that the
-        backbone behind it can run at a bucketed batch size."""
+        backbone behind it can run at a bucketed batch size.  `out`: write into this float32[rows >= n, 3, 128, 64]
+        tensor instead (the static input of a captured trunk graph); its rows beyond n are zeroed."""
         with self.lock:
             self._enter()
-            if rows is not None and rows > n:
+            if out is not None:
+                assert out.dtype == torch.float32 and out.is_contiguous() and tuple(out.shape[1:]) == (3, 128, 64) and out.shape[0] >= n
+                if out.shape[0] > n:
+                    out[n:].zero_()
+            elif rows is not None and rows > n:
                 out = self.empty((rows, 3, 128, 64), torch.float32)
                 out[n:].zero_()
             else:
