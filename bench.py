@@ -309,6 +309,32 @@ def run_hvb(args, rank, world):
         t3 = time.perf_counter()
         fit[tag] = {"features_ms": 1e3 * (t1 - t0), "all_gather_ms": 1e3 * (t2 - t1), "standardise+affinity_ms": 1e3 * (t3 - t2),
                     "total_ms": 1e3 * (t3 - t0), "rows": int(feats.shape[0])}
+    # the same exchange through the C ABI's own entry points (hvb_allgather_counts / hvb_allgather_features), and the opt-in
+    # device clustering (K8: subspace iteration + Lloyd runs) on the gathered rows at the non-underflowing bandwidth
+    if world > 1:
+        from hvb.dist import all_gather_features
+        local = path.classifier.features_from_frame(fwd_dev, sk_dev, skf_dev)[0]
+        for _ in range(2):
+            g2 = all_gather_features(local, backend="hvb")
+        torch.cuda.synchronize()
+        barrier()
+        t0 = time.perf_counter()
+        g2 = all_gather_features(local, backend="hvb")
+        torch.cuda.synchronize()
+        fit["warm"]["all_gather_c_abi_ms"] = 1e3 * (time.perf_counter() - t0)
+        fit["warm"]["all_gather_c_abi_equals_torch"] = bool(torch.equal(g2, feats))
+    from hvb.spectral import DeviceSpectralClustering
+    xs = path.classifier.features_normalized_
+    _, aff = ctx.gram_affinity(xs, 1.0 / xs.shape[1], 0, want_d2=False, want_a=True)
+    for _ in range(2):
+        sc = DeviceSpectralClustering(2, 10, 42)
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        lab = sc.fit_predict(aff)
+        fit["warm"]["device_spectral_clustering_ms (gamma = 1/625)"] = 1e3 * (time.perf_counter() - t0)
+    fit["warm"]["device_spectral_outer_rounds"] = int(sc.info_.get("outer_iterations", 0))
+    fit["warm"]["device_spectral_cluster_sizes"] = [int((lab == 0).sum()), int((lab == 1).sum())]
+    del aff
 
     vp = VideoProcessor(device=dev, config=Config(), detector=det, team_classifier=path.classifier_router(), tracker=args.tracker)
     det.head_hook = hook_chunks

@@ -106,6 +106,19 @@ PROTOTYPES = {
     "hvb_bytetrack_destroy": [_vp, _vp],
     "hvb_bytetrack_reset": [_vp, _vp],
     "hvb_bytetrack_update": [_vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i64, _i64, _f, C.c_uint32, _i, _vp, _vp, _vp],
+    "hvb_spectral_block": [C.POINTER(_i)],
+    "hvb_laplacian_normalize": [_vp, _vp, _i, _vp, _vp],
+    "hvb_sym_block_matvec": [_vp, _vp, _i, _vp, _d, _vp],
+    "hvb_block_gram": [_vp, _vp, _vp, _i, _i, _vp],
+    "hvb_block_rotate": [_vp, _vp, _vp, _i, _vp, _vp, _vp],
+    "hvb_kmeans_lloyd": [_vp, _vp, _i, _i, _i, _vp, _i, _i, _d, _vp, _vp, _vp, _vp, _vp],
+    "hvb_comm_unique_id": [_vp],
+    "hvb_comm_create": [_vp, _vp, _i, _i, _pp],
+    "hvb_comm_wrap": [_vp, _vp, _pp],
+    "hvb_comm_destroy": [_vp, _vp],
+    "hvb_comm_info": [_vp, C.POINTER(_i), C.POINTER(_i)],
+    "hvb_allgather_counts": [_vp, _vp, _i, _vp, C.POINTER(_i64)],
+    "hvb_allgather_features": [_vp, _vp, _vp, _i, _i, _vp, _vp],
     "hvb_color_features_host": [_vp, _vp, _sz, _vp, _i, _i, _vp, _vp],
     "hvb_jersey_color_stats": [_vp, _vp, _vp, _i, _i, _vp],
     "hvb_jersey_color_stats_host": [_vp, _vp, _sz, _vp, _i, _i, _vp],

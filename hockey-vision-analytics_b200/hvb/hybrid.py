@@ -51,25 +51,42 @@ class _TrunkGraph:
     """Static input / output buffers + the captured forward of the MobileNetV3 trunk at one bucketed batch size.
     begin() -> the static input (K3b writes it), replay() -> the static output, end() marks both free again; an event
     orders reuse across streams (the chunk pipeline runs the team stage on its own stream)."""
-    EAGER_CALLS = 2
 
     def __init__(self, clf: "HybridTeamClassifier", rows: int):
-        self.clf, self.rows, self.calls = clf, rows, 0
+        self.clf, self.rows = clf, rows
         self.graph = self.x = self.y = self.free = None
+        self.failed = False
 
     def ready(self) -> bool:
+        """Captured on the first use of a bucket size: one eager forward first (cuDNN autotuning for this batch size), then
+        the capture, both on a side stream.  Begun / ended by hand instead of `with torch.cuda.graph(...)`: that context
+        manager synchronises the device and empties the caching allocator on entry, which made every later eager forward
+        of the process re-cudaMalloc its activations (measured: the eager frame-at-a-time loop fell from 190 to 96
+        frames/s).  thread_local: the chunk pipeline's staging thread allocates and copies while this captures."""
         if self.graph is not None:
             return True
-        self.calls += 1
-        if self.calls <= self.EAGER_CALLS:
+        if self.failed:
             return False
         dev = self.clf.ctx.device
-        self.x = torch.zeros((self.rows, 3, 128, 64), dtype=torch.float32, device=dev)
+        cur = torch.cuda.current_stream(dev)
+        x = torch.zeros((self.rows, 3, 128, 64), dtype=torch.float32, device=dev)
+        side = torch.cuda.Stream(device=dev)
+        side.wait_stream(cur)
         g = torch.cuda.CUDAGraph()
-        # thread_local: the chunk pipeline's staging thread allocates pinned memory / issues copies while this captures
-        with torch.cuda.graph(g, capture_error_mode="thread_local"):
-            self.y = self.clf._trunk_forward(self.x)
-        self.graph = g
+        try:
+            with torch.cuda.stream(side):
+                self.clf._trunk_forward(x)
+                g.capture_begin(capture_error_mode="thread_local")
+                try:
+                    y = self.clf._trunk_forward(x)
+                finally:
+                    g.capture_end()
+        except RuntimeError:
+            self.failed = True                 # e.g. a capture already in progress on this thread: stay on the eager forward
+            return False
+        cur.wait_stream(side)
+        x.record_stream(cur)
+        self.graph, self.x, self.y = g, x, y
         return True
 
     def begin(self) -> torch.Tensor:
@@ -172,7 +189,7 @@ class HybridTeamClassifier:
     def _trunk_graph(self, rows: int):
         """The trunk forward at bucket size `rows` as ONE CUDA-graph replay (frame-at-a-time calls are launch-bound: the
         ~150 launches of the eager MobileNetV3 forward took 1.72 ms of host time for 11 crops on the B200 box,
-        tools/probe_e2e4k.py).  The first two calls at a bucket size run eagerly (cuDNN autotuning); the third captures."""
+        tools/probe_e2e4k.py; the replay 0.3 ms).  Captured on the first call at a bucket size."""
         if not self.graph_trunk:
             return None
         g = self._trunk_graphs.get(rows)

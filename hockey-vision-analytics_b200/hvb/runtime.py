@@ -379,6 +379,94 @@ class Context:
                                                 ptr(row), ptr(tid), ptr(cnt)))
         return row, tid, cnt
 
+    # ------------------------------------------------------------------ K8 (device spectral clustering pieces)
+    def laplacian_normalize(self, a: torch.Tensor):
+        """float64[n,n] affinity -> (M = D^-1/2 A0 D^-1/2 float64[n,n], dd = sqrt(degree) float64[n])."""
+        n = a.shape[0]
+        a = a.contiguous()
+        with self.lock:
+            self._enter()
+            m = self.empty((n, n), torch.float64)
+            dd = self.empty((n,), torch.float64)
+            check(self.lib.hvb_laplacian_normalize(self.handle, ptr(a), n, ptr(m), ptr(dd)))
+        return m, dd
+
+    def sym_block_matvec(self, m: torch.Tensor, x: torch.Tensor, shift: float = 0.0, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+        """Y = (M + shift I) X for x float64[8, n] (each vector contiguous)."""
+        n = m.shape[0]
+        with self.lock:
+            self._enter()
+            y = out if out is not None else self.empty((8, n), torch.float64)
+            check(self.lib.hvb_sym_block_matvec(self.handle, ptr(m), n, ptr(x), float(shift), ptr(y)))
+        return y
+
+    def block_gram(self, a: torch.Tensor, b: torch.Tensor, mode: int = 0) -> torch.Tensor:
+        """mode 0: float64[65] with [:64] = A^T B (8 x 8 row-major); mode 1: [:64] = R^-1 of A^T A = R^T R, [64] = not-PD flag."""
+        with self.lock:
+            self._enter()
+            out = self.empty((65,), torch.float64)
+            check(self.lib.hvb_block_gram(self.handle, ptr(a), ptr(b), a.shape[1], mode, ptr(out)))
+        return out
+
+    def block_rotate(self, x: torch.Tensor, y: Optional[torch.Tensor], q: torch.Tensor, lam: Optional[torch.Tensor] = None):
+        """In place: X <- X Q, Y <- Y Q (q float64[8,8] on the device); with lam float64[8]: returns |Y q_j - lam_j X q_j|^2."""
+        with self.lock:
+            self._enter()
+            res = self.empty((8,), torch.float64) if lam is not None else None
+            check(self.lib.hvb_block_rotate(self.handle, ptr(x), ptr(y), x.shape[1], ptr(q), ptr(lam), ptr(res)))
+        return res
+
+    def kmeans_lloyd(self, x: torch.Tensor, init_centers: torch.Tensor, max_iter: int, tol: float):
+        """x float64[n,d] (mean-centred), init_centers float64[n_init,k,d] -> labels i32[n_init,n], centres, inertia,
+        n_iter, flags — every initialisation in one launch."""
+        n, d = x.shape
+        n_init, k, _ = init_centers.shape
+        x, init_centers = x.contiguous(), init_centers.contiguous()
+        with self.lock:
+            self._enter()
+            labels = self.empty((n_init, n), torch.int32)
+            centers = self.empty((n_init, k, d), torch.float64)
+            inertia = self.empty((n_init,), torch.float64)
+            n_iter = self.empty((n_init,), torch.int32)
+            flags = self.empty((n_init,), torch.int32)
+            check(self.lib.hvb_kmeans_lloyd(self.handle, ptr(x), n, d, k, ptr(init_centers), n_init, int(max_iter), float(tol),
+                                            ptr(labels), ptr(centers), ptr(inertia), ptr(n_iter), ptr(flags)))
+        return labels, centers, inertia, n_iter, flags
+
+    # ------------------------------------------------------------------ feature exchange (NCCL bound inside libhvb)
+    def comm_unique_id(self) -> bytes:
+        buf = (C.c_uint8 * 128)()
+        check(self.lib.hvb_comm_unique_id(C.cast(buf, C.c_void_p)))
+        return bytes(buf)
+
+    def comm_create(self, unique_id: bytes, world: int, rank: int) -> C.c_void_p:
+        """Collective over all ranks: ncclCommInitRank on this context's device."""
+        h = C.c_void_p()
+        buf = (C.c_uint8 * 128).from_buffer_copy(unique_id)
+        with self.lock:
+            check(self.lib.hvb_comm_create(self.handle, C.cast(buf, C.c_void_p), int(world), int(rank), C.byref(h)))
+        return h
+
+    def comm_destroy(self, comm) -> None:
+        with self.lock:
+            check(self.lib.hvb_comm_destroy(self.handle, comm))
+
+    def allgather_features(self, comm, local: torch.Tensor, world: int) -> Tuple[torch.Tensor, np.ndarray]:
+        """local float64[n_g, d] on this device -> (float64[sum n_g, d] in rank order, the per-rank row counts)."""
+        if local.dtype != torch.float64 or local.dim() != 2:
+            raise ValueError("expected a float64 [n, d] tensor")
+        local = local.contiguous()
+        n, d = local.shape
+        counts = np.zeros((world,), np.int32)
+        total = C.c_int64()
+        with self.lock:
+            self._enter()
+            check(self.lib.hvb_allgather_counts(self.handle, comm, n, ptr(counts), C.byref(total)))
+            out = self.empty((int(total.value), d), torch.float64)
+            if total.value:
+                check(self.lib.hvb_allgather_features(self.handle, comm, ptr(local) if n else None, n, d, ptr(counts), ptr(out)))
+        return out, counts
+
     # ------------------------------------------------------------------ K5 (backbone glue; NHWC float32)
     ACT = {"none": 0, "silu": 1, "relu": 2, "hardswish": 3, "silu_fast": 4}
 

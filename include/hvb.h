@@ -385,6 +385,53 @@ HVB_API int hvb_bytetrack_update(hvb_ctx* ctx, hvb_bytetrack* tracker, const flo
                          int64_t clip_stride, int64_t frame_stride, float min_conf, uint32_t class_mask, int seq,
                          int32_t* out_row_dev, int32_t* out_tid_dev, int32_t* out_count_dev);
 
+/* ---------------------------------------------------------------- K8: device spectral clustering (opt-in)
+ * What SpectralClustering(affinity='precomputed', n_init=10, random_state=42).fit_predict does with K4a's affinity in
+ * HybridTeamClassifier.fit (hockey/common/team_hybrid.py:185-193): sklearn.manifold.spectral_embedding(norm_laplacian=True,
+ * drop_first=False) then KMeans on the N x k embedding.  SURVEY.md §8f rank 3; opt-in because the solver differs from
+ * the reference's ARPACK / LOBPCG.  All float64; vectors come in blocks of hvb_spectral_block() = 8, stored [8][n].
+ *   hvb_laplacian_normalize  scipy csgraph.laplacian(normed=True) pieces: dd = sqrt(column sums of A with a zero diagonal)
+ *                            (1 for isolated nodes), M = D^-1/2 A0 D^-1/2 (L = I - M)
+ *   hvb_sym_block_matvec     Y = (M + shift I) X — the one pass over the N x N matrix of a subspace-iteration step
+ *   hvb_block_gram           mode 0: out[64] = A^T B;  mode 1 (a == b): out[0..63] = R^-1 with A^T A = R^T R (Cholesky QR),
+ *                            out[64] = 1.0 when A^T A was not positive definite
+ *   hvb_block_rotate         X <- X Q (and Y <- Y Q); with lambda: out_res[8] = |Y q_j - lambda_j X q_j|^2
+ *   hvb_kmeans_lloyd         sklearn _kmeans_single_lloyd for n_init initialisations in one launch (one CTA each) on the
+ *                            mean-centred x [n][d]: labels [n_init][n], centres [n_init][k][d], inertia, iterations, flags
+ *                            (1 = a cluster went empty: the caller redoes that fit with sklearn's relocation); k, d <= 8 */
+HVB_API int hvb_spectral_block(int* out_block);
+HVB_API int hvb_laplacian_normalize(hvb_ctx* ctx, const double* a_dev, int n, double* m_dev, double* dd_dev);
+HVB_API int hvb_sym_block_matvec(hvb_ctx* ctx, const double* m_dev, int n, const double* x_dev, double shift, double* y_dev);
+HVB_API int hvb_block_gram(hvb_ctx* ctx, const double* a_dev, const double* b_dev, int n, int mode, double* out_dev /*[65]*/);
+HVB_API int hvb_block_rotate(hvb_ctx* ctx, double* x_dev, double* y_dev /*or NULL*/, int n, const double* q_dev /*[8][8]*/,
+                     const double* lambda_dev /*[8] or NULL*/, double* out_res_dev /*[8] or NULL*/);
+HVB_API int hvb_kmeans_lloyd(hvb_ctx* ctx, const double* x_dev, int n, int d, int k, const double* init_centers_dev, int n_init,
+                     int max_iter, double tol, int32_t* out_labels_dev, double* out_centers_dev, double* out_inertia_dev,
+                     int32_t* out_n_iter_dev, int32_t* out_flags_dev);
+
+/* ---------------------------------------------------------------- feature exchange for the global team fit
+ * SURVEY.md §8b `hvb_allgather_features` / §8e: the one collective on the path.  Before HybridTeamClassifier.fit
+ * (hockey/common/team_hybrid.py:155-196) standardises the crop features, every rank needs the float64[n_g, 625] rows of
+ * all ranks in rank order, bit-identical.  NCCL is bound at run time (dlopen libnccl.so.2, or $HVB_NCCL_LIB): without it
+ * these calls return HVB_ERR_UNSUPPORTED and nothing else in the library is affected.
+ *   hvb_comm_unique_id  rank 0 makes the 128-byte id; the host ships it to the other ranks over its own channel
+ *   hvb_comm_create     collective: ncclCommInitRank on the context's device
+ *   hvb_comm_wrap       adopt a communicator the host already owns (ncclComm_t); not destroyed by hvb_comm_destroy
+ *   hvb_allgather_counts    phase 1, synchronises: every rank's row count (the host sizes out_dev from them)
+ *   hvb_allgather_features  phase 2, stream-ordered: an all-gather-v (one ncclGroup of per-rank broadcasts straight into
+ *                           the compacted output, no padding pass); out_dev: float64[sum counts, d] */
+#define HVB_COMM_ID_BYTES 128
+typedef struct hvb_comm hvb_comm;
+HVB_API int hvb_comm_unique_id(uint8_t* out_id128);
+HVB_API int hvb_comm_create(hvb_ctx* ctx, const uint8_t* id128, int world, int rank, hvb_comm** out_comm);
+HVB_API int hvb_comm_wrap(hvb_ctx* ctx, void* nccl_comm, hvb_comm** out_comm);
+HVB_API int hvb_comm_destroy(hvb_ctx* ctx, hvb_comm* comm);
+HVB_API int hvb_comm_info(hvb_comm* comm, int* out_world, int* out_rank);
+HVB_API int hvb_allgather_counts(hvb_ctx* ctx, hvb_comm* comm, int n_local, int32_t* out_counts_host /*[world]*/,
+                         int64_t* out_total /*or NULL*/);
+HVB_API int hvb_allgather_features(hvb_ctx* ctx, hvb_comm* comm, const double* local_dev, int n_local, int d,
+                           const int32_t* counts_host /*[world]*/, double* out_dev);
+
 /* ---------------------------------------------------------------- host-buffer entry points
  * What a non-Python binding (cgo / JNI / N-API) would call: host in, host out, synchronous.
  * They stage through context-owned pinned + device scratch and run the same kernels. */

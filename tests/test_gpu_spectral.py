@@ -79,3 +79,81 @@ def test_gathered_fit_size(ctx):
     assert np.array_equal(lab, which) or np.array_equal(lab, 1 - which)
     print("fit_features N=2000 with the device solver: %.3f s" % dt)
     assert dt < 5.0
+
+
+# ---------------------------------------------------------------- K8 kernels against their numpy twin (tests/spectral_twin.py)
+def _affinity(seed, n, d=20):
+    rng = np.random.default_rng(seed)
+    x = np.vstack([rng.normal(0, 1, (n // 2, d)), rng.normal(0, 1, (n - n // 2, d)) + 2.5])
+    x = x[rng.permutation(n)]
+    d2 = ((x[:, None, :] - x[None, :, :]) ** 2).sum(-1)
+    return np.exp(-d2 / d)
+
+
+@pytest.mark.parametrize("n", [33, 257, 1000])
+def test_k8_laplacian_matvec_gram_rotate_match_the_twin(ctx, n):
+    from spectral_twin import NumpyOps
+    a = _affinity(n, n)
+    m, dd = ctx.laplacian_normalize(torch.from_numpy(a).cuda())
+    m_ref, dd_ref = NumpyOps.normalize(a)
+    assert np.allclose(dd.cpu().numpy(), dd_ref, rtol=1e-14, atol=0)
+    assert np.allclose(m.cpu().numpy(), m_ref, rtol=1e-13, atol=1e-300)
+    rng = np.random.default_rng(1)
+    x = rng.standard_normal((8, n))
+    xd = torch.from_numpy(x).cuda()
+    y = ctx.sym_block_matvec(m, xd, 0.25)
+    y_ref = NumpyOps.matvec(m_ref, x, 0.25)
+    assert np.abs(y.cpu().numpy() - y_ref).max() <= 1e-12 * np.abs(y_ref).max()
+    g = ctx.block_gram(xd, y, 0).cpu().numpy()
+    assert np.abs(g[:64] - NumpyOps.gram(x, y_ref, 0)[:64]).max() <= 1e-11 * np.abs(g[:64]).max()
+    rinv = ctx.block_gram(xd, xd, 1)
+    assert rinv[64].item() == 0.0
+    ctx.block_rotate(xd, None, rinv[:64])
+    q = xd.cpu().numpy()
+    assert np.abs(q @ q.T - np.eye(8)).max() <= 1e-12 * max(1.0, np.linalg.cond(x @ x.T))     # orthonormal after one Cholesky QR
+    lam = rng.standard_normal(8)
+    rot = np.linalg.qr(rng.standard_normal((8, 8)))[0]
+    x2, y2 = q.copy(), y_ref.copy()
+    res_ref = NumpyOps.rotate(x2, y2, rot, lam)
+    yd = torch.from_numpy(y_ref).cuda()
+    res = ctx.block_rotate(xd, yd, torch.from_numpy(np.ascontiguousarray(rot)).cuda(), torch.from_numpy(lam).cuda())
+    assert np.abs(xd.cpu().numpy() - x2).max() <= 1e-13 and np.abs(yd.cpu().numpy() - y2).max() <= 1e-12 * np.abs(y2).max()
+    assert np.allclose(res.cpu().numpy(), res_ref, rtol=1e-10)
+    # a collapsed block is reported, not silently factorised
+    bad = torch.from_numpy(np.repeat(x[:1], 8, axis=0).copy()).cuda()
+    assert ctx.block_gram(bad, bad, 1)[64].item() == 1.0
+
+
+@pytest.mark.parametrize("n,k", [(135, 2), (135, 3), (2000, 2)])
+def test_k8_kmeans_lloyd_matches_the_twin_and_sklearn(ctx, n, k):
+    from sklearn.cluster import KMeans
+    from spectral_twin import NumpyOps
+    from hvb.spectral import _DeviceOps, kmeans_best_of
+    rng = np.random.default_rng(n + k)
+    cen = rng.normal(0, 2.0, (3, 2))
+    emb = np.vstack([rng.normal(0, 0.4, (n // 3, 2)) + cen[i] for i in range(3)] + [rng.normal(0, 0.4, (n - 3 * (n // 3), 2)) + cen[0]])
+    x = emb - emb.mean(0)
+    init = np.stack([x[rng.choice(len(x), k, replace=False)] for _ in range(10)])
+    tol = float(np.mean(np.var(x, axis=0)) * 1e-4)
+    got = [t.cpu().numpy() for t in ctx.kmeans_lloyd(torch.from_numpy(x).cuda(), torch.from_numpy(init).cuda(), 300, tol)]
+    ref = NumpyOps.kmeans(x, init, 300, tol)
+    assert np.array_equal(got[0], ref[0]) and np.array_equal(got[3], ref[3]) and np.array_equal(got[4], ref[4])
+    assert np.allclose(got[1], ref[1], rtol=1e-12, atol=1e-14) and np.allclose(got[2], ref[2], rtol=1e-12)
+    km = KMeans(n_clusters=k, n_init=10, random_state=np.random.RandomState(3)).fit(emb)
+    lab = kmeans_best_of(emb, k, 10, np.random.RandomState(3), _DeviceOps(ctx))
+    assert np.array_equal(lab, km.labels_)
+
+
+@pytest.mark.parametrize("n", [220, 2000])
+def test_k8_subspace_embedding_equals_the_dense_solver(ctx, n):
+    from hvb.spectral import _DeviceOps, spectral_embedding_dense, spectral_embedding_subspace
+    a = torch.from_numpy(_affinity(7, n)).cuda()
+    info = {}
+    torch.cuda.synchronize(); t0 = time.perf_counter()
+    got = spectral_embedding_subspace(a, 2, _DeviceOps(ctx), info=info)
+    t1 = time.perf_counter()
+    dense = spectral_embedding_dense(a, 2).cpu().numpy()
+    t2 = time.perf_counter()
+    assert np.abs(got - dense).max() <= 1e-8 * np.abs(dense).max()
+    print("N=%d: subspace solver %.1f ms (%d outer rounds, %d matvecs, residual %.1e), cuSOLVER eigh %.1f ms"
+          % (n, 1e3 * (t1 - t0), info["outer_iterations"], info["matvecs"], info["residuals"].max(), 1e3 * (t2 - t1)))

@@ -48,7 +48,7 @@ def report(name, ms, nbytes=None, flops=None, **kw):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--reps", type=int, default=20)
-    ap.add_argument("--only", default="", help="comma-separated sections: k1,k2,k3,k4,k4b,track,k5,k6")
+    ap.add_argument("--only", default="", help="comma-separated sections: k1,k2,k3,k4,k4b,track,k5,k6,k8")
     ap.add_argument("--profile", action="store_true", help="one launch per kernel configuration, no timing (for ncu)")
     args = ap.parse_args()
     if args.profile:
@@ -272,8 +272,42 @@ def main():
             report("   cuDNN conv2d + K5 " + tag, timed(lambda: ctx.bias_act(torch.conv2d(x, w), b, "silu_fast"), R), alg)
             del x, out
 
+    def sec_k8():
+        # K8: the subspace-iteration pass over the normalised affinity, and the whole device spectral fit
+        from hvb.spectral import DeviceSpectralClustering, _DeviceOps, spectral_embedding_subspace
+        for n in (2000, 8192):
+            g = torch.Generator(device="cuda").manual_seed(0)
+            c = torch.randn((2, 32), device="cuda", dtype=torch.float64, generator=g) * 1.5
+            x = torch.randn((n, 32), device="cuda", dtype=torch.float64, generator=g) + c[torch.arange(n, device="cuda") % 2]
+            a = torch.exp(-torch.cdist(x, x) ** 2 / 32)
+            m, dd = ctx.laplacian_normalize(a)
+            report("K8 laplacian_normalize N=%d" % n, timed(lambda: ctx.laplacian_normalize(a), R), 2 * n * n * 8 + n * n * 8)
+            v = torch.randn((8, n), device="cuda", dtype=torch.float64, generator=g)
+            y = torch.empty_like(v)
+            report("K8 sym_block_matvec N=%d (8 vectors)" % n, timed(lambda: ctx.sym_block_matvec(m, v, 0.1, y), R), n * n * 8 + 2 * 8 * n * 8,
+                   flops=2 * 8 * n * n)
+            if R > 0:
+                info = {}
+                torch.cuda.synchronize()
+                import time as _t
+                t0 = _t.perf_counter()
+                spectral_embedding_subspace(a, 2, _DeviceOps(ctx), info=info)
+                t1 = _t.perf_counter()
+                lab = DeviceSpectralClustering(2, 10, 42).fit_predict(a)
+                t2 = _t.perf_counter()
+                torch.linalg.eigh(m)
+                torch.cuda.synchronize()
+                t3 = _t.perf_counter()
+                print(json.dumps({"kernel": "K8 device spectral fit N=%d" % n, "embedding_ms": round(1e3 * (t1 - t0), 2),
+                                  "embedding+kmeans_ms": round(1e3 * (t2 - t1), 2), "cusolver_eigh_ms": round(1e3 * (t3 - t2), 2),
+                                  "outer_rounds": info["outer_iterations"], "matvecs": info["matvecs"],
+                                  "residual": float(info["residuals"].max()), "labels_split": [int((lab == 0).sum()), int((lab == 1).sum())]}), flush=True)
+            del a, m, x
+
     if want('k3'):
         sec_k3()
+    if want('k8'):
+        sec_k8()
     if want('k6'):
         sec_k6()
     if want('k4'):
