@@ -19,6 +19,7 @@
 // with sklearn's own routine and random stream, best-of-n_init) is host code in hvb/spectral.py.
 #include "hvb_common.cuh"
 
+#include <algorithm>
 #include <math.h>
 
 namespace {
@@ -30,16 +31,33 @@ constexpr int kMvRows = (kMvThreads / 32) * kMvRowsPerWarp;     // 32 rows per C
 constexpr int kMvTile = 512;          // columns of X staged per step: 8 x 512 doubles = 32 KB
 
 // ---------------------------------------------------------------------------------------------- Laplacian pieces
-__global__ void __launch_bounds__(128)
+// 32 columns per CTA, 8 warps: warp r adds rows r, r + 8, ... of its columns (a coalesced 256-byte segment per row, four
+// loads in flight), the eight partial sums are combined in warp order — deterministic, not numpy's row-after-row order
+// (the two differ in the last bits only; the solver's tolerance is 1e-10).
+__global__ void __launch_bounds__(256)
 degree_kernel(const double* __restrict__ a, int n, double* __restrict__ dd) {
-    const int j = blockIdx.x * blockDim.x + threadIdx.x;
-    if (j >= n) return;
-    double w = 0.0;                                        // numpy's sum(axis=0): rows added one after the other
-    for (int i = 0; i < n; i++) {
-        const double v = a[(size_t)i * n + j];
-        w = __dadd_rn(w, i == j ? 0.0 : v);
+    __shared__ double part[8][32];
+    const int lane = threadIdx.x & 31, r = threadIdx.x >> 5;
+    const int j = blockIdx.x * 32 + lane;
+    double w0 = 0.0, w1 = 0.0, w2 = 0.0, w3 = 0.0;
+    if (j < n) {
+        int i = r;
+        for (; i + 24 < n; i += 32) {
+            const double v0 = a[(size_t)i * n + j], v1 = a[(size_t)(i + 8) * n + j], v2 = a[(size_t)(i + 16) * n + j], v3 = a[(size_t)(i + 24) * n + j];
+            w0 = __dadd_rn(w0, i == j ? 0.0 : v0);
+            w1 = __dadd_rn(w1, i + 8 == j ? 0.0 : v1);
+            w2 = __dadd_rn(w2, i + 16 == j ? 0.0 : v2);
+            w3 = __dadd_rn(w3, i + 24 == j ? 0.0 : v3);
+        }
+        for (; i < n; i += 8) w0 = __dadd_rn(w0, i == j ? 0.0 : a[(size_t)i * n + j]);
     }
-    dd[j] = w == 0.0 ? 1.0 : sqrt(w);
+    part[r][lane] = __dadd_rn(__dadd_rn(w0, w1), __dadd_rn(w2, w3));
+    __syncthreads();
+    if (r == 0 && j < n) {
+        double w = 0.0;
+        for (int k = 0; k < 8; k++) w = __dadd_rn(w, part[k][lane]);
+        dd[j] = w == 0.0 ? 1.0 : sqrt(w);
+    }
 }
 
 __global__ void __launch_bounds__(256)
@@ -61,14 +79,18 @@ column_sum_kernel(const double* __restrict__ partial, int n_blk, int width, doub
 
 // ---------------------------------------------------------------------------------------------- Y = (M + shift I) X
 // x, y: [kB][n] (each vector contiguous).  A warp owns 4 consecutive rows of M; the CTA stages a 512-column tile of the
-// 8 vectors in shared memory, every lane walks the tile with stride 32: 4 coalesced 256-byte row segments of M against 8
-// shared-memory operands = 32 DFMA per 4 loads.
+// 8 vectors in shared memory and every lane walks the tile two columns at a time: 4 coalesced 512-byte row segments of M
+// (128-bit loads, 8 in flight per lane) against 8 shared-memory operand pairs = 64 DFMA per 4 loads.  blockIdx.y splits
+// the columns so that small matrices still fill the 148 SMs; the split partial sums are combined in split order by
+// matvec_finish_kernel (deterministic), which also adds shift * x.
+template <bool VEC2>
 __global__ void __launch_bounds__(kMvThreads)
-sym_block_matvec_kernel(const double* __restrict__ m, int n, const double* __restrict__ x, double shift,
-                        double* __restrict__ y) {
-    __shared__ double xs[kB][kMvTile];
+sym_block_matvec_kernel(const double* __restrict__ m, int n, const double* __restrict__ x, int cols_per_split,
+                        double* __restrict__ ypart) {
+    __shared__ __align__(16) double xs[kB][kMvTile];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int row0 = blockIdx.x * kMvRows + warp * kMvRowsPerWarp;
+    const int c_begin = blockIdx.y * cols_per_split, c_end = min(n, c_begin + cols_per_split);
     double acc[kMvRowsPerWarp][kB];
 #pragma unroll
     for (int r = 0; r < kMvRowsPerWarp; r++)
@@ -78,23 +100,46 @@ sym_block_matvec_kernel(const double* __restrict__ m, int n, const double* __res
 #pragma unroll
     for (int r = 0; r < kMvRowsPerWarp; r++) mrow[r] = m + (size_t)min(row0 + r, n - 1) * n;
 
-    for (int c0 = 0; c0 < n; c0 += kMvTile) {
-        const int cw = min(kMvTile, n - c0);
+    for (int c0 = c_begin; c0 < c_end; c0 += kMvTile) {
+        const int cw = min(kMvTile, c_end - c0);
         __syncthreads();
         for (int p = threadIdx.x; p < kB * kMvTile; p += kMvThreads) {
             const int j = p / kMvTile, c = p - j * kMvTile;
             xs[j][c] = c < cw ? x[(size_t)j * n + c0 + c] : 0.0;
         }
         __syncthreads();
-        for (int c = lane; c < cw; c += 32) {
-            double mv[kMvRowsPerWarp];
+        if (VEC2) {                                           // n even, c0 even: every (row, c0 + 2k) address is 16-byte aligned
+            const int cw2 = cw & ~1;
+#pragma unroll 1
+            for (int c = 2 * lane; c < cw2; c += 64) {
+                double2 mv[kMvRowsPerWarp];
 #pragma unroll
-            for (int r = 0; r < kMvRowsPerWarp; r++) mv[r] = __ldg(mrow[r] + c0 + c);
+                for (int r = 0; r < kMvRowsPerWarp; r++) mv[r] = __ldg(reinterpret_cast<const double2*>(mrow[r] + c0 + c));
 #pragma unroll
-            for (int j = 0; j < kB; j++) {
-                const double xv = xs[j][c];
+                for (int j = 0; j < kB; j++) {
+                    const double2 xv = *reinterpret_cast<const double2*>(&xs[j][c]);
 #pragma unroll
-                for (int r = 0; r < kMvRowsPerWarp; r++) acc[r][j] = __fma_rn(mv[r], xv, acc[r][j]);
+                    for (int r = 0; r < kMvRowsPerWarp; r++) acc[r][j] = __fma_rn(mv[r].y, xv.y, __fma_rn(mv[r].x, xv.x, acc[r][j]));
+                }
+            }
+            if ((cw & 1) && lane == 0) {                      // odd tail column of the last tile of a split
+                const int c = cw - 1;
+#pragma unroll
+                for (int j = 0; j < kB; j++)
+#pragma unroll
+                    for (int r = 0; r < kMvRowsPerWarp; r++) acc[r][j] = __fma_rn(__ldg(mrow[r] + c0 + c), xs[j][c], acc[r][j]);
+            }
+        } else {
+            for (int c = lane; c < cw; c += 32) {
+                double mv[kMvRowsPerWarp];
+#pragma unroll
+                for (int r = 0; r < kMvRowsPerWarp; r++) mv[r] = __ldg(mrow[r] + c0 + c);
+#pragma unroll
+                for (int j = 0; j < kB; j++) {
+                    const double xv = xs[j][c];
+#pragma unroll
+                    for (int r = 0; r < kMvRowsPerWarp; r++) acc[r][j] = __fma_rn(mv[r], xv, acc[r][j]);
+                }
             }
         }
     }
@@ -108,6 +153,7 @@ sym_block_matvec_kernel(const double* __restrict__ m, int n, const double* __res
             acc[r][j] = v;
         }
     if (lane < kB) {
+        double* yp = ypart + (size_t)blockIdx.y * kB * n;
 #pragma unroll
         for (int r = 0; r < kMvRowsPerWarp; r++) {
             const int row = row0 + r;
@@ -115,10 +161,20 @@ sym_block_matvec_kernel(const double* __restrict__ m, int n, const double* __res
                 double v = 0.0;
 #pragma unroll
                 for (int j = 0; j < kB; j++) if (lane == j) v = acc[r][j];
-                y[(size_t)lane * n + row] = __fma_rn(shift, x[(size_t)lane * n + row], v);
+                yp[(size_t)lane * n + row] = v;
             }
         }
     }
+}
+
+__global__ void __launch_bounds__(256)
+matvec_finish_kernel(const double* __restrict__ ypart, int splits, int n, const double* __restrict__ x, double shift,
+                     double* __restrict__ y) {
+    const int p = blockIdx.x * blockDim.x + threadIdx.x;
+    if (p >= kB * n) return;
+    double s = 0.0;
+    for (int k = 0; k < splits; k++) s = __dadd_rn(s, ypart[(size_t)k * kB * n + p]);
+    y[p] = __fma_rn(shift, x[p], s);
 }
 
 // ---------------------------------------------------------------------------------------------- small products
@@ -354,7 +410,7 @@ int hvb_spectral_block(int* out_block) {
 int hvb_laplacian_normalize(hvb_ctx* ctx, const double* a_dev, int n, double* m_dev, double* dd_dev) {
     HVB_CHECK_CTX(ctx);
     HVB_ARG(a_dev && m_dev && dd_dev && n >= 1 && n <= 65535, "bad arguments");
-    degree_kernel<<<hvb_div_up(n, 128), 128, 0, ctx->stream>>>(a_dev, n, dd_dev);
+    degree_kernel<<<hvb_div_up(n, 32), 256, 0, ctx->stream>>>(a_dev, n, dd_dev);
     HVB_LAUNCHED(ctx);
     normalize_kernel<<<dim3(hvb_div_up(n, 256), n), 256, 0, ctx->stream>>>(a_dev, dd_dev, n, m_dev);
     HVB_LAUNCHED(ctx);
@@ -364,7 +420,19 @@ int hvb_laplacian_normalize(hvb_ctx* ctx, const double* a_dev, int n, double* m_
 int hvb_sym_block_matvec(hvb_ctx* ctx, const double* m_dev, int n, const double* x_dev, double shift, double* y_dev) {
     HVB_CHECK_CTX(ctx);
     HVB_ARG(m_dev && x_dev && y_dev && n >= 1 && x_dev != y_dev, "bad arguments");
-    sym_block_matvec_kernel<<<hvb_div_up(n, kMvRows), kMvThreads, 0, ctx->stream>>>(m_dev, n, x_dev, shift, y_dev);
+    const int row_ctas = hvb_div_up(n, kMvRows);
+    int splits = std::max(1, std::min(8, hvb_div_up(2 * ctx->sm_count, row_ctas)));
+    int cols = hvb_div_up(n, splits);
+    cols = hvb_div_up(cols, 64) * 64;                         // split boundaries on 512-byte lines (and even columns)
+    splits = hvb_div_up(n, cols);
+    void* ypart = nullptr;
+    HVB_TRY(hvb_scratch2(ctx, (size_t)splits * kB * n * sizeof(double), &ypart));
+    const bool vec2 = (n % 2 == 0) && ((uintptr_t)m_dev % 16 == 0);
+    const dim3 grid(row_ctas, splits);
+    if (vec2) sym_block_matvec_kernel<true><<<grid, kMvThreads, 0, ctx->stream>>>(m_dev, n, x_dev, cols, (double*)ypart);
+    else sym_block_matvec_kernel<false><<<grid, kMvThreads, 0, ctx->stream>>>(m_dev, n, x_dev, cols, (double*)ypart);
+    HVB_LAUNCHED(ctx);
+    matvec_finish_kernel<<<hvb_div_up((int64_t)kB * n, 256), 256, 0, ctx->stream>>>((const double*)ypart, splits, n, x_dev, shift, y_dev);
     HVB_LAUNCHED(ctx);
     return HVB_OK;
 }

@@ -67,6 +67,7 @@ PROTOTYPES = {
     "hvb_memcpy_h2d": [_vp, _vp, _vp, _sz],
     "hvb_memcpy_d2h": [_vp, _vp, _vp, _sz],
     "hvb_memset": [_vp, _vp, _i, _sz],
+    "hvb_stage_frames": [_vp, _i, _sz, _vp, _i],
     "hvb_ctx_launch_count": [_vp, _i, C.POINTER(C.c_uint64)],
     "hvb_timer_start": [_vp],
     "hvb_timer_stop_ms": [_vp, C.POINTER(_f)],

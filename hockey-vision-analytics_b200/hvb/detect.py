@@ -8,6 +8,8 @@ libhvb kernels.  Batches of frames go through one K1 launch and one K2a launch.
 """
 from __future__ import annotations
 
+import os
+
 from typing import Dict, List, Optional, Sequence, Tuple
 
 import numpy as np
@@ -70,6 +72,12 @@ class Detector:
         self.cuda_graph = (self.runner is not None) if cuda_graph is None else bool(cuda_graph)
         self._graphs: Dict[Tuple, object] = {}
         self._staging: Dict[Tuple, dict] = {}
+        try:
+            cores = len(os.sched_getaffinity(0))
+        except AttributeError:
+            cores = os.cpu_count() or 1
+        # worker threads of the host-side staging copy: half the cores this process may run on, at most 8
+        self.staging_threads = int(os.environ.get("HVB_STAGING_THREADS", max(1, min(8, cores // 2))))
         self._plans: Dict[Tuple, LetterboxPlan] = {}
         self._meta: Dict[Tuple, torch.Tensor] = {}
         # Synthetic-input hook (hvb.synth.DeviceOverlay): an object with begin_chunk(n_frames) — called once per detect
@@ -112,16 +120,26 @@ class Detector:
         if slot["events"][i] is not None:
             slot["events"][i].synchronize()                 # the H2D copy that last used this buffer has finished
         buf = slot["bufs"][i]
-        if isinstance(frames, np.ndarray):                  # torch's CPU copy is vectorised and multi-threaded for large tensors
-            buf.copy_(torch.from_numpy(frames))
-        else:
-            for k, f in enumerate(frames):
-                buf[k].copy_(torch.from_numpy(f))
+        self._stage(frames, buf, n, h, w)
         dev = buf.to(self.device, non_blocking=True)
         ev = torch.cuda.Event()
         ev.record()
         slot["events"][i] = ev
         return dev
+
+    def _stage(self, frames, buf: torch.Tensor, n: int, h: int, w: int) -> None:
+        """Host frames -> the pinned staging buffer through hvb_stage_frames (worker threads inside libhvb, GIL released).
+        torch's per-frame copy_ ran single-threaded when called from the staging thread of process_video_chunked: 398 MB
+        per 64-frame chunk took as long as the GPU step (tools/probe_staging.py)."""
+        import ctypes
+        each = h * w * 3
+        rows = [frames[k] for k in range(n)]
+        if all(isinstance(f, np.ndarray) and f.dtype == np.uint8 and f.shape == (h, w, 3) and f.flags.c_contiguous for f in rows):
+            ptrs = (ctypes.c_void_p * n)(*[f.ctypes.data for f in rows])
+            _ffi.check(_ffi.lib().hvb_stage_frames(ctypes.cast(ptrs, ctypes.c_void_p), n, each, buf.data_ptr(), self.staging_threads))
+            return
+        for k, f in enumerate(rows):                        # strided views / other dtypes: the general copy
+            buf[k].copy_(torch.from_numpy(np.ascontiguousarray(f, np.uint8)))
 
     def forward_heads(self, x: torch.Tensor, cls_index: int = 0) -> List[torch.Tensor]:
         """Backbone forward (PyTorch).  Returns the 3 raw head tensors (SplitHeads from the K5 runner, else float32

@@ -72,6 +72,9 @@ HVB_API int hvb_host_alloc(hvb_ctx* ctx, size_t bytes, void** out_host);   /* pi
 HVB_API int hvb_host_free(hvb_ctx* ctx, void* ptr_host);
 HVB_API int hvb_memcpy_h2d(hvb_ctx* ctx, void* dst_dev, const void* src_host, size_t bytes);  /* async */
 HVB_API int hvb_memcpy_d2h(hvb_ctx* ctx, void* dst_host, const void* src_dev, size_t bytes);  /* async */
+/* Host-side staging: n separately allocated frames of bytes_each bytes (hockey/main.py:321 yields one array per frame)
+ * -> one contiguous (pinned) buffer, copied by n_threads workers.  No CUDA call; the source of the chunk's one H2D copy. */
+HVB_API int hvb_stage_frames(const void* const* src_host, int n, size_t bytes_each, void* dst_host, int n_threads);
 HVB_API int hvb_memset(hvb_ctx* ctx, void* dst_dev, int value, size_t bytes);
 /* Launch counter: number of libhvb kernels launched on this context since the last reset. */
 HVB_API int hvb_ctx_launch_count(hvb_ctx* ctx, int reset, uint64_t* out_launches);

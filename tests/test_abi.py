@@ -78,3 +78,17 @@ def test_product_never_imports_oracle():
             if f.endswith((".py", ".cu", ".cuh", ".h")):
                 txt = open(os.path.join(dirpath, f)).read()
                 assert not re.search(r"^\s*(from|import)\s+oracle\b", txt, re.M), "%s imports the oracle" % f
+
+
+def test_stage_frames_copies_every_frame_with_any_thread_count():
+    """hvb_stage_frames (host-side staging of separately allocated frames into one buffer) needs no GPU."""
+    from hvb import _ffi
+    rng = np.random.default_rng(0)
+    frames = [rng.integers(0, 256, (37, 53, 3), dtype=np.uint8) for _ in range(11)]
+    ptrs = (ctypes.c_void_p * len(frames))(*[f.ctypes.data for f in frames])
+    for threads in (1, 3, 8, 100):
+        dst = np.zeros((len(frames), 37, 53, 3), np.uint8)
+        _ffi.check(_ffi.lib().hvb_stage_frames(ctypes.cast(ptrs, ctypes.c_void_p), len(frames), frames[0].nbytes, dst.ctypes.data, threads))
+        assert all(np.array_equal(dst[k], f) for k, f in enumerate(frames))
+    assert _ffi.lib().hvb_stage_frames(None, 0, 10, None, 4) == 0                   # empty chunk
+    assert _ffi.lib().hvb_stage_frames(None, 2, 10, dst.ctypes.data, 4) != 0        # loud on a null table
