@@ -66,6 +66,7 @@ class B200InferenceSlicer:
             concurrent_classes = os.environ.get("HVB_SLICER_CONCURRENT", "0") == "1"
         self.concurrent_classes = concurrent_classes
         self._side_streams = None
+        self.stage_events = None              # set to a list to collect (stage name, CUDA event) marks of the next run_device call
 
     def _overlap(self) -> Tuple[int, int]:
         if self.overlap_wh is not None:
@@ -110,7 +111,16 @@ class B200InferenceSlicer:
             det.head_hook.begin_chunk(n, repeat=hook == "repeat")
         mode = _ffi.LB_SLICE_UNIFORM if self.uniform_tiles else _ffi.LB_SLICE_EXACT
         plan = det.plan(n, h, w, mode, self.tile_imgsz, self.slice_wh, self._overlap())
+        ev = self.stage_events                                   # bench instrumentation: None, or a list to append to
+
+        def mark(name):
+            if ev is not None:
+                e = torch.cuda.Event(enable_timing=True)
+                e.record()
+                ev.append((name, e))
+        mark("start")
         views = plan.class_views(plan.run(frames_dev))
+        mark("K1b slice letterbox")
         n_slots = n * plan.tiles_per_frame
         out = (ctx.empty((n_slots, det.max_det, 4), torch.float32), ctx.empty((n_slots, det.max_det), torch.float32),
                ctx.empty((n_slots, det.max_det), torch.int32), torch.zeros((n_slots,), dtype=torch.int32, device=ctx.device))
@@ -145,8 +155,10 @@ class B200InferenceSlicer:
         else:
             for c, x in enumerate(views):
                 heads = det.forward_heads(x, c)
+                mark("forward")
                 meta_h, meta_d = det._meta_dev(plan, c)
                 *_, state = det._decode(heads, meta_h, meta_d, n_slots, out=out)
+                mark("K2a decode + NMS")
                 states.append(state)
         xyxy, cf, cl, cnt = out
         key = ("slot_off", id(plan))
@@ -167,6 +179,7 @@ class B200InferenceSlicer:
         else:
             keep = ctx.merge_nms(g_xyxy, g_conf, None if self.class_agnostic else g_cls, seg, n, total, self.iou_threshold,
                                  self.class_agnostic)
+        mark("gather + K2b cross-slice NMS")
         if sync:
             return g_xyxy[:total], g_conf[:total], g_cls[:total], keep, seg
         return g_xyxy, g_conf, g_cls, keep, seg, cnt

@@ -56,6 +56,13 @@ for T in (2, 4, 8):
     out["numpy_pool%d_ms" % T] = timed(pooled)
     out["numpy_pool%d_side_thread_ms" % T] = in_thread(pooled)
     pool.shutdown()
+import ctypes
+from hvb import _ffi
+ptrs = (ctypes.c_void_p * n)(*[f.ctypes.data for f in frames])
+for T in (1, 2, 4, 8):
+    fn = lambda: _ffi.check(_ffi.lib().hvb_stage_frames(ctypes.cast(ptrs, ctypes.c_void_p), n, h * w * 3, buf.data_ptr(), T))
+    out["hvb_stage_frames_%d_threads_ms" % T] = timed(fn)
+    out["hvb_stage_frames_%d_threads_side_thread_ms" % T] = in_thread(fn)
 torch.set_num_threads(1)
 out["torch_copy_1thread_main_ms"] = timed(t_torch)
 print(json.dumps(out))
