@@ -146,13 +146,17 @@ k3b_table_kernel(int* __restrict__ tab) {
     for (int x = 0; x < kFastK; x++) part[2 * out_size + o * kFastK + x] = kk[x];
 }
 
+// Bilinear taps are non-negative and sum to at most 2^22 + 4 (eight taps, each rounded up by at most 1/2): the rounded
+// accumulator 2^21 + sum(v * k) lies in [0, 256 * 2^22), so Pillow's clip8 reduces to the shift — no min / max needed.
+__device__ __forceinline__ uint32_t shr8(int v) { return (uint32_t)v >> kPrecision; }
+
 template <int TAPS>
 __device__ __forceinline__ void hpass_item(const uint8_t* __restrict__ src, int cnt, const int (&kk)[kFastK], uint32_t* __restrict__ dst) {
     int s0 = 1 << (kPrecision - 1), s1 = s0, s2 = s0;
 #pragma unroll
     for (int x = 0; x < TAPS; x++)
         if (x < cnt) { s0 += src[3 * x] * kk[x]; s1 += src[3 * x + 1] * kk[x]; s2 += src[3 * x + 2] * kk[x]; }
-    *dst = (uint32_t)clip8(s0) | ((uint32_t)clip8(s1) << 8) | ((uint32_t)clip8(s2) << 16);
+    *dst = shr8(s0) | (shr8(s1) << 8) | (shr8(s2) << 16);
 }
 
 __global__ void __launch_bounds__(kThreads, 4)
@@ -167,7 +171,12 @@ mnv3_prep_fast_kernel(const uint8_t* __restrict__ pixels, const hvb_crop_desc* _
     const int* v_k = S.vtab + 2 * kOutH;
 
     bool lut_ready = false;
-    for (int ci = blockIdx.x; ci < n; ci += gridDim.x) {
+    // Work item = (crop, band of 64 output rows): with one crop per item the persistent grid (4 CTAs x 148 SMs = 592) ran
+    // 768 crops as "1 or 2 crops per CTA" — a makespan of two crops for 1.3 crops of average work (ncu r02d: the SMs were
+    // active for 63 % of the kernel's duration); half-crop items make it 1.5.
+    for (int item = blockIdx.x; item < 2 * n; item += gridDim.x) {
+        const int ci = item >> 1, band = item & 1;
+        const int y_begin = band * (kOutH / 2), y_end = y_begin + kOutH / 2;
         const hvb_crop_desc cd = crops[ci];
         const hvb_rect rc = hvb_roi_rect(cd.h, cd.w, roi_mode);
         const int rw = max(rc.right - rc.left, 0), rh = max(rc.bottom - rc.top, 0);
@@ -177,9 +186,10 @@ mnv3_prep_fast_kernel(const uint8_t* __restrict__ pixels, const hvb_crop_desc* _
         uint8_t* o8 = out_u8 ? out_u8 + (int64_t)ci * kOutH * kOutW * 3 : nullptr;
         if (rw <= 0 || rh <= 0) {
             // empty ROI: the reference's `except:` path (zero feature row)
-            for (int i = threadIdx.x; i < 3 * kOutH * kOutW; i += kThreads) o[i] = 0.f;
-            if (o8) for (int i = threadIdx.x; i < 3 * kOutH * kOutW; i += kThreads) o8[i] = 0;
-            if (out_valid && threadIdx.x == 0) out_valid[ci] = 0;
+            for (int c = 0; c < 3; c++)
+                for (int i = threadIdx.x; i < (kOutH / 2) * kOutW; i += kThreads) o[(c * kOutH + y_begin) * kOutW + i] = 0.f;
+            if (o8) for (int i = threadIdx.x; i < 3 * (kOutH / 2) * kOutW; i += kThreads) o8[3 * y_begin * kOutW + i] = 0;
+            if (out_valid && threadIdx.x == 0 && band == 0) out_valid[ci] = 0;
             continue;
         }
         if (!lut_ready) {
@@ -191,7 +201,7 @@ mnv3_prep_fast_kernel(const uint8_t* __restrict__ pixels, const hvb_crop_desc* _
             }
             lut_ready = true;                       // visible after the __syncthreads below
         }
-        if (out_valid && threadIdx.x == 0) out_valid[ci] = 1;
+        if (out_valid && threadIdx.x == 0 && band == 0) out_valid[ci] = 1;
         const uint8_t* base = pixels + cd.offset + (int64_t)rc.top * cd.pitch + (int64_t)rc.left * 3;
         const int row_bytes = rw * 3;
         const int pitch_s = ((row_bytes + 3 + 3) >> 2) << 2;       // room for a shift of up to 3 bytes, word multiple
@@ -214,35 +224,77 @@ mnv3_prep_fast_kernel(const uint8_t* __restrict__ pixels, const hvb_crop_desc* _
         }
         __syncthreads();
 
-        int y0 = 0;
-        while (y0 < kOutH) {
+        int y0 = y_begin;
+        while (y0 < y_end) {
             // largest block of output rows whose source-row window fits the staging + intermediate buffers: the window
             // end ymin + n is non-decreasing in y, so the rows that fit are a prefix and one block-wide count finds it
             const int r_lo = v_ymin[y0];
             const int y = threadIdx.x;
-            const int fits = __syncthreads_count(y >= y0 && y < kOutH && v_ymin[y] + v_n[y] - r_lo <= rmax);
+            const int fits = __syncthreads_count(y >= y0 && y < y_end && v_ymin[y] + v_n[y] - r_lo <= rmax);
             const int y1 = y0 + max(fits, 1);
             const int r_hi = v_ymin[y1 - 1] + v_n[y1 - 1];
             const int nrows = r_hi - r_lo;
-            // ---- stage rows [r_lo, r_hi): warp per row, lane per aligned 32-bit word; all loads independent
-            for (int r = warp; r < nrows; r += kThreads / 32) {
-                const uint8_t* rowp = base + (int64_t)(r_lo + r) * cd.pitch;
-                const int sh = (int)(reinterpret_cast<uintptr_t>(rowp) & 3);
-                const uint8_t* ap = rowp - sh;                      // aligned-down address of the row's first word
-                const int nwords = (sh + row_bytes + 3) >> 2;
-                uint32_t* dst = S.roi + r * (pitch_s >> 2);
-                for (int i = lane; i < nwords; i += 32) {
-                    uint32_t v;
-                    const int b0 = 4 * i - sh;                      // ROI byte index of the word's first byte
-                    if (b0 >= 0 && b0 + 4 <= row_bytes) {
-                        v = __ldg(reinterpret_cast<const uint32_t*>(ap) + i);
-                    } else {                                        // first / last partial word: only bytes of the ROI
-                        v = 0;
+            // ---- stage rows [r_lo, r_hi): a warp takes FOUR rows per pass (r, r + 8, r + 16, r + 24), a lane two aligned
+            // 32-bit words of each — up to eight independent loads in flight per lane before the first shared store.  ncu
+            // on the one-row-at-a-time loop (profiles/r02d_ncu_k3.md, tools/ncu_lines.py): 30 % of the kernel's stall samples
+            // sat on this phase (a 45-pixel row is 34 words: two dependent global-latency round trips per row and warp).
+            {
+                const int wpr = pitch_s >> 2;
+                const int slack_lo = min(rc.left * 3, 3), slack_hi = min((cd.w - rc.right) * 3, 3);   // crop-row bytes beside the ROI
+                for (int rb = warp; rb < nrows; rb += 4 * (kThreads / 32)) {
+                    uint32_t v[4][2];
+                    bool live[4][2];
 #pragma unroll
-                        for (int k = 0; k < 4; k++)
-                            if (b0 + k >= 0 && b0 + k < row_bytes) v |= (uint32_t)__ldg(rowp + b0 + k) << (8 * k);
+                    for (int u = 0; u < 4; u++) {
+                        const int r = rb + u * (kThreads / 32);
+                        const uint8_t* rowp = base + (int64_t)(r_lo + min(r, nrows - 1)) * cd.pitch;
+                        const int sh = (int)(reinterpret_cast<uintptr_t>(rowp) & 3);
+                        const uint8_t* ap = rowp - sh;                  // aligned-down address of the row's first word
+                        const int nwords = (sh + row_bytes + 3) >> 2;
+#pragma unroll
+                        for (int j = 0; j < 2; j++) {
+                            const int i = lane + 32 * j;
+                            live[u][j] = r < nrows && i < nwords;
+                            v[u][j] = 0;
+                            if (live[u][j]) {
+                                const int b0 = 4 * i - sh;              // ROI byte index of the word's first byte
+                                // whole words: inside the ROI row, or (partial first / last word) still inside the CROP's own
+                                // row, whose bytes belong to the caller's buffer — the extra bytes are never read back
+                                if (b0 >= -slack_lo && b0 + 4 <= row_bytes + slack_hi) {
+                                    v[u][j] = __ldg(reinterpret_cast<const uint32_t*>(ap) + i);
+                                } else {                                // at the edge of the crop row: only bytes of the ROI
+#pragma unroll
+                                    for (int k = 0; k < 4; k++)
+                                        if (b0 + k >= 0 && b0 + k < row_bytes) v[u][j] |= (uint32_t)__ldg(rowp + b0 + k) << (8 * k);
+                                }
+                            }
+                        }
                     }
-                    dst[i] = v;
+#pragma unroll
+                    for (int u = 0; u < 4; u++)
+#pragma unroll
+                        for (int j = 0; j < 2; j++)
+                            if (live[u][j]) S.roi[(rb + u * (kThreads / 32)) * wpr + lane + 32 * j] = v[u][j];
+                }
+                if (wpr > 64) {                                         // rows wider than 64 words (ROI wider than 84 px): the rest
+                    for (int r = warp; r < nrows; r += kThreads / 32) {
+                        const uint8_t* rowp = base + (int64_t)(r_lo + r) * cd.pitch;
+                        const int sh = (int)(reinterpret_cast<uintptr_t>(rowp) & 3);
+                        const uint8_t* ap = rowp - sh;
+                        const int nwords = (sh + row_bytes + 3) >> 2;
+                        for (int i = 64 + lane; i < nwords; i += 32) {
+                            uint32_t w = 0;
+                            const int b0 = 4 * i - sh;
+                            if (b0 + 4 <= row_bytes) {
+                                w = __ldg(reinterpret_cast<const uint32_t*>(ap) + i);
+                            } else {
+#pragma unroll
+                                for (int k = 0; k < 4; k++)
+                                    if (b0 + k < row_bytes) w |= (uint32_t)__ldg(rowp + b0 + k) << (8 * k);
+                            }
+                            S.roi[r * wpr + i] = w;
+                        }
+                    }
                 }
             }
             __syncthreads();
@@ -282,7 +334,7 @@ mnv3_prep_fast_kernel(const uint8_t* __restrict__ pixels, const hvb_crop_desc* _
                     }
                     int v[4][3];
 #pragma unroll
-                    for (int px = 0; px < 4; px++) { v[px][0] = clip8(a[px][0]); v[px][1] = clip8(a[px][1]); v[px][2] = clip8(a[px][2]); }
+                    for (int px = 0; px < 4; px++) { v[px][0] = (int)shr8(a[px][0]); v[px][1] = (int)shr8(a[px][1]); v[px][2] = (int)shr8(a[px][2]); }
 #pragma unroll
                     for (int c = 0; c < 3; c++) {
                         float4 f;
@@ -452,8 +504,8 @@ int hvb_mnv3_preprocess(hvb_ctx* ctx, const uint8_t* pixels_dev, const hvb_crop_
     auto gen = mnv3_prep_kernel<kGenK, kGenRows, false>;
     HVB_CUDA(cudaFuncSetAttribute(fast, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(SmemFast)));
     HVB_CUDA(cudaFuncSetAttribute(gen, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(SmemGen)));
-    // fast pass: one CTA per crop up to the four CTAs (64 registers x 256 threads) resident per SM
-    const int gfast = n < ctx->sm_count * 4 ? n : ctx->sm_count * 4;
+    // fast pass: items = (crop, half of the output rows); at most the four CTAs (64 registers x 256 threads) resident per SM
+    const int gfast = 2 * n < ctx->sm_count * 4 ? 2 * n : ctx->sm_count * 4;
     fast<<<gfast, kThreads, sizeof(SmemFast), ctx->stream>>>(pixels_dev, crops_dev, n, roi_mode, (const int*)ctx->k3b_tab_dev, out_dev,
                                                              out_u8_dev, out_valid_dev);
     HVB_LAUNCHED(ctx);
