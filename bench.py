@@ -511,7 +511,7 @@ def run_hvb(args, rank, world):
     # ---- secondary workload: 4K sliced puck path (C4): planted pucks, cross-slice duplicates in the tile overlaps
     roofline_4k = None
     if args.with_4k:
-        roofline_4k = bench_4k(args, rank, world, dev, barrier, max_over_ranks, peak, extra)
+        roofline_4k = bench_4k(args, rank, world, dev, barrier, max_over_ranks, peak, extra, path)
     # ---- BASELINE config 1: 1280x720, 60 frames, YOLOv8n (nc=1), sliced puck detection; CPU arm beside it at N=1
     if args.with_c1 and rank == 0:
         bench_c1(args, world, dev, extra)
@@ -584,7 +584,7 @@ def run_hvb(args, rank, world):
         print(json.dumps(line))
 
 
-def bench_4k(args, rank, world, dev, barrier, max_over_ranks, peak, extra):
+def bench_4k(args, rank, world, dev, barrier, max_over_ranks, peak, extra, path):
     """C4: 4K frames -> K1b slice letterbox (40 tiles, 5 shape classes) -> YOLOv8n per class -> planted pucks -> K2a ->
     gather -> K2b cross-slice merge.  Returns the top-level roofline block of the 4K path (K1b + K2a at 640 tiles)."""
     import torch
@@ -675,6 +675,32 @@ def bench_4k(args, rank, world, dev, barrier, max_over_ranks, peak, extra):
                   "c4_merged_detections_per_frame_before_cross_slice_nms": merged_per_frame,
                   "c4_detections_per_frame_after_cross_slice_nms": kept_per_frame})
     puck.detector.head_hook = None
+    # ---- BASELINE config 5, one GPU's share: a 4K clip through the FULL pipeline — players (whole-frame letterbox to
+    # 720x1280, YOLOv8m, planted candidates, K2a, K7, team stage on the tracked skaters) AND the sliced puck path on the
+    # same device-resident chunk, per step.  (The global fit's all-gather is `extra.fit`.)
+    from hvb.video import Config, VideoProcessor
+    det = path.detector
+    cls4 = [np.array([0] * (PLAYERS - 1) + [1])] * F4
+    ov_players = PlantedOverlay.whole_frame(31 + rank, (2160, 3840), IMGSZ, boxes4, cls4, nc=2, dup=DUP)
+    hook_players = ov_players.to_device(dev, [list(range(F4))])
+    hook_pucks = ov4.to_device(dev, [list(range(F4))], plan=plan4)
+    vp4 = VideoProcessor(device=dev, config=Config(), detector=det, team_classifier=path.classifier_router(), tracker=args.tracker)
+    tracked = [0, 0]
+
+    def full_step():
+        det.head_hook = hook_players
+        for r in vp4.process_chunks([f4_dev]):
+            tracked[0] += len(r.detections); tracked[1] += 1
+        det.head_hook = None
+        puck.detector.head_hook = hook_pucks
+        out = puck.process_chunk_device(f4_dev, graph=True)
+        puck.detector.head_hook = None
+        return out
+
+    ms5 = timed(full_step, k4, 3)
+    extra["c5_4k_full_pipeline_frames_per_sec"] = world * F4 * k4 / (ms5 / 1e3)
+    extra["c5_note"] = ("per step and GPU: %d 4K frames, players (K1a 4K->720x1280, YOLOv8m, K2a, K7, team stage; %.1f tracked per frame) + sliced "
+                        "puck path (640 tiles, one graph replay), device-resident" % (F4, tracked[0] / max(tracked[1], 1)))
     return {"workload": "C4: 4K sliced puck detection, %d frames = %d tiles per step, 3 planted objects per frame (x2 candidates, cross-slice duplicates)"
                         % (F4, F4 * int(plan4.tiles_per_frame)),
             "kernel": "letterbox_kernel<true> (K1b slice letterbox, exact 5-shape-class mode)", "bound": "hbm",
