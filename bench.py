@@ -492,7 +492,7 @@ def run_hvb(args, rank, world):
     # the drop-in at its default chunk of 32 frames
     det.head_hook = overlay.to_device(dev, [list(range(32)), list(range(32, 64))] if F >= 64 else [list(range(F))])
     ch = 32 if F >= 64 else F
-    clip = [frames[i] for k in range(6) for i in (range(32) if k % 2 == 0 else range(32, 64))] if F >= 64 else [frames[i] for k in range(6) for i in range(F)]
+    clip = [frames[i] for k in range(12) for i in (range(32) if k % 2 == 0 else range(32, 64))] if F >= 64 else [frames[i] for k in range(12) for i in range(F)]
     vpc = VideoProcessor(device=dev, config=Config(), detector=det, team_classifier=path.classifier_router(), tracker=args.tracker)
     list(vpc.process_video_chunked(clip[:2 * ch], chunk=ch, initialize=False))
     barrier()

@@ -27,18 +27,6 @@
 #else
 #define BT_HD inline
 #endif
-// The big building blocks (Kalman correction, assignment, cost matrix) are called from several places of bt_update; fully
-// inlined the kernel body is 28 k instructions and a single warp spends 18 % of its stall samples on instruction-cache
-// misses (profiles/r02f_ncu_k7_k2a.md).  BT_OUTLINE=1 keeps one copy of each.
-#ifndef BT_OUTLINE
-#define BT_OUTLINE 0
-#endif
-#if defined(__CUDACC__) && BT_OUTLINE
-#define BT_HDN __host__ __device__ __noinline__
-#else
-#define BT_HDN BT_HD
-#endif
-
 #if defined(__CUDA_ARCH__)
 #define BT_LANE ((int)(threadIdx.x & 31))
 #define BT_NL 32
@@ -130,7 +118,7 @@ BT_HD double bt_iou_cost(const double* a, const double* b, int flags, const doub
 }
 
 // cost[i * nb + j] for the boxes staged in w->abox / w->bbox (+ w->bscore when fuse)
-BT_HDN void bt_cost_matrix(BtWork* w, int na, int nb, int flags, bool fuse, double* cost) {
+BT_HD void bt_cost_matrix(BtWork* w, int na, int nb, int flags, bool fuse, double* cost) {
     const int total = na * nb;
     for (int p = BT_LANE; p < total; p += BT_NL) {
         const int i = p / nb, j = p - i * nb;
@@ -158,7 +146,7 @@ BT_HD void bt_predict(BtClip* c, int t) {                 // KalmanFilter.multi_
     for (int i = 0; i < 8; i++) P[i * 8 + i] = P[i * 8 + i] + q[i];
 }
 
-BT_HDN void bt_correct(BtClip* c, int t, const float* z32) {   // KalmanFilter.update for one track, measurement xyah
+BT_HD void bt_correct(BtClip* c, int t, const float* z32) {   // KalmanFilter.update for one track, measurement xyah
     double* m = c->mean[t];
     double* P = c->cov[t];
     const double h = m[3];
@@ -241,7 +229,7 @@ BT_HD bool bt_cand_better(const BtCand& a, const BtCand& b) {      // a beats b
     return a.un ? a.it > b.it : a.it < b.it;
 }
 
-BT_HDN int bt_lsap(int nr, int nc, const double* C, BtWork* w) {
+BT_HD int bt_lsap(int nr, int nc, const double* C, BtWork* w) {
     const int lane = BT_LANE;
     for (int j = lane; j < nc; j += BT_NL) { w->v[j] = 0.0; w->row4col[j] = -1; w->path[j] = -1; }
     for (int i = lane; i < nr; i += BT_NL) { w->u[i] = 0.0; w->col4row[i] = -1; }
@@ -310,7 +298,7 @@ BT_HDN int bt_lsap(int nr, int nc, const double* C, BtWork* w) {
 
 // matching.linear_assignment: clamp costs above thresh to thresh + 1e-4, solve, keep matches with cost <= thresh.
 // Results in w->ma/mb (row order), w->ua, w->ub (ascending).
-BT_HDN void bt_assign(BtWork* w, int na, int nb, double* cost, double* costT, double thresh) {
+BT_HD void bt_assign(BtWork* w, int na, int nb, double* cost, double* costT, double thresh) {
     const int lane = BT_LANE;
     if (na == 0 || nb == 0) {
         if (lane == 0) {
