@@ -302,9 +302,12 @@ mnv3_prep_fast_kernel(const uint8_t* __restrict__ pixels, const hvb_crop_desc* _
             {
                 const uint8_t* sroi = reinterpret_cast<const uint8_t*>(S.roi);
                 const int sh0 = (int)(reinterpret_cast<uintptr_t>(base + (int64_t)r_lo * cd.pitch) & 3), dsh = cd.pitch & 3;
-                if (ksh <= 4) {
+                if (ksh <= 3) {                                 // ROI not wider than 64 px (no horizontal down-scaling): 3 taps
                     for (int row = hq; row < nrows; row += kThreads / kOutW)
-                        hpass_item<4>(sroi + row * pitch_s + ((sh0 + row * dsh) & 3) + hxmin * 3, hcnt, hk, S.inter + row * kOutW + xx);
+                        hpass_item<3>(sroi + row * pitch_s + ((sh0 + row * dsh) & 3) + hxmin * 3, hcnt, hk, S.inter + row * kOutW + xx);
+                } else if (ksh <= 5) {                          // up to 128 px wide: 5 taps
+                    for (int row = hq; row < nrows; row += kThreads / kOutW)
+                        hpass_item<5>(sroi + row * pitch_s + ((sh0 + row * dsh) & 3) + hxmin * 3, hcnt, hk, S.inter + row * kOutW + xx);
                 } else {
                     for (int row = hq; row < nrows; row += kThreads / kOutW)
                         hpass_item<kFastK>(sroi + row * pitch_s + ((sh0 + row * dsh) & 3) + hxmin * 3, hcnt, hk, S.inter + row * kOutW + xx);

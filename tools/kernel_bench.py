@@ -68,6 +68,7 @@ def main():
                                           ("K1a 1080p->736x1280 x64", 64, 1080, 1920, _ffi.LB_WHOLE, 1280),
                                           ("K1a 720p->384x640 x64 (2x area path)", 64, 720, 1280, _ffi.LB_WHOLE, 640),
                                           ("K1b 4K sliced exact x4", 4, 2160, 3840, _ffi.LB_SLICE_EXACT, 640),
+                                          ("K1b 4K sliced exact x16 (bench.py's 4K launch)", 16, 2160, 3840, _ffi.LB_SLICE_EXACT, 640),
                                           ("K1b 4K sliced uniform x8", 8, 2160, 3840, _ffi.LB_SLICE_UNIFORM, 640)):
             frames = torch.from_numpy(rng.integers(0, 256, (n, h, w, 3), dtype=np.uint8)).cuda()
             plan = ctx.letterbox_plan(n, h, w, mode, imgsz)
