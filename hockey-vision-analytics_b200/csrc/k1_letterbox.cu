@@ -98,29 +98,13 @@ __device__ __forceinline__ void lb_store(float* __restrict__ tile_f32, uint8_t* 
     }
 }
 
-template <bool U8OUT, int MINBLOCKS>
-__global__ void __launch_bounds__(kThreads, MINBLOCKS)
-letterbox_kernel(const uint8_t* __restrict__ frames, int64_t frame_bytes, int32_t pitch,
-                 const LbJob* __restrict__ jobs, const LbBlock* __restrict__ blk2job, int blocks_per_frame,
-                 const XCoef* __restrict__ xtab, const YCoef* __restrict__ ytab, int smem_row_words, int frames_aligned16,
-                 float* __restrict__ out_f32, uint8_t* __restrict__ out_u8) {
-    extern __shared__ __align__(16) uint32_t spix[];      // [rows][smem_row_words] pixel words
-    __shared__ YCoef s_y[kTH];                            // vertical coefficients of the block's rows (smem-row relative)
-
-    const int frame = blockIdx.x / blocks_per_frame;
-    const LbBlock bd = blk2job[blockIdx.x - frame * blocks_per_frame];    // two 128-bit loads: everything staging needs
-    const uint32_t packed = bd.packed;
-    const LbJob& job = jobs[packed >> 24];
-    const int oy0 = ((packed >> 12) & 0xfff) * kTH;
-    const int ox0 = (packed & 0xfff) * kTW;
-    const int mode = job.mode, top = job.top, left = job.left, new_w = job.new_w, new_h = job.new_h;
-    const int out_w = job.out_w, out_h = job.out_h, src_w = job.src_w;
-    const XCoef* xt = xtab + job.xtab;
-    const YCoef* yt = ytab + job.ytab;
-    // source window of this block (pixels [gx_lo, sx_hi], rows [sy_lo, sy_hi]); gx_lo is a multiple of 4
-    const bool has_src = (bd.flags & 1) != 0;
-    const int gx_lo = bd.gx_lo, sy_lo = bd.sy_lo;
-
+// Phase 1 of the kernel: stage the block's source window into shared memory as pixel words and fill the vertical
+// coefficient rows; ends with the CTA-wide barrier.  NT = threads per CTA.
+template <int NT>
+__device__ __forceinline__ void lb_prologue(const uint8_t* __restrict__ frames, int frame, int64_t frame_bytes, int32_t pitch,
+                                            const LbBlock& bd, bool has_src, int smem_row_words, int frames_aligned16,
+                                            uint32_t* __restrict__ spix, YCoef* __restrict__ s_y, int oy0, int top, int new_h,
+                                            int mode, const YCoef* __restrict__ yt, int sy_lo) {
     // ---- stage source rows [sy_lo, sy_hi], pixels [gx_lo, sx_hi] as pixel words: warp per row, lane per 4-pixel group
     if (has_src) {
         const uint8_t* src = frames + (int64_t)frame * frame_bytes + bd.src_off;
@@ -130,13 +114,13 @@ letterbox_kernel(const uint8_t* __restrict__ frames, int64_t frame_bytes, int32_
             // 16-pixel groups: three 128-bit loads -> four 128-bit shared stores; up to 3 items per thread in flight
             const int n16 = n_groups >> 2, n_items16 = n_rows * n16;
             const float inv16 = 1.0f / (float)n16;
-            for (int it0 = threadIdx.x; it0 < n_items16; it0 += 3 * kThreads) {
+            for (int it0 = threadIdx.x; it0 < n_items16; it0 += 3 * NT) {
                 uint4 q[3][3];
                 int soff[3], fsw[3];
                 bool live[3];
 #pragma unroll
                 for (int k = 0; k < 3; k++) {
-                    const int it = it0 + k * kThreads;
+                    const int it = it0 + k * NT;
                     live[k] = it < n_items16;
                     int r = (int)((float)it * inv16);
                     int g = it - r * n16;
@@ -171,7 +155,7 @@ letterbox_kernel(const uint8_t* __restrict__ frames, int64_t frame_bytes, int32_
         // issued before the first byte permute consumes one (memory-level parallelism hides DRAM latency)
         const int n_items = n_rows * n_groups;
         const float inv_groups = 1.0f / (float)n_groups;
-        for (int it0 = threadIdx.x; it0 < n_items; it0 += 4 * kThreads) {
+        for (int it0 = threadIdx.x; it0 < n_items; it0 += 4 * NT) {
             uint32_t a[4], b[4], c[4];
             int soff[4];
             bool fast[4], live[4];
@@ -179,7 +163,7 @@ letterbox_kernel(const uint8_t* __restrict__ frames, int64_t frame_bytes, int32_
             int g4[4];
 #pragma unroll
             for (int k = 0; k < 4; k++) {
-                const int it = it0 + k * kThreads;
+                const int it = it0 + k * NT;
                 live[k] = it < n_items;
                 int r = (int)((float)it * inv_groups);
                 int g = it - r * n_groups;
@@ -232,6 +216,34 @@ letterbox_kernel(const uint8_t* __restrict__ frames, int64_t frame_bytes, int32_
         s_y[threadIdx.x] = yc;
     }
     __syncthreads();
+
+}
+
+template <bool U8OUT, int MINBLOCKS>
+__global__ void __launch_bounds__(kThreads, MINBLOCKS)
+letterbox_kernel(const uint8_t* __restrict__ frames, int64_t frame_bytes, int32_t pitch,
+                 const LbJob* __restrict__ jobs, const LbBlock* __restrict__ blk2job, int blocks_per_frame,
+                 const XCoef* __restrict__ xtab, const YCoef* __restrict__ ytab, int smem_row_words, int frames_aligned16,
+                 float* __restrict__ out_f32, uint8_t* __restrict__ out_u8) {
+    extern __shared__ __align__(16) uint32_t spix[];      // [rows][smem_row_words] pixel words
+    __shared__ YCoef s_y[kTH];                            // vertical coefficients of the block's rows (smem-row relative)
+
+    const int frame = blockIdx.x / blocks_per_frame;
+    const LbBlock bd = blk2job[blockIdx.x - frame * blocks_per_frame];    // two 128-bit loads: everything staging needs
+    const uint32_t packed = bd.packed;
+    const LbJob& job = jobs[packed >> 24];
+    const int oy0 = ((packed >> 12) & 0xfff) * kTH;
+    const int ox0 = (packed & 0xfff) * kTW;
+    const int mode = job.mode, top = job.top, left = job.left, new_w = job.new_w, new_h = job.new_h;
+    const int out_w = job.out_w, out_h = job.out_h, src_w = job.src_w;
+    const XCoef* xt = xtab + job.xtab;
+    const YCoef* yt = ytab + job.ytab;
+    // source window of this block (pixels [gx_lo, sx_hi], rows [sy_lo, sy_hi]); gx_lo is a multiple of 4
+    const bool has_src = (bd.flags & 1) != 0;
+    const int gx_lo = bd.gx_lo, sy_lo = bd.sy_lo;
+
+    lb_prologue<kThreads>(frames, frame, frame_bytes, pitch, bd, has_src, smem_row_words, frames_aligned16, spix, s_y, oy0, top, new_h,
+                          mode, yt, sy_lo);
 
     // ---- one thread per output column, walking down the block's rows: the horizontal result of a
     // source row is kept in registers and reused when the next output row needs the same row.
