@@ -151,13 +151,23 @@ color_features_kernel(const uint8_t* __restrict__ pixels, const hvb_crop_desc* _
         const int rw = max(rc.right - rc.left, 0), rh = max(rc.bottom - rc.top, 0);
         const int npx = rw * rh;
         const uint8_t* base = pixels + cd.offset + (int64_t)rc.top * cd.pitch + (int64_t)rc.left * 3;
-        const float inv_rw = rw > 0 ? 1.0f / (float)rw : 0.0f;
 
         ThreadAcc acc;
         acc.clear();
         // Uniform trip counts for the whole CTA: every thread runs n_iter iterations (tail lanes
         // skip the pixel), so the warp-collective flush is always reached converged.
         const int n_iter = (npx + kThreads - 1) / kThreads;
+        // This thread's pixels are p = tid, tid + 256, ...: (row, column) walk incrementally — 256 = drow * rw + dcol — so
+        // the per-pixel address costs a few adds instead of a float reciprocal multiply, two fix-ups and a 64-bit
+        // multiply-add (SASS of the previous loop: 41 of 168 instructions per pixel were addressing and predication).
+        const int rws = max(rw, 1);
+        const int drow = kThreads / rws, dcol = kThreads - drow * rws;
+        const int64_t step_bytes = (int64_t)drow * cd.pitch + dcol * 3;
+        const int64_t wrap_bytes = (int64_t)cd.pitch - (int64_t)rws * 3;
+        const int row0 = (int)threadIdx.x / rws;
+        int col = (int)threadIdx.x - row0 * rws;
+        const uint8_t* px = base + (int64_t)row0 * cd.pitch + col * 3;
+        const int n_mine = (int)threadIdx.x < npx ? (npx - 1 - (int)threadIdx.x) / kThreads + 1 : 0;
         for (int it0 = 0; it0 < n_iter; it0 += kBatch) {
             const int it1 = min(it0 + kBatch, n_iter);
             // ncu (profiles/r02a_ncu_k3.md): the one-pixel-at-a-time loop spent 4.6 of every 5.9 stall cycles per issue on
@@ -167,16 +177,14 @@ color_features_kernel(const uint8_t* __restrict__ pixels, const hvb_crop_desc* _
                 bool ok[kUnroll];
 #pragma unroll
                 for (int u = 0; u < kUnroll; u++) {
-                    const int p = (it + u) * kThreads + threadIdx.x;
-                    ok[u] = (it + u) < it1 && p < npx;
+                    const bool in_batch = (it + u) < it1;          // the last group of a 255-step batch is partial: the
+                    ok[u] = in_batch && (it + u) < n_mine;         // next batch starts at it1, so the walk must stop there too
                     pb[u] = pg[u] = pr[u] = 0;
-                    if (ok[u]) {
-                        int row = (int)((float)p * inv_rw);
-                        int col = p - row * rw;
-                        if (col < 0) { row--; col += rw; }
-                        if (col >= rw) { row++; col -= rw; }
-                        const uint8_t* px = base + (int64_t)row * cd.pitch + col * 3;
-                        pb[u] = __ldg(px); pg[u] = __ldg(px + 1); pr[u] = __ldg(px + 2);
+                    if (ok[u]) { pb[u] = __ldg(px); pg[u] = __ldg(px + 1); pr[u] = __ldg(px + 2); }
+                    if (in_batch) {
+                        px += step_bytes;
+                        col += dcol;
+                        if (col >= rws) { col -= rws; px += wrap_bytes; }
                     }
                 }
 #pragma unroll
@@ -282,11 +290,19 @@ jersey_color_stats_kernel(const uint8_t* __restrict__ pixels, const hvb_crop_des
         const int rw = max(rc.right - rc.left, 0), rh = max(rc.bottom - rc.top, 0);
         const int npx = rw * rh;
         const uint8_t* base = pixels + cd.offset + (int64_t)rc.top * cd.pitch + (int64_t)rc.left * 3;
-        const float inv_rw = rw > 0 ? 1.0f / (float)rw : 0.0f;
 
         JerseyAcc acc;
         acc.clear();
         const int n_iter = (npx + kThreads - 1) / kThreads;          // uniform trip count, see color_features_kernel
+        // incremental (row, column) walk of this thread's pixels tid, tid + 256, ...: see color_features_kernel
+        const int rws = max(rw, 1);
+        const int drow = kThreads / rws, dcol = kThreads - drow * rws;
+        const int64_t step_bytes = (int64_t)drow * cd.pitch + dcol * 3;
+        const int64_t wrap_bytes = (int64_t)cd.pitch - (int64_t)rws * 3;
+        const int row0 = (int)threadIdx.x / rws;
+        int col = (int)threadIdx.x - row0 * rws;
+        const uint8_t* px = base + (int64_t)row0 * cd.pitch + col * 3;
+        const int n_mine = (int)threadIdx.x < npx ? (npx - 1 - (int)threadIdx.x) / kThreads + 1 : 0;
         for (int it0 = 0; it0 < n_iter; it0 += kBatch) {
             const int it1 = min(it0 + kBatch, n_iter);
             for (int it = it0; it < it1; it += kUnroll) {
@@ -294,16 +310,14 @@ jersey_color_stats_kernel(const uint8_t* __restrict__ pixels, const hvb_crop_des
                 bool ok[kUnroll];
 #pragma unroll
                 for (int u = 0; u < kUnroll; u++) {
-                    const int p = (it + u) * kThreads + threadIdx.x;
-                    ok[u] = (it + u) < it1 && p < npx;
+                    const bool in_batch = (it + u) < it1;          // the last group of a 255-step batch is partial: the
+                    ok[u] = in_batch && (it + u) < n_mine;         // next batch starts at it1, so the walk must stop there too
                     pb[u] = pg[u] = pr[u] = 0;
-                    if (ok[u]) {
-                        int row = (int)((float)p * inv_rw);
-                        int col = p - row * rw;
-                        if (col < 0) { row--; col += rw; }
-                        if (col >= rw) { row++; col -= rw; }
-                        const uint8_t* px = base + (int64_t)row * cd.pitch + col * 3;
-                        pb[u] = __ldg(px); pg[u] = __ldg(px + 1); pr[u] = __ldg(px + 2);
+                    if (ok[u]) { pb[u] = __ldg(px); pg[u] = __ldg(px + 1); pr[u] = __ldg(px + 2); }
+                    if (in_batch) {
+                        px += step_bytes;
+                        col += dcol;
+                        if (col >= rws) { col -= rws; px += wrap_bytes; }
                     }
                 }
 #pragma unroll

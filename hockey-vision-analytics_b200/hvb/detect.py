@@ -140,8 +140,9 @@ class Detector:
         if not all(isinstance(f, np.ndarray) and f.dtype == np.uint8 and f.shape == (h, w, 3) and f.flags.c_contiguous for f in rows):
             return None
         try:
-            srcs = [torch.from_numpy(f) for f in (rows[0], rows[-1])]
-            if not all(t.is_pinned() for t in srcs):
+            if not torch.from_numpy(rows[0]).is_pinned():    # the common case (pageable frames) costs one pointer query
+                return None
+            if not all(torch.from_numpy(f).is_pinned() for f in rows[1:]):
                 return None
         except (RuntimeError, TypeError):                    # read-only arrays etc.: the staged path copes
             return None

@@ -80,7 +80,7 @@ class _TrunkGraph:
                 try:
                     y = self.clf._trunk_forward(x)
                 finally:
-                    g.capture_end()
+                    g.capture_end()                # also ends a capture whose body raised (the error then surfaces here)
         except RuntimeError:
             self.failed = True                 # e.g. a capture already in progress on this thread: stay on the eager forward
             return False

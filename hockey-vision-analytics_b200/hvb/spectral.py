@@ -204,6 +204,9 @@ class DeviceSpectralClustering:
         return self.ops
 
     def fit_predict(self, affinity: torch.Tensor) -> np.ndarray:
+        if self.ops is None and not isinstance(affinity, torch.Tensor):
+            from .runtime import get_context
+            affinity = get_context("cuda:0").to_device(np.asarray(affinity, np.float64))     # loud without a B200
         n = affinity.shape[0]
         emb = None
         if self.solver == "subspace" and n >= SMALL_N and self.n_clusters <= BLOCK - 2:
