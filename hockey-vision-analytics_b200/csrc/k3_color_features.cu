@@ -60,45 +60,78 @@ __device__ __forceinline__ void bgr_to_lab(const ColorTables& t, int b, int g, i
     B = min(max(bb, 0), 255);
 }
 
+// Histograms: one private 32-bit counter per (bin, thread) in shared memory — address (bin * 256 + tid): every lane its
+// own bank whatever the bin, so a flat-colour ROI (all lanes in one bin) costs the same as a random one, and an increment
+// is one address multiply-add + one shared-memory reduction.  (Round 1 kept packed 8-bit counters in registers: ~35
+// instructions per pixel for the three increments; measured 30.1 us against 28.8 us for 768 crops, run r02r.)
+// The same two conversions with the tables addressed through their 32-bit shared-window address (formed once per CTA):
+// through a generic reference the compiler re-derived the window base — S2R SR_CgaCtaId + LEA, twice — for every pixel.
+__device__ __forceinline__ int lds_s32(uint32_t a) { int v; asm("ld.shared.s32 %0, [%1];" : "=r"(v) : "r"(a)); return v; }
+__device__ __forceinline__ int lds_u16(uint32_t a) { uint32_t v; asm("ld.shared.u16 %0, [%1];" : "=r"(v) : "r"(a)); return (int)v; }
+
+__device__ __forceinline__ void bgr_to_hsv(uint32_t tab_sa, int b, int g, int r, int& h, int& s, int& v) {
+    v = max(max(b, g), r);
+    const int vmin = min(min(b, g), r);
+    const int diff = v - vmin;
+    s = (diff * lds_s32(tab_sa + HVB_TAB_SDIV + 4 * v) + (1 << 11)) >> 12;
+    int hh = (v == r) ? (g - b) : (v == g) ? (b - r + 2 * diff) : (r - g + 4 * diff);
+    hh = (hh * lds_s32(tab_sa + HVB_TAB_HDIV + 4 * diff) + (1 << 11)) >> 12;
+    h = hh < 0 ? hh + 180 : hh;
+}
+
+__device__ __forceinline__ void bgr_to_lab(uint32_t tab_sa, int b, int g, int r, int& L, int& A, int& B) {
+    const int R = lds_u16(tab_sa + HVB_TAB_GTAB + 2 * r), G = lds_u16(tab_sa + HVB_TAB_GTAB + 2 * g), Bl = lds_u16(tab_sa + HVB_TAB_GTAB + 2 * b);
+    const int fX = lds_u16(tab_sa + HVB_TAB_CTAB + 2 * ((R * 1777 + G * 1541 + Bl * 778 + (1 << 11)) >> 12));
+    const int fY = lds_u16(tab_sa + HVB_TAB_CTAB + 2 * ((R * 871 + G * 2929 + Bl * 296 + (1 << 11)) >> 12));
+    const int fZ = lds_u16(tab_sa + HVB_TAB_CTAB + 2 * ((R * 73 + G * 448 + Bl * 3575 + (1 << 11)) >> 12));
+    const int l = (296 * fY - 1336934 + (1 << 14)) >> 15;
+    const int a = (500 * (fX - fY) + 128 * 32768 + (1 << 14)) >> 15;
+    const int bb = (200 * (fY - fZ) + 128 * 32768 + (1 << 14)) >> 15;
+    L = min(max(l, 0), 255);
+    A = min(max(a, 0), 255);
+    B = min(max(bb, 0), 255);
+}
+
 struct ThreadAcc {
-    unsigned long long hH0, hH1, hH2, hS, hV;   // packed 8-bit counters
     uint32_t cnt;                               // packed 8-bit: S<30, S>100, white
     uint32_t sum[6];
     uint32_t sq[6];
     __device__ __forceinline__ void clear() {
-        hH0 = hH1 = hH2 = hS = hV = 0ull;
         cnt = 0;
 #pragma unroll
         for (int i = 0; i < 6; i++) { sum[i] = 0; sq[i] = 0; }
     }
 };
 
-__device__ __forceinline__ void accumulate_pixel(const ColorTables& t, ThreadAcc& a, int b, int g, int r) {
+__device__ __forceinline__ void hist_inc(uint32_t shared_addr) {
+    asm volatile("red.shared.add.u32 [%0], 1;" :: "r"(shared_addr) : "memory");
+}
+
+// priv_sa: shared-window address of this thread's counter of bin 0 (formed once per CTA; through a generic pointer the
+// compiler re-derived the window base — two S2R and two LEA — for every pixel)
+__device__ __forceinline__ void accumulate_pixel(uint32_t tab_sa, ThreadAcc& a, uint32_t priv_sa, int b, int g, int r) {
     int h, s, v, L, A, B;
-    bgr_to_hsv(t, b, g, r, h, s, v);
-    bgr_to_lab(t, b, g, r, L, A, B);
-    int hb = (h * 205) >> 11;                      // h / 10 for 0 <= h < 180
-    unsigned long long one = 1ull << ((hb & 7) * 8);
-    a.hH0 += (hb < 8) ? one : 0ull;
-    a.hH1 += (hb >= 8 && hb < 16) ? one : 0ull;
-    a.hH2 += (hb >= 16) ? one : 0ull;
-    a.hS += 1ull << ((s >> 5) * 8);
-    a.hV += 1ull << ((v >> 5) * 8);
+    bgr_to_hsv(tab_sa, b, g, r, h, s, v);
+    bgr_to_lab(tab_sa, b, g, r, L, A, B);
+    const int hb = (h * 205) >> 11;                // h / 10 for 0 <= h < 180
+    hist_inc(priv_sa + (uint32_t)hb * (kThreads * 4));
+    hist_inc(priv_sa + (uint32_t)(18 + (s >> 5)) * (kThreads * 4));
+    hist_inc(priv_sa + (uint32_t)(26 + (v >> 5)) * (kThreads * 4));
     a.cnt += (s < 30 ? 1u : 0u) | (s > 100 ? (1u << 8) : 0u) | ((v > 200 && s < 30) ? (1u << 16) : 0u);
     a.sum[0] += h; a.sum[1] += s; a.sum[2] += v; a.sum[3] += L; a.sum[4] += A; a.sum[5] += B;
     a.sq[0] += h * h; a.sq[1] += s * s; a.sq[2] += v * v; a.sq[3] += L * L; a.sq[4] += A * A; a.sq[5] += B * B;
 }
 
 // Warp-aggregate the per-thread accumulators and add them into the CTA accumulators.
-__device__ __forceinline__ void flush(ThreadAcc& a, uint32_t* s_u32, unsigned long long* s_u64) {
+__device__ __forceinline__ void flush(ThreadAcc& a, uint32_t* __restrict__ priv, uint32_t* s_u32, unsigned long long* s_u64) {
     const unsigned full = 0xffffffffu;
     const int lane = threadIdx.x & 31;
     uint32_t mine0 = 0, mine1 = 0;      // lane k keeps quantity k (first 32) and quantity 32+k
 #pragma unroll
     for (int k = 0; k < 34; k++) {
-        unsigned long long w = (k < 8) ? a.hH0 : (k < 16) ? a.hH1 : (k < 18) ? a.hH2 : (k < 26) ? a.hS : a.hV;
-        int sh = (k < 18) ? (k & 7) : ((k - 18) & 7);
-        uint32_t tot = __reduce_add_sync(full, (uint32_t)(w >> (8 * sh)) & 0xffu);
+        const uint32_t part = priv[k * kThreads];
+        priv[k * kThreads] = 0;
+        uint32_t tot = __reduce_add_sync(full, part);
         if (k < 32) { if (lane == k) mine0 = tot; } else { if (lane == k - 32) mine1 = tot; }
     }
 #pragma unroll
@@ -125,7 +158,7 @@ __device__ __forceinline__ double u128_to_double(unsigned __int128 x) {
 }
 
 #ifndef HVB_K3A_MINBLOCKS
-#define HVB_K3A_MINBLOCKS 5            /* CTAs per SM the register allocation allows: 4 = 59 regs, 5 = 48, 6 = 40 (small spills) */
+#define HVB_K3A_MINBLOCKS 4            /* CTAs per SM the register allocation allows: 4 = up to 64 registers (nothing re-materialised in the pixel loop); 5 = 48, 6 = 40 measured no faster (run r02j) */
 #endif
 __global__ void __launch_bounds__(kThreads, HVB_K3A_MINBLOCKS)
 color_features_kernel(const uint8_t* __restrict__ pixels, const hvb_crop_desc* __restrict__ crops, int n,
@@ -134,6 +167,12 @@ color_features_kernel(const uint8_t* __restrict__ pixels, const hvb_crop_desc* _
     __shared__ __align__(16) ColorTables tab;
     __shared__ uint32_t s_u32[40];
     __shared__ unsigned long long s_u64[kNumU64];
+    __shared__ uint32_t s_priv[34 * kThreads];                  // [bin][thread] private histogram counters (34 KB)
+    uint32_t* priv = s_priv + threadIdx.x;
+    const uint32_t priv_sa = (uint32_t)__cvta_generic_to_shared(priv);
+    const uint32_t tab_sa = (uint32_t)__cvta_generic_to_shared(&tab);
+#pragma unroll
+    for (int k = 0; k < 34; k++) priv[k * kThreads] = 0;        // own column only: no barrier needed
     // the crop descriptor is requested BEFORE the tables: its latency hides behind the 8.5 KB table copy instead of
     // following it (ncu r02d: a quarter of the stall samples sat on the table copy / descriptor / first pixel loads, three
     // dependent global round trips at the head of a CTA that lives ~15 us)
@@ -189,10 +228,10 @@ color_features_kernel(const uint8_t* __restrict__ pixels, const hvb_crop_desc* _
                 }
 #pragma unroll
                 for (int u = 0; u < kUnroll; u++)
-                    if (ok[u]) accumulate_pixel(tab, acc, pb[u], pg[u], pr[u]);
+                    if (ok[u]) accumulate_pixel(tab_sa, acc, priv_sa, pb[u], pg[u], pr[u]);
             }
             __syncwarp();
-            flush(acc, s_u32, s_u64);
+            flush(acc, priv, s_u32, s_u64);
         }
         __syncthreads();
 
@@ -279,6 +318,7 @@ jersey_color_stats_kernel(const uint8_t* __restrict__ pixels, const hvb_crop_des
     __shared__ uint32_t s_u32[32];
     __shared__ unsigned long long s_u64[4];
     load_tables(&tab, tables_dev);
+    const uint32_t tab_sa = (uint32_t)__cvta_generic_to_shared(&tab);
 
     for (int ci = blockIdx.x; ci < n; ci += gridDim.x) {
         if (threadIdx.x < 32) s_u32[threadIdx.x] = 0;
@@ -325,8 +365,8 @@ jersey_color_stats_kernel(const uint8_t* __restrict__ pixels, const hvb_crop_des
                     if (!ok[u]) continue;
                     const int b = pb[u], g = pg[u], r = pr[u];
                     int h, s, v, L, A, B;
-                    bgr_to_hsv(tab, b, g, r, h, s, v);
-                    bgr_to_lab(tab, b, g, r, L, A, B);
+                    bgr_to_hsv(tab_sa, b, g, r, h, s, v);
+                    bgr_to_lab(tab_sa, b, g, r, L, A, B);
                     // np.abs(a - 128) < 10 on uint8 arrays: a < 128 wraps to >= 128, so only 128..137 pass
                     const bool white = (L > 200) && (A >= 128 && A < 138) && (B >= 128 && B < 138);
                     if (white) {
