@@ -508,11 +508,15 @@ def run_hvb(args, rank, world):
     ch = 32 if F >= 64 else F
     clip = [frames[i] for k in range(12) for i in (range(32) if k % 2 == 0 else range(32, 64))] if F >= 64 else [frames[i] for k in range(12) for i in range(F)]
     vpc = VideoProcessor(device=dev, config=Config(), detector=det, team_classifier=path.classifier_router(), tracker=args.tracker)
-    list(vpc.process_video_chunked(clip[:2 * ch], chunk=ch, initialize=False))
+    list(vpc.process_video_chunked(clip[:4 * ch], chunk=ch, initialize=False))
     barrier()
-    t0 = time.perf_counter()
-    n_out = sum(1 for _ in vpc.process_video_chunked(clip, chunk=ch, initialize=False))
-    extra["clip_chunked_drop_in_fps_chunk32"] = n_out / (time.perf_counter() - t0)
+    runs = []
+    for _ in range(3):                      # a 384-frame clip lasts a quarter of a second: median of three passes
+        t0 = time.perf_counter()
+        n_out = sum(1 for _ in vpc.process_video_chunked(clip, chunk=ch, initialize=False))
+        runs.append(n_out / (time.perf_counter() - t0))
+    extra["clip_chunked_drop_in_fps_chunk32"] = float(np.median(runs))
+    extra["clip_chunked_drop_in_fps_chunk32_runs"] = [round(r, 1) for r in runs]
     del vpc
     det.head_hook = None
     if world > 1:                                   # the host-side figures of every rank
