@@ -22,11 +22,20 @@
 #include "hvb_common.cuh"
 
 #include <algorithm>
+#include <type_traits>
 #include <math.h>
 #include <map>
 
-#ifndef HVB_K1_MADHI
-#define HVB_K1_MADHI 0     /* IMAD.HI is half rate on sm_100: measured slower than IMAD + SHF */
+
+// A/B switches of the column loop (run r02v): each defaults to the variant that measured faster
+#ifndef HVB_K1_VERT_IDP
+#define HVB_K1_VERT_IDP 1       /* vertical pass: permute + dp2a (FMA pipe) instead of shift / lea.hi / add / shift (ALU pipe) */
+#endif
+#ifndef HVB_K1_CONV_MAGIC
+#define HVB_K1_CONV_MAGIC 1     /* byte -> float/255 as permute + one FMA instead of extract + I2FP + FMUL */
+#endif
+#ifndef HVB_K1_ADDR32
+#define HVB_K1_ADDR32 1         /* one 32-bit row offset + per-plane base instead of three 64-bit pointer increments */
 #endif
 
 namespace {
@@ -68,6 +77,40 @@ struct __align__(16) YCoef { int32_t r0, r1; int32_t b0, b1; };
 
 __device__ __forceinline__ float u8_over_255(int v) {
     return __fmul_rz(__int2float_rn(v), 0x1.010102p-8f);   // == float(v) / 255.0f for 0 <= v <= 255
+}
+
+// float(byte SEL of w) / 255 without an int->float conversion or a shift: a byte permute drops the byte into the
+// mantissa of 2^23 (0x4B0000vv == 8388608 + v), and ONE fused multiply-add rounded toward zero removes the offset:
+// (2^23 + v) * k - 2^23 * k == v * k exactly inside the FMA (2^23 * k is a power-of-two multiple of k, hence
+// representable), so the result is bit for bit u8_over_255(v).  One ALU-pipe + one FMA-pipe instruction per value
+// instead of three ALU-pipe ones (extract, I2FP, and the 64-bit pointer arithmetic it competed with).
+template <int SEL>
+__device__ __forceinline__ float byte_over_255(uint32_t w) {
+#if HVB_K1_CONV_MAGIC
+    const uint32_t bits = __byte_perm(w, 0x4B000000u, 0x7540 | SEL);
+    return __fmaf_rz(__uint_as_float(bits), 0x1.010102p-8f, -0x1.010102p+15f);
+#else
+    return u8_over_255((int)((w >> (8 * SEL)) & 255u));
+#endif
+}
+
+// Same for a word that already carries 0x4B in byte 3 and zero in byte 2 (the vertical pass below builds it that way
+// for free through the dp2a accumulator): a one-source permute with an immediate selector.
+__device__ __forceinline__ float magic_byte1_over_255(uint32_t w) {
+#if HVB_K1_CONV_MAGIC
+    return __fmaf_rz(__uint_as_float(__byte_perm(w, w, 0x3221)), 0x1.010102p-8f, -0x1.010102p+15f);
+#else
+    return u8_over_255((int)((w >> 8) & 255u));
+#endif
+}
+
+__device__ __forceinline__ void stg_f32(float* base, uint32_t byte_off, float v) {
+    // base + byte_off with a 32-bit offset: the compiler forms the address with one carry add per store instead of
+    // carrying three 64-bit pointers through the loop.  (An inline-asm st.global here — volatile, so ordered against
+    // the volatile shared-memory loads of the next row — cost 23 % on the whole kernel, run r02u.)
+    float* p = reinterpret_cast<float*>(reinterpret_cast<char*>(base) + byte_off);
+    __builtin_assume(__isGlobal(p));
+    *p = v;
 }
 
 // Horizontal 2-tap filter of one source row for this thread's column: three dp2a, pre-shifted by 4
@@ -142,6 +185,9 @@ __device__ __forceinline__ void lb_prologue(const uint8_t* __restrict__ frames, 
                     for (int t = 0; t < 4; t++) {
                         const uint32_t a = w[3 * t], b = w[3 * t + 1], c = w[3 * t + 2];
                         uint4 o;
+                        // The column loop never reads byte 3 of a pixel word, but the masks stay: without them the first
+                        // word of a group is a plain register copy that the compiler scheduled straight after its load,
+                        // stalling the thread before the loads of its next two items were issued (run r02v: +16 %).
                         o.x = a & 0x00ffffffu;
                         o.y = __byte_perm(a, b, 0x0543) & 0x00ffffffu;
                         o.z = __byte_perm(b, c, 0x0432) & 0x00ffffffu;
@@ -184,9 +230,11 @@ __device__ __forceinline__ void lb_prologue(const uint8_t* __restrict__ frames, 
                 if (!live[k]) continue;
                 uint4 w;
                 if (fast[k]) {
-                    w.x = a[k] & 0x00ffffffu;                              // B0 G0 R0
-                    w.y = __byte_perm(a[k], b[k], 0x0543) & 0x00ffffffu;   // a.b3 b.b0 b.b1
-                    w.z = __byte_perm(b[k], c[k], 0x0432) & 0x00ffffffu;   // b.b2 b.b3 c.b0
+                    // byte 3 of a pixel word is never read by the column loop, so it is not cleared on this path (the
+                    // 32-bit loads land directly in the registers of the 128-bit store: no copy, unlike the path above)
+                    w.x = a[k];                                            // B0 G0 R0 (+ B1)
+                    w.y = __byte_perm(a[k], b[k], 0x0543);                 // a.b3 b.b0 b.b1 (+ b.b2)
+                    w.z = __byte_perm(b[k], c[k], 0x0432);                 // b.b2 b.b3 c.b0 (+ c.b1)
                     w.w = c[k] >> 8;                                       // c.b1 c.b2 c.b3
                 } else {                                                   // unaligned tile or the end of a frame row
                     uint32_t v[4];
@@ -211,7 +259,6 @@ __device__ __forceinline__ void lb_prologue(const uint8_t* __restrict__ frames, 
             else if (mode == MODE_AREA2) { yc.r0 = 2 * dy - sy_lo; yc.r1 = yc.r0 + 1; }
             else { yc.r0 = dy - sy_lo; yc.r1 = yc.r0; }
             yc.r0 *= 4 * smem_row_words; yc.r1 *= 4 * smem_row_words;      // byte offsets of the two source rows
-            yc.b0 <<= 16; yc.b1 <<= 16;                                    // so that umulhi(b, h) == (b * h) >> 16
         }
         s_y[threadIdx.x] = yc;
     }
@@ -286,36 +333,62 @@ letterbox_kernel(const uint8_t* __restrict__ frames, int64_t frame_bytes, int32_
     // so that the 64-byte-strided 128-bit staging stores of a quarter-warp fall into distinct banks
     const uint32_t a0 = (uint32_t)__cvta_generic_to_shared(spix) + 4u * ((uint32_t)i0 ^ ((((uint32_t)i0 >> 5) & 3u) << 2));
     const uint32_t a1 = (uint32_t)__cvta_generic_to_shared(spix) + 4u * ((uint32_t)i1 ^ ((((uint32_t)i1 >> 5) & 3u) << 2));
-    float* q0 = U8OUT ? nullptr : tile_f32 + o;             // R plane, then +plane, +2*plane
+    // Output addressing: three plane bases (R, G, B = source channels 2, 1, 0) and ONE 32-bit byte offset that
+    // advances by a row per iteration; each store address is a single IMAD.WIDE (see stg_f32).
+#if HVB_K1_ADDR32
+    float* const q0 = U8OUT ? nullptr : tile_f32;
+    float* const q1 = U8OUT ? nullptr : q0 + plane;
+    float* const q2 = U8OUT ? nullptr : q1 + plane;
+    uint32_t ob = 4u * (uint32_t)o;
+    const uint32_t ob_step = 4u * (uint32_t)out_w;
+#else
+    float* q0 = U8OUT ? nullptr : tile_f32 + o;
     float* q1 = U8OUT ? nullptr : q0 + plane;
     float* q2 = U8OUT ? nullptr : q1 + plane;
+    constexpr uint32_t ob = 0;
+#endif
+    auto next_row = [&]() {
+#if HVB_K1_ADDR32
+        ob += ob_step;
+#else
+        q0 += out_w; q1 += out_w; q2 += out_w;
+#endif
+    };
     uint8_t* q8 = U8OUT ? tile_u8 + 3 * o : nullptr;
 
-    auto emit = [&](int vb, int vg, int vr) {
+    // one output pixel whose channel values are bytes SB / SG / SR of the words wb / wg / wr
+    auto emit = [&](uint32_t wb, auto sb, uint32_t wg, auto sg, uint32_t wr, auto sr) {
+        constexpr int SB = decltype(sb)::value, SG = decltype(sg)::value, SR = decltype(sr)::value;
         if (U8OUT) {
-            q8[0] = (uint8_t)vb; q8[1] = (uint8_t)vg; q8[2] = (uint8_t)vr;
+            q8[0] = (uint8_t)(wb >> (8 * SB)); q8[1] = (uint8_t)(wg >> (8 * SG)); q8[2] = (uint8_t)(wr >> (8 * SR));
             q8 += 3 * out_w;
         } else {
-            *q0 = u8_over_255(vr); *q1 = u8_over_255(vg); *q2 = u8_over_255(vb);
-            q0 += out_w; q1 += out_w; q2 += out_w;
+            stg_f32(q0, ob, byte_over_255<SR>(wr));
+            stg_f32(q1, ob, byte_over_255<SG>(wg));
+            stg_f32(q2, ob, byte_over_255<SB>(wb));
+            next_row();
         }
     };
+    using B0 = std::integral_constant<int, 0>;
+    using B1 = std::integral_constant<int, 1>;
+    using B2 = std::integral_constant<int, 2>;
 
     if (mode == MODE_COPY) {
 #pragma unroll 4
         for (int j = ja; j < jb; j++) {
             const uint32_t p = lds32(a0 + (uint32_t)s_y[j].r0);
-            emit(p & 255, (p >> 8) & 255, p >> 16);
+            emit(p, B0{}, p, B1{}, p, B2{});
         }
     } else if (mode == MODE_AREA2) {
 #pragma unroll 4
         for (int j = ja; j < jb; j++) {
             const YCoef yc = s_y[j];
             const uint32_t p00 = lds32(a0 + yc.r0), p01 = lds32(a1 + yc.r0), p10 = lds32(a0 + yc.r1), p11 = lds32(a1 + yc.r1);
-            // B and R ride in the two 16-bit lanes of one word, G in another
+            // B and R ride in the two 16-bit lanes of one word, G in another; (sum + 2) >> 2 lands in bytes 0 / 2
+            // after the shift (lane sums <= 1022: ten bits, the upper eight are the value)
             const uint32_t br = (p00 & 0x00ff00ffu) + (p01 & 0x00ff00ffu) + (p10 & 0x00ff00ffu) + (p11 & 0x00ff00ffu) + 0x00020002u;
             const uint32_t gg = ((p00 >> 8) & 255) + ((p01 >> 8) & 255) + ((p10 >> 8) & 255) + ((p11 >> 8) & 255) + 2;
-            emit((br >> 2) & 255, gg >> 2, (br >> 18) & 255);
+            emit(br >> 2, B0{}, gg >> 2, B0{}, br >> 2, B2{});
         }
     } else {
         uint32_t ph[3] = {0u, 0u, 0u};
@@ -332,17 +405,30 @@ letterbox_kernel(const uint8_t* __restrict__ frames, int64_t frame_bytes, int32_
             lb_hrow(lds32(a0 + yc.r1), lds32(a1 + yc.r1), apk, h1);
             ph[0] = h1[0]; ph[1] = h1[1]; ph[2] = h1[2];
             prev_r1 = yc.r1;
-            const uint32_t b0 = (uint32_t)yc.b0, b1 = (uint32_t)yc.b1;     // coefficients << 16
-            // OpenCV vertical pass: ((b0*(H0>>4))>>16) + ((b1*(H1>>4))>>16) + 2 >> 2, as two mad.hi per channel
-#if HVB_K1_MADHI
-            emit((int)((__umulhi(b1, h1[0]) + (__umulhi(b0, h0[0]) + 2u)) >> 2),
-                 (int)((__umulhi(b1, h1[1]) + (__umulhi(b0, h0[1]) + 2u)) >> 2),
-                 (int)((__umulhi(b1, h1[2]) + (__umulhi(b0, h0[2]) + 2u)) >> 2));
+            const uint32_t c0 = (uint32_t)yc.b0, c1 = (uint32_t)yc.b1;
+            // OpenCV vertical pass: (((c0*(H0>>4))>>16) + ((c1*(H1>>4))>>16) + 2) >> 2.  The "+2" rides on the first
+            // product as 2<<16 (no carry into it: products < 2^27), one byte permute pairs the two upper halves, and a
+            // dp2a by (64, 64) adds them AND moves the final ">>2" to a byte boundary: the pixel value is byte 1 of the
+            // result (64 * sum <= 64 * 1022 < 2^16; the accumulator plants the 2^23 exponent byte for the float path).  Per channel: 2 IMAD + 1 IDP on the FMA pipe, 1 PRMT on the ALU pipe.
+#if HVB_K1_VERT_IDP
+            uint32_t v[3];
+#pragma unroll
+            for (int c = 0; c < 3; c++) {
+                const uint32_t hi2 = __byte_perm(c0 * h0[c] + 0x20000u, c1 * h1[c], 0x7632);
+                v[c] = __dp2a_lo(hi2, 0x4040u, (U8OUT || !HVB_K1_CONV_MAGIC) ? 0u : 0x4B000000u);
+            }
+            if (U8OUT) {
+                emit(v[0], B1{}, v[1], B1{}, v[2], B1{});
+            } else {                                      // byte 3 = 0x4B, byte 2 = 0, byte 1 = the value
+                stg_f32(q0, ob, magic_byte1_over_255(v[2]));
+                stg_f32(q1, ob, magic_byte1_over_255(v[1]));
+                stg_f32(q2, ob, magic_byte1_over_255(v[0]));
+                next_row();
+            }
 #else
-            const uint32_t c0 = b0 >> 16, c1 = b1 >> 16;
-            emit((int)((((c0 * h0[0]) >> 16) + ((c1 * h1[0]) >> 16) + 2u) >> 2),
-                 (int)((((c0 * h0[1]) >> 16) + ((c1 * h1[1]) >> 16) + 2u) >> 2),
-                 (int)((((c0 * h0[2]) >> 16) + ((c1 * h1[2]) >> 16) + 2u) >> 2));
+            emit((((c0 * h0[0]) >> 16) + ((c1 * h1[0]) >> 16) + 2u) >> 2, B0{},
+                 (((c0 * h0[1]) >> 16) + ((c1 * h1[1]) >> 16) + 2u) >> 2, B0{},
+                 (((c0 * h0[2]) >> 16) + ((c1 * h1[2]) >> 16) + 2u) >> 2, B0{});
 #endif
         }
     }
