@@ -18,7 +18,9 @@
 // so that afterwards one LDS.32 fetches a whole pixel.  The 2-tap horizontal filter of a channel is
 // then ONE dp2a (two 16-bit coefficients x two 8-bit samples) after a byte permute that pairs the
 // samples of the two taps; every thread owns ONE output column and walks down the 16 rows of the block,
-// reusing the horizontal result of a source row shared by consecutive output rows; a warp writes 128 contiguous bytes per plane per row.
+// reusing the horizontal result of a source row shared by consecutive output rows; a warp writes 128 contiguous bytes per
+// plane per row.  The vertical pass and the byte -> float conversion are arranged so that their work sits on the FMA pipe
+// (IMAD, IDP.2A, FFMA) rather than on the ALU pipe the shifts of OpenCV's rounding rule would otherwise saturate.
 #include "hvb_common.cuh"
 
 #include <algorithm>
@@ -26,17 +28,6 @@
 #include <math.h>
 #include <map>
 
-
-// A/B switches of the column loop (run r02v): each defaults to the variant that measured faster
-#ifndef HVB_K1_VERT_IDP
-#define HVB_K1_VERT_IDP 1       /* vertical pass: permute + dp2a (FMA pipe) instead of shift / lea.hi / add / shift (ALU pipe) */
-#endif
-#ifndef HVB_K1_CONV_MAGIC
-#define HVB_K1_CONV_MAGIC 1     /* byte -> float/255 as permute + one FMA instead of extract + I2FP + FMUL */
-#endif
-#ifndef HVB_K1_ADDR32
-#define HVB_K1_ADDR32 1         /* one 32-bit row offset + per-plane base instead of three 64-bit pointer increments */
-#endif
 
 namespace {
 
@@ -83,25 +74,17 @@ __device__ __forceinline__ float u8_over_255(int v) {
 // mantissa of 2^23 (0x4B0000vv == 8388608 + v), and ONE fused multiply-add rounded toward zero removes the offset:
 // (2^23 + v) * k - 2^23 * k == v * k exactly inside the FMA (2^23 * k is a power-of-two multiple of k, hence
 // representable), so the result is bit for bit u8_over_255(v).  One ALU-pipe + one FMA-pipe instruction per value
-// instead of three ALU-pipe ones (extract, I2FP, and the 64-bit pointer arithmetic it competed with).
+// instead of an extract, an I2FP and an FMUL (the A/B of the pieces is in profiles/r02w_k1_variants.md).
 template <int SEL>
 __device__ __forceinline__ float byte_over_255(uint32_t w) {
-#if HVB_K1_CONV_MAGIC
     const uint32_t bits = __byte_perm(w, 0x4B000000u, 0x7540 | SEL);
     return __fmaf_rz(__uint_as_float(bits), 0x1.010102p-8f, -0x1.010102p+15f);
-#else
-    return u8_over_255((int)((w >> (8 * SEL)) & 255u));
-#endif
 }
 
 // Same for a word that already carries 0x4B in byte 3 and zero in byte 2 (the vertical pass below builds it that way
 // for free through the dp2a accumulator): a one-source permute with an immediate selector.
 __device__ __forceinline__ float magic_byte1_over_255(uint32_t w) {
-#if HVB_K1_CONV_MAGIC
     return __fmaf_rz(__uint_as_float(__byte_perm(w, w, 0x3221)), 0x1.010102p-8f, -0x1.010102p+15f);
-#else
-    return u8_over_255((int)((w >> 8) & 255u));
-#endif
 }
 
 __device__ __forceinline__ void stg_f32(float* base, uint32_t byte_off, float v) {
@@ -113,14 +96,14 @@ __device__ __forceinline__ void stg_f32(float* base, uint32_t byte_off, float v)
     *p = v;
 }
 
-// Horizontal 2-tap filter of one source row for this thread's column: three dp2a, pre-shifted by 4
-// like OpenCV's vertical pass expects.
 __device__ __forceinline__ uint32_t lds32(uint32_t shared_byte_addr) {
     uint32_t v;
     asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(shared_byte_addr));
     return v;
 }
 
+// Horizontal 2-tap filter of one source row for this thread's column: three dp2a, pre-shifted by 4
+// like OpenCV's vertical pass expects.
 __device__ __forceinline__ void lb_hrow(uint32_t p0, uint32_t p1, uint32_t apk, uint32_t (&h)[3]) {
     const uint32_t bg = __byte_perm(p0, p1, 0x5140), rr = __byte_perm(p0, p1, 0x0062);
     h[0] = __dp2a_lo(apk, bg, 0u) >> 4;
@@ -334,26 +317,13 @@ letterbox_kernel(const uint8_t* __restrict__ frames, int64_t frame_bytes, int32_
     const uint32_t a0 = (uint32_t)__cvta_generic_to_shared(spix) + 4u * ((uint32_t)i0 ^ ((((uint32_t)i0 >> 5) & 3u) << 2));
     const uint32_t a1 = (uint32_t)__cvta_generic_to_shared(spix) + 4u * ((uint32_t)i1 ^ ((((uint32_t)i1 >> 5) & 3u) << 2));
     // Output addressing: three plane bases (R, G, B = source channels 2, 1, 0) and ONE 32-bit byte offset that
-    // advances by a row per iteration; each store address is a single IMAD.WIDE (see stg_f32).
-#if HVB_K1_ADDR32
+    // advances by a row per iteration; each store address costs one IADD3 + one IMAD.X (see stg_f32).
     float* const q0 = U8OUT ? nullptr : tile_f32;
     float* const q1 = U8OUT ? nullptr : q0 + plane;
     float* const q2 = U8OUT ? nullptr : q1 + plane;
     uint32_t ob = 4u * (uint32_t)o;
     const uint32_t ob_step = 4u * (uint32_t)out_w;
-#else
-    float* q0 = U8OUT ? nullptr : tile_f32 + o;
-    float* q1 = U8OUT ? nullptr : q0 + plane;
-    float* q2 = U8OUT ? nullptr : q1 + plane;
-    constexpr uint32_t ob = 0;
-#endif
-    auto next_row = [&]() {
-#if HVB_K1_ADDR32
-        ob += ob_step;
-#else
-        q0 += out_w; q1 += out_w; q2 += out_w;
-#endif
-    };
+    auto next_row = [&]() { ob += ob_step; };
     uint8_t* q8 = U8OUT ? tile_u8 + 3 * o : nullptr;
 
     // one output pixel whose channel values are bytes SB / SG / SR of the words wb / wg / wr
@@ -409,13 +379,14 @@ letterbox_kernel(const uint8_t* __restrict__ frames, int64_t frame_bytes, int32_
             // OpenCV vertical pass: (((c0*(H0>>4))>>16) + ((c1*(H1>>4))>>16) + 2) >> 2.  The "+2" rides on the first
             // product as 2<<16 (no carry into it: products < 2^27), one byte permute pairs the two upper halves, and a
             // dp2a by (64, 64) adds them AND moves the final ">>2" to a byte boundary: the pixel value is byte 1 of the
-            // result (64 * sum <= 64 * 1022 < 2^16; the accumulator plants the 2^23 exponent byte for the float path).  Per channel: 2 IMAD + 1 IDP on the FMA pipe, 1 PRMT on the ALU pipe.
-#if HVB_K1_VERT_IDP
+            // result (64 * sum <= 64 * 1022 < 2^16; the accumulator plants the 2^23 exponent byte for the float path).
+            // Per channel: 2 IMAD + 1 IDP on the FMA pipe and 1 PRMT on the ALU pipe, instead of SHF, LEA.HI, VIADD, SHF on
+            // the ALU pipe (ncu on the round-1 loop: ALU pipe 71 % busy; run r02w: -3 % alone, 0.74 -> 0.79 in the step).
             uint32_t v[3];
 #pragma unroll
             for (int c = 0; c < 3; c++) {
                 const uint32_t hi2 = __byte_perm(c0 * h0[c] + 0x20000u, c1 * h1[c], 0x7632);
-                v[c] = __dp2a_lo(hi2, 0x4040u, (U8OUT || !HVB_K1_CONV_MAGIC) ? 0u : 0x4B000000u);
+                v[c] = __dp2a_lo(hi2, 0x4040u, U8OUT ? 0u : 0x4B000000u);
             }
             if (U8OUT) {
                 emit(v[0], B1{}, v[1], B1{}, v[2], B1{});
@@ -425,11 +396,6 @@ letterbox_kernel(const uint8_t* __restrict__ frames, int64_t frame_bytes, int32_
                 stg_f32(q2, ob, magic_byte1_over_255(v[0]));
                 next_row();
             }
-#else
-            emit((((c0 * h0[0]) >> 16) + ((c1 * h1[0]) >> 16) + 2u) >> 2, B0{},
-                 (((c0 * h0[1]) >> 16) + ((c1 * h1[1]) >> 16) + 2u) >> 2, B0{},
-                 (((c0 * h0[2]) >> 16) + ((c1 * h1[2]) >> 16) + 2u) >> 2, B0{});
-#endif
         }
     }
 }
