@@ -12,7 +12,7 @@
 // exhaustively on the host and again by tests/test_gpu_letterbox.py).
 //
 // One launch covers a chunk of frames: grid = blocks_per_frame x n_frames.  Each CTA produces an
-// 16-row x 256-column block of one tile's output.  It first stages the source pixels the block
+// 16-row x 128-column block of one tile's output.  It first stages the source pixels the block
 // needs into shared memory AS 32-BIT PIXEL WORDS (B | G<<8 | R<<16): 4-pixel groups are fetched
 // with three aligned 32-bit loads and re-packed with byte permutes into one 128-bit shared store,
 // so that afterwards one LDS.32 fetches a whole pixel.  The 2-tap horizontal filter of a channel is
@@ -34,9 +34,13 @@ namespace {
 #ifndef HVB_K1_TH
 #define HVB_K1_TH 16
 #endif
+#ifndef HVB_K1_TW
+#define HVB_K1_TW 128           /* run r02x: 128 x 16 blocks against 256 x 16 — K1b 479 vs 523 us per 16 4K frames (a 640-wide tile is
+                                   five 128-column blocks but two and a HALF 256-column ones), K1a 186 vs 189 us; 8 / 32 rows measured slower */
+#endif
 constexpr int kTH = HVB_K1_TH;  // output rows per CTA
-constexpr int kTW = 256;        // output columns per CTA
-constexpr int kThreads = 256;   // one thread per output column of the block
+constexpr int kTW = HVB_K1_TW;  // output columns per CTA
+constexpr int kThreads = kTW;   // one thread per output column of the block
 
 enum { MODE_COPY = 0, MODE_LINEAR = 1, MODE_AREA2 = 2 };
 
@@ -250,7 +254,7 @@ __device__ __forceinline__ void lb_prologue(const uint8_t* __restrict__ frames, 
 }
 
 template <bool U8OUT, int MINBLOCKS>
-__global__ void __launch_bounds__(kThreads, MINBLOCKS)
+__global__ void __launch_bounds__(kThreads, MINBLOCKS * 256 / kThreads)     // MINBLOCKS counts 256-thread CTAs
 letterbox_kernel(const uint8_t* __restrict__ frames, int64_t frame_bytes, int32_t pitch,
                  const LbJob* __restrict__ jobs, const LbBlock* __restrict__ blk2job, int blocks_per_frame,
                  const XCoef* __restrict__ xtab, const YCoef* __restrict__ ytab, int smem_row_words, int frames_aligned16,
