@@ -26,6 +26,7 @@
 #include <algorithm>
 #include <type_traits>
 #include <math.h>
+#include <stdlib.h>
 #include <map>
 
 
@@ -464,7 +465,6 @@ struct hvb_lb_plan {
     int tiles_per_frame = 0;
     int blocks_per_frame = 0;
     int smem_row_stride = 0, smem_bytes = 0;
-    bool resize_heavy = false;           // most output pixels come from LINEAR/AREA2 jobs
     int64_t out_elems = 0, read_bytes = 0, write_bytes = 0;
     void* dev = nullptr;                  // one allocation: jobs | blk2job | xtab | ytab
     LbJob* jobs_dev = nullptr;
@@ -627,15 +627,6 @@ int hvb_lb_plan_create(hvb_ctx* ctx, int n_frames, int frame_h, int frame_w, int
     p->read_bytes = std::min<int64_t>(p->read_bytes, (int64_t)frame_h * frame_w * 3) * n_frames;
     p->write_bytes *= n_frames;
     p->blocks_per_frame = (int)blk.size();
-    {
-        int64_t px_resize = 0, px_all = 0;
-        for (int t = 0; t < T; t++) {
-            const int64_t px = (int64_t)geo[t].out_h * geo[t].out_w;
-            px_all += px;
-            if (jobs[t].mode != MODE_COPY) px_resize += px;
-        }
-        p->resize_heavy = 2 * px_resize > px_all;
-    }
     p->smem_row_stride = (max_span + 15) & ~15;                        // pixel words per staged row: whole 16-word groups (the bank swizzle permutes chunks inside a group)
     p->smem_bytes = p->smem_row_stride * max_rows * 4;
     if (p->smem_bytes > ctx->max_smem_optin - 1024) {
@@ -686,7 +677,6 @@ int hvb_lb_plan_create(hvb_ctx* ctx, int n_frames, int frame_h, int frame_w, int
     p->ytab_dev = (YCoef*)((uint8_t*)p->dev + o_y);
     if (p->smem_bytes > 48 * 1024) {
         HVB_CUDA(cudaFuncSetAttribute(letterbox_kernel<false, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, p->smem_bytes));
-        HVB_CUDA(cudaFuncSetAttribute(letterbox_kernel<false, 5>, cudaFuncAttributeMaxDynamicSharedMemorySize, p->smem_bytes));
         HVB_CUDA(cudaFuncSetAttribute(letterbox_kernel<true, 5>, cudaFuncAttributeMaxDynamicSharedMemorySize, p->smem_bytes));
     }
     *out_plan = p;
@@ -749,18 +739,15 @@ static int lb_run(hvb_lb_plan* p, const uint8_t* frames_dev, float* out_f32, uin
     const int grid = p->blocks_per_frame * p->n_frames;
     const int64_t frame_bytes = (int64_t)p->frame_h * p->frame_w * 3;
     const int al16 = (((uintptr_t)frames_dev & 15) == 0) ? 1 : 0;
-    // Resize-heavy plans (whole-frame letterbox) run best with 64 registers / 4 CTAs per SM; copy-dominated
-    // slice plans with 51 registers / 5 CTAs per SM (measured on B200, see profiles/).
+    // 64 registers / eight 128-thread CTAs per SM for every float32 plan.  (With 256-thread blocks the copy-dominated slice
+    // plans ran best at 48 registers / 5 CTAs per SM; with 128-thread blocks 64 registers win for both kinds — run r02y:
+    // K1b 479 -> 463 us per 16 4K frames, K1a 186 against 221 us with the 48-register build.)
     if (out_u8)
         letterbox_kernel<true, 5><<<grid, kThreads, p->smem_bytes, ctx->stream>>>(
             frames_dev, frame_bytes, p->frame_w * 3, p->jobs_dev, p->blk2job_dev, p->blocks_per_frame, p->xtab_dev,
             p->ytab_dev, p->smem_row_stride, al16, nullptr, out_u8);
-    else if (p->resize_heavy)
-        letterbox_kernel<false, 4><<<grid, kThreads, p->smem_bytes, ctx->stream>>>(
-            frames_dev, frame_bytes, p->frame_w * 3, p->jobs_dev, p->blk2job_dev, p->blocks_per_frame, p->xtab_dev,
-            p->ytab_dev, p->smem_row_stride, al16, out_f32, nullptr);
     else
-        letterbox_kernel<false, 5><<<grid, kThreads, p->smem_bytes, ctx->stream>>>(
+        letterbox_kernel<false, 4><<<grid, kThreads, p->smem_bytes, ctx->stream>>>(
             frames_dev, frame_bytes, p->frame_w * 3, p->jobs_dev, p->blk2job_dev, p->blocks_per_frame, p->xtab_dev,
             p->ytab_dev, p->smem_row_stride, al16, out_f32, nullptr);
     HVB_LAUNCHED(ctx);
