@@ -39,6 +39,7 @@ namespace {
 #define HVB_K1_TW 128           /* run r02x: 128 x 16 blocks against 256 x 16 — K1b 479 vs 523 us per 16 4K frames (a 640-wide tile is
                                    five 128-column blocks but two and a HALF 256-column ones), K1a 186 vs 189 us; 8 / 32 rows measured slower */
 #endif
+constexpr int kRowUnroll = 4;   // rows of the column loop unrolled together (2 / 16 measured the same, 8 spills: run r02za)
 constexpr int kTH = HVB_K1_TH;  // output rows per CTA
 constexpr int kTW = HVB_K1_TW;  // output columns per CTA
 constexpr int kThreads = kTW;   // one thread per output column of the block
@@ -349,13 +350,13 @@ letterbox_kernel(const uint8_t* __restrict__ frames, int64_t frame_bytes, int32_
     using B2 = std::integral_constant<int, 2>;
 
     if (mode == MODE_COPY) {
-#pragma unroll 4
+#pragma unroll kRowUnroll
         for (int j = ja; j < jb; j++) {
             const uint32_t p = lds32(a0 + (uint32_t)s_y[j].r0);
             emit(p, B0{}, p, B1{}, p, B2{});
         }
     } else if (mode == MODE_AREA2) {
-#pragma unroll 4
+#pragma unroll kRowUnroll
         for (int j = ja; j < jb; j++) {
             const YCoef yc = s_y[j];
             const uint32_t p00 = lds32(a0 + yc.r0), p01 = lds32(a1 + yc.r0), p10 = lds32(a0 + yc.r1), p11 = lds32(a1 + yc.r1);
@@ -368,7 +369,7 @@ letterbox_kernel(const uint8_t* __restrict__ frames, int64_t frame_bytes, int32_
     } else {
         uint32_t ph[3] = {0u, 0u, 0u};
         int prev_r1 = -1;
-#pragma unroll 4
+#pragma unroll kRowUnroll
         for (int j = ja; j < jb; j++) {
             const YCoef yc = s_y[j];
             uint32_t h0[3], h1[3];
