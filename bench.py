@@ -503,6 +503,16 @@ def run_hvb(args, rank, world):
         for _ in range(20):
             vpf.process_frame(frames[0])
         extra["frame_at_a_time_process_frame_fps_" + tag] = 20 / (time.perf_counter() - t0)
+        if args.profile_dropin and flag:
+            import cProfile, io, pstats
+            pf = cProfile.Profile()
+            pf.enable()
+            for _ in range(20):
+                vpf.process_frame(frames[0])
+            pf.disable()
+            buf = io.StringIO()
+            pstats.Stats(pf, stream=buf).sort_stats("cumulative").print_stats(60)
+            print("==== process_frame x20 (cuda graph)\n" + buf.getvalue(), file=sys.stderr)
         del vpf
     det.cuda_graph = False
     # the drop-in at its default chunk of 32 frames
@@ -513,10 +523,24 @@ def run_hvb(args, rank, world):
     list(vpc.process_video_chunked(clip[:4 * ch], chunk=ch, initialize=False))
     barrier()
     runs = []
+    prof = None
+    if args.profile_dropin:                 # host-side profile of the drop-in's main thread (tools: where the 2x against e2e goes)
+        import cProfile
+        prof = cProfile.Profile()
     for _ in range(3):                      # a 384-frame clip lasts a quarter of a second: median of three passes
         t0 = time.perf_counter()
+        if prof is not None:
+            prof.enable()
         n_out = sum(1 for _ in vpc.process_video_chunked(clip, chunk=ch, initialize=False))
+        if prof is not None:
+            prof.disable()
         runs.append(n_out / (time.perf_counter() - t0))
+    if prof is not None:
+        import io, pstats
+        buf = io.StringIO()
+        pstats.Stats(prof, stream=buf).sort_stats("cumulative").print_stats(45)
+        pstats.Stats(prof, stream=buf).sort_stats("tottime").print_stats(30)
+        print(buf.getvalue(), file=sys.stderr)
     extra["clip_chunked_drop_in_fps_chunk32"] = float(np.median(runs))
     extra["clip_chunked_drop_in_fps_chunk32_runs"] = [round(r, 1) for r in runs]
     del vpc
@@ -801,6 +825,7 @@ def main():
     ap.add_argument("--no-c1", dest="with_c1", action="store_false")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--profile-4k", action="store_true", help="with --profile-region: bracket the eager 4K sliced steps instead of the 1080p steps")
+    ap.add_argument("--profile-dropin", action="store_true", help="cProfile of the main thread over the timed process_video_chunked passes (to stderr)")
     ap.add_argument("--profile-region", action="store_true", help="cudaProfilerStart/Stop around the timed device steps (for ncu --profile-from-start off)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "hvb" else args.warmup
