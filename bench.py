@@ -415,7 +415,11 @@ def run_hvb(args, rank, world):
             run_e2e(1, src)
         return world * F * args.steps / (ms / 1e3)
 
-    fps_e2e = timed_e2e(frames_p)
+    # three passes of K steps each, the median reported: on the shared GPU boxes one pass in three or four loses up to half
+    # its rate to something outside the process (same library, same box, back to back: 714 / 1676 frames/s in run r02za) while
+    # the device-timed figure does not move; every pass is listed in extra.e2e_passes_fps
+    e2e_passes = [timed_e2e(frames_p) for _ in range(3)]
+    fps_e2e = float(np.median(e2e_passes))
     fps_e2e_pageable = timed_e2e(frames)
     md = det.max_det
     n_team = int(round(per_frame["team_classified_per_frame"] * F))
@@ -487,8 +491,8 @@ def run_hvb(args, rank, world):
     del trk
 
     extra = {"fit": fit, "gpu_stage_ms_per_frame": gpu_stage_ms, "per_frame": per_frame, "tracker": args.tracker,
-             "e2e_source": "frames in page-locked host memory, one H2D copy per chunk straight from them (no staging copy)",
-             "e2e_from_pageable_frames_fps": fps_e2e_pageable, "staging_threads": det.staging_threads,
+             "e2e_source": "frames in page-locked host memory, one H2D copy per chunk straight from them (no staging copy); median of three passes of K steps (extra.e2e_passes_fps)",
+             "e2e_passes_fps": [round(v, 1) for v in e2e_passes], "e2e_from_pageable_frames_fps": fps_e2e_pageable, "staging_threads": det.staging_threads,
              "k7_bytetrack_us_per_frame_step": round(k7_us_per_frame, 2), "host_threads_per_rank": per_rank}
 
     # ---- the reference's actual loop shape: one frame at a time through process_frame (detect -> track -> crops -> predict)

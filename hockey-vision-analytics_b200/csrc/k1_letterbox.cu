@@ -102,6 +102,10 @@ __device__ __forceinline__ void stg_f32(float* base, uint32_t byte_off, float v)
     *p = v;
 }
 
+__device__ __forceinline__ void sts128(uint32_t shared_byte_addr, const uint4& v) {
+    asm volatile("st.shared.v4.u32 [%0], {%1, %2, %3, %4};" :: "r"(shared_byte_addr), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
+}
+
 __device__ __forceinline__ uint32_t lds32(uint32_t shared_byte_addr) {
     uint32_t v;
     asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(shared_byte_addr));
@@ -143,33 +147,50 @@ __device__ __forceinline__ void lb_prologue(const uint8_t* __restrict__ frames, 
         const int n_groups = bd.n_groups, n_rows = bd.n_rows, row_px = bd.row_px;
         const bool vec_ok = (bd.flags & 2) != 0;
         if ((bd.flags & 4) && frames_aligned16) {
-            // 16-pixel groups: three 128-bit loads -> four 128-bit shared stores; up to 3 items per thread in flight
+            // 16-pixel groups: three 128-bit loads -> four 128-bit shared stores; up to 3 items per thread in flight.
+            // Index arithmetic is kept off the critical instruction count (ncu r02zd: the kernel issues 80 instructions
+            // per output pixel at 72 % of the issue slots, 18 of them in this phase): (row, group) of a thread's first
+            // item comes from one reciprocal multiply, the next two items advance it by a constant step; the shared
+            // address of an item and its bank-swizzle phase travel from the load loop to the store loop packed in
+            // ONE register (the compiler otherwise re-derived both from the item index, ~30 instructions per item).
             const int n16 = n_groups >> 2, n_items16 = n_rows * n16;
             const float inv16 = 1.0f / (float)n16;
+            const uint32_t spix_sa = (uint32_t)__cvta_generic_to_shared(spix);       // 16-byte aligned: low four bits free
+            const uint32_t srow_bytes = 4u * (uint32_t)smem_row_words;               // multiple of 64
+            int dr = (int)((float)NT * inv16);                                       // NT items further = dr rows + dg groups
+            int dg = NT - dr * n16;
+            if (dg < 0) { dr--; dg += n16; }
+            if (dg >= n16) { dr++; dg -= n16; }
             for (int it0 = threadIdx.x; it0 < n_items16; it0 += 3 * NT) {
                 uint4 q[3][3];
-                int soff[3], fsw[3];
+                uint32_t desc[3];                      // shared byte address of the item's 16-word group | swizzle phase (2 bits)
                 bool live[3];
+                int r = (int)((float)it0 * inv16);
+                int g = it0 - r * n16;
+                if (g < 0) { r--; g += n16; }
+                if (g >= n16) { r++; g -= n16; }
 #pragma unroll
                 for (int k = 0; k < 3; k++) {
-                    const int it = it0 + k * NT;
-                    live[k] = it < n_items16;
-                    int r = (int)((float)it * inv16);
-                    int g = it - r * n16;
-                    if (g < 0) { r--; g += n16; }
-                    if (g >= n16) { r++; g -= n16; }
-                    soff[k] = r * smem_row_words + 16 * g;
-                    fsw[k] = (g >> 1) & 3;             // bank swizzle of the 16-byte chunk inside its 16-word group
+                    // (r, g) and the descriptor are made opaque to the optimiser: left alone it re-associated the three
+                    // items' index arithmetic into ~75 instructions between the load groups and re-derived it for the stores
+                    asm volatile("" : "+r"(r), "+r"(g));
+                    live[k] = it0 + k * NT < n_items16;
+                    // bank swizzle of the 16-byte chunks inside the 16-word group: chunk ^= (g >> 1) & 3
+                    desc[k] = (spix_sa + (uint32_t)r * srow_bytes + 64u * (uint32_t)g) | (((uint32_t)g >> 1) & 3u);
+                    asm volatile("" : "+r"(desc[k]));
                     if (live[k]) {
-                        const uint4* p128 = reinterpret_cast<const uint4*>(src + r * pitch + g * 48);
+                        const uint4* p128 = reinterpret_cast<const uint4*>(src + (r * pitch + g * 48));
                         q[k][0] = __ldg(p128); q[k][1] = __ldg(p128 + 1); q[k][2] = __ldg(p128 + 2);
                     }
+                    g += dg; r += dr;
+                    if (g >= n16) { g -= n16; r++; }
                 }
 #pragma unroll
                 for (int k = 0; k < 3; k++) {
                     if (!live[k]) continue;
                     const uint32_t w[12] = {q[k][0].x, q[k][0].y, q[k][0].z, q[k][0].w, q[k][1].x, q[k][1].y, q[k][1].z, q[k][1].w,
                                             q[k][2].x, q[k][2].y, q[k][2].z, q[k][2].w};
+                    const uint32_t sa = desc[k] & ~3u, x = (desc[k] & 3u) << 4;
 #pragma unroll
                     for (int t = 0; t < 4; t++) {
                         const uint32_t a = w[3 * t], b = w[3 * t + 1], c = w[3 * t + 2];
@@ -181,7 +202,7 @@ __device__ __forceinline__ void lb_prologue(const uint8_t* __restrict__ frames, 
                         o.y = __byte_perm(a, b, 0x0543) & 0x00ffffffu;
                         o.z = __byte_perm(b, c, 0x0432) & 0x00ffffffu;
                         o.w = c >> 8;
-                        *reinterpret_cast<uint4*>(spix + soff[k] + 4 * (t ^ fsw[k])) = o;
+                        sts128(sa + (x ^ (16u * t)), o);
                     }
                 }
             }
@@ -264,8 +285,8 @@ letterbox_kernel(const uint8_t* __restrict__ frames, int64_t frame_bytes, int32_
     extern __shared__ __align__(16) uint32_t spix[];      // [rows][smem_row_words] pixel words
     __shared__ YCoef s_y[kTH];                            // vertical coefficients of the block's rows (smem-row relative)
 
-    const int frame = blockIdx.x / blocks_per_frame;
-    const LbBlock bd = blk2job[blockIdx.x - frame * blocks_per_frame];    // two 128-bit loads: everything staging needs
+    const int frame = blockIdx.y;                                         // grid = (blocks of a frame, frames): no division
+    const LbBlock bd = blk2job[blockIdx.x];                               // two 128-bit loads: everything staging needs
     const uint32_t packed = bd.packed;
     const LbJob& job = jobs[packed >> 24];
     const int oy0 = ((packed >> 12) & 0xfff) * kTH;
@@ -737,7 +758,8 @@ static int lb_run(hvb_lb_plan* p, const uint8_t* frames_dev, float* out_f32, uin
     HVB_CHECK_CTX(ctx);
     HVB_ARG(frames_dev && (out_f32 || out_u8), "null buffer");
     HVB_ARG(((uintptr_t)frames_dev & 3) == 0, "frames_dev must be 4-byte aligned");
-    const int grid = p->blocks_per_frame * p->n_frames;
+    HVB_ARG(p->n_frames <= 65535, "more than 65535 frames per launch");
+    const dim3 grid((unsigned)p->blocks_per_frame, (unsigned)p->n_frames);
     const int64_t frame_bytes = (int64_t)p->frame_h * p->frame_w * 3;
     const int al16 = (((uintptr_t)frames_dev & 15) == 0) ? 1 : 0;
     // 64 registers / eight 128-thread CTAs per SM for every float32 plan.  (With 256-thread blocks the copy-dominated slice
