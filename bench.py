@@ -595,11 +595,11 @@ def run_hvb(args, rank, world):
 
     k1_roof = {"kernel": "letterbox_kernel<false> (K1a, 1080p->736x1280, %d frames/launch)" % F, "bound": "hbm",
                "achieved": k1_bytes / (k1_ms / 1e3) / 1e9, "peak": peak, "peak_source": peak_src, "unit": "GB/s",
-               "frac": k1_bytes / (k1_ms / 1e3) / 1e9 / peak, "traffic": ncu_traffic(["K1a_1080p_x%d_%s" % (F, r) for r in ("r02y", "r02f")]),
+               "frac": k1_bytes / (k1_ms / 1e3) / 1e9 / peak, "traffic": ncu_traffic(["K1a_1080p_x%d_%s" % (F, r) for r in ("r02zf", "r02f")]),
                "algorithmic_bytes_per_launch": int(k1_bytes), "avg_launch_ms": k1_ms}
     if k5 is not None:
         n5 = k5["launches_per_step"]
-        t5 = ncu_traffic(["K5_bias_act_step_x%d_%s" % (F, r) for r in ("r02y", "r02f")], launches=n5)   # summed over the launches of one step
+        t5 = ncu_traffic(["K5_bias_act_step_x%d_%s" % (F, r) for r in ("r02zf", "r02f")], launches=n5)   # summed over the launches of one step
         roofline = {"kernel": "bias_act_kernel (K5 conv epilogue: bias + SiLU + residual -> dense / concat-slice destinations), "
                               "%d launches per step of %d frames" % (n5, F),
                     "bound": "hbm", "achieved": k5["achieved"], "peak": peak, "peak_source": peak_src, "unit": "GB/s",
@@ -754,7 +754,7 @@ def bench_4k(args, rank, world, dev, barrier, max_over_ranks, peak, extra, path)
                         % (F4, F4 * int(plan4.tiles_per_frame)),
             "kernel": "letterbox_kernel<true> (K1b slice letterbox, exact 5-shape-class mode)", "bound": "hbm",
             "achieved": k1b_bytes / (k1b_ms / 1e3) / 1e9, "peak": peak, "unit": "GB/s", "frac": k1b_bytes / (k1b_ms / 1e3) / 1e9 / peak,
-            "algorithmic_bytes_per_launch": int(k1b_bytes), "avg_launch_ms": k1b_ms, "traffic": ncu_traffic(["K1b_4k_x%d_r02y" % F4, "K1b_4k_x%d" % F4]),
+            "algorithmic_bytes_per_launch": int(k1b_bytes), "avg_launch_ms": k1b_ms, "traffic": ncu_traffic(["K1b_4k_x%d_r02zf" % F4, "K1b_4k_x%d" % F4]),
             "frames_per_sec": world * F4 * k4 / (ms4 / 1e3), "e2e_frames_per_sec": world * F4 * k4 / (ms4_e2e / 1e3),
             "stage_ms_per_chunk": {k: round(v, 4) for k, v in stage4.items()},
             "k2a": {"launches_per_chunk": len(plan4.classes), "tiles": tiles, "candidates_per_frame": merged_per_frame,
