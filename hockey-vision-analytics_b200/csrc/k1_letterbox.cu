@@ -656,8 +656,8 @@ int hvb_lb_plan_create(hvb_ctx* ctx, int n_frames, int frame_h, int frame_w, int
         hvb_set_error("letterbox block needs %d bytes of shared memory (down-scale factor too large)", p->smem_bytes);
         return HVB_ERR_CAPACITY;
     }
-    if ((int64_t)p->blocks_per_frame * n_frames > 0x7fffffffLL) {
-        delete p; hvb_set_error("grid too large"); return HVB_ERR_CAPACITY;
+    if (n_frames > 65535) {           // the launch grid is (blocks of a frame, frames): gridDim.y
+        delete p; hvb_set_error("more than 65535 frames per letterbox plan: split the chunk"); return HVB_ERR_CAPACITY;
     }
 
     // ---- host-visible tile list (frame-major) for the decode stage

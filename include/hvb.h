@@ -131,7 +131,8 @@ HVB_API int hvb_lb_plan_num_tiles(const hvb_lb_plan* plan, int* out_n);         
 HVB_API int hvb_lb_plan_get_tiles(const hvb_lb_plan* plan, hvb_lb_tile* out_tiles_host, int capacity);
 HVB_API int hvb_lb_plan_out_floats(const hvb_lb_plan* plan, int64_t* out_floats);    /* size of the output buffer */
 HVB_API int hvb_lb_plan_bytes(const hvb_lb_plan* plan, int64_t* out_read_bytes, int64_t* out_write_bytes); /* algorithmic */
-/* frames_dev: uint8[n_frames, frame_h, frame_w, 3] BGR, dense.  out_dev: float32[out_floats]. */
+/* frames_dev: uint8[n_frames, frame_h, frame_w, 3] BGR, dense.  out_dev: float32[out_floats].
+ * One launch per call, grid = (blocks of a frame, n_frames): a plan holds at most 65535 frames (HVB_ERR_CAPACITY beyond). */
 HVB_API int hvb_lb_plan_run(hvb_lb_plan* plan, const uint8_t* frames_dev, float* out_dev);
 /* Test hook: the uint8 stage only (resize + 114 padding, still BGR/HWC), same batch layout in bytes. */
 HVB_API int hvb_lb_plan_run_u8(hvb_lb_plan* plan, const uint8_t* frames_dev, uint8_t* out_dev);
